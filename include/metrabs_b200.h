@@ -1,0 +1,168 @@
+/*
+ * metrabs_b200.h - C ABI of libmetrabs_b200.so: the B200 (sm_100a) implementation of the MeTRAbs per-crop
+ * inference hot path   crops -> CNN backbone -> 1x1-conv head -> 2D + volumetric soft-argmax -> metric scaling
+ * -> reconstruct_absolute -> joints [B,J,3].
+ *
+ * The reference (isarandi/metrabs) is pure Python and has no FFI; its boundary for this path is the nn.Module
+ * contract consumed at metrabs_pytorch/multiperson/multiperson_model.py:240-242.  Each entry point below names
+ * the reference function it replaces (file:line relative to /root/reference/metrabs_pytorch/).  INTEGRATION.md
+ * shows the ctypes binding a maintainer would add on the reference side.
+ *
+ * Conventions: plain C, raw pointers + sizes, no torch types.  Unless a function says "host", pointers are
+ * DEVICE pointers on the handle's device and work is enqueued on `stream` (a cudaStream_t passed as void*;
+ * NULL = legacy default stream) without synchronising the host and without allocating: the caller owns inputs,
+ * outputs and the workspace; the library owns only its weight arena.  Every function returns 0 (MTB_OK) or a
+ * negative mtb_status; mtb_last_error() gives the message of the last failure on that handle (or the global
+ * one when the handle is NULL).  A handle is bound to one device and is not re-entrant; distinct handles are
+ * independent (one process per GPU drives one handle).
+ */
+#ifndef METRABS_B200_H_
+#define METRABS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTB_ABI_VERSION 1
+
+typedef enum {
+  MTB_OK = 0,
+  MTB_ERR_INVALID_ARG = -1,
+  MTB_ERR_CUDA = -2,
+  MTB_ERR_NOT_FINALIZED = -3,
+  MTB_ERR_MISSING_WEIGHT = -4,
+  MTB_ERR_WORKSPACE = -5,
+  MTB_ERR_UNSUPPORTED = -6,
+  MTB_ERR_NCCL = -7
+} mtb_status;
+
+typedef enum { MTB_DTYPE_F32 = 0, MTB_DTYPE_BF16 = 1, MTB_DTYPE_F16 = 2, MTB_DTYPE_I64 = 3 } mtb_dtype;
+
+/* Backbone families of BASELINE.json's configs.  EFFNET covers EfficientNetV2-S/M/L and any table in the same
+ * block grammar (backbones/efficientnet.py:379-433); RESNET50 / MOBILENETV3_SMALL follow the TF-only
+ * metrabs_tf/backbones/{resnet,mobilenet_v3}.py. */
+typedef enum { MTB_ARCH_EFFNET = 0, MTB_ARCH_RESNET50 = 1, MTB_ARCH_MOBILENETV3_SMALL = 2,
+               MTB_ARCH_HEAD_ONLY = 3 } mtb_arch;
+
+/* Arithmetic of the conv/GEMM kernels.  FP32: CUDA-core fp32 FMA everywhere (the 1e-3 parity mode).
+ * BF16_TC: bf16 operands on tcgen05 tensor cores with fp32 accumulation in TMEM, bf16 activations in HBM
+ * (the throughput mode; the reference itself deploys under fp16 autocast, multiperson_model.py:241). */
+typedef enum { MTB_PRECISION_FP32 = 0, MTB_PRECISION_BF16_TC = 1 } mtb_precision;
+
+/* Layout of a logits tensor handed to the standalone soft-argmax. */
+typedef enum {
+  MTB_LAYOUT_BDJHW = 0, /* reference layout after rearrange 'b (d j) h w -> b d j h w' (models/metrabs.py:79) */
+  MTB_LAYOUT_BHWN = 1   /* library-internal NHWC, channel n = J + d*J + j (2D logits in n < J) */
+} mtb_layout;
+
+#define MTB_MAX_STAGES 16
+
+/* One row of EfficientNet's inverted_residual_setting (backbones/efficientnet.py:47-107). */
+typedef struct {
+  int32_t block;       /* 0 = FusedMBConv (:176-234), 1 = MBConv (:110-173) */
+  int32_t expand;      /* expand_ratio */
+  int32_t kernel;      /* 3 */
+  int32_t stride;      /* stride of the first block of the stage */
+  int32_t cin, cout;
+  int32_t layers;
+  int32_t bottomright; /* bottomright_stride: pad (pb-1, pe+1) on the first block (:140-141, :195-196) */
+} mtb_stage;
+
+/* Frozen copy of the get_config() keys the path reads (util.py:41-57; config/config_l.yaml:1-21). */
+typedef struct {
+  int32_t abi_version;                /* MTB_ABI_VERSION */
+  int32_t arch;                       /* mtb_arch */
+  int32_t precision;                  /* mtb_precision */
+  int32_t device;                     /* CUDA device ordinal */
+  int32_t proc_side;                  /* S */
+  int32_t stride_train, stride_test;
+  int32_t centered_stride;
+  int32_t legacy_centered_stride_bug; /* models/util.py:17-18 */
+  int32_t depth;                      /* D */
+  int32_t n_joints;                   /* J (n_raw_points) */
+  int32_t feature_channels;           /* C: channels entering the head (needed for MTB_ARCH_HEAD_ONLY) */
+  float box_size_mm;
+  float mix_3d_inside_fov;            /* < 0 means None (ptu3d.py:28) */
+  int32_t weak_perspective;           /* must be 0: the reference's weak-perspective solve crashes (ptu.py:30) */
+  int32_t n_stages;                   /* EFFNET only */
+  int32_t last_channel;               /* EFFNET only: 1280 */
+  mtb_stage stages[MTB_MAX_STAGES];
+} mtb_config;
+
+typedef struct mtb_handle mtb_handle;
+
+/* Metrabs.__init__ (models/metrabs.py:12-45) + backbone construction (backbones/efficientnet.py:237-357). */
+int mtb_create(const mtb_config* cfg, mtb_handle** out);
+int mtb_destroy(mtb_handle* h);
+const char* mtb_last_error(const mtb_handle* h);
+const char* mtb_version(void);
+
+/* load_state_dict (scripts/demo_image.py:73): one call per entry, `name` in the reference key schema
+ * ("backbone.1.<stage>.<block>.block.<i>.0.weight", "heatmap_heads.conv_final.bias", ...).  `data` is a HOST
+ * pointer to a contiguous tensor in torch layout; it is copied.  Unknown names are ignored
+ * (num_batches_tracked).  mtb_finalize_weights folds BN, repacks to NHWC / K-major, uploads, and fails with
+ * MTB_ERR_MISSING_WEIGHT naming the first absent key. */
+int mtb_load_weight(mtb_handle* h, const char* name, const void* data, int dtype, const int64_t* shape, int ndim);
+int mtb_finalize_weights(mtb_handle* h);
+
+size_t mtb_workspace_bytes(const mtb_handle* h, int batch);
+/* Elements per crop of the feature map [H*W*C] and its spatial side, after finalize. */
+int mtb_feature_shape(const mtb_handle* h, int* hw_side, int* channels);
+
+/* self.backbone(image) (models/metrabs.py:50): crops fp32 NCHW [B,3,S,S] in [0,1] -> features NHWC
+ * [B,S/s,S/s,C] (fp32, or bf16 in BF16_TC mode). */
+int mtb_backbone_forward(mtb_handle* h, const float* crops, int batch, void* features, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* MetrabsHeads.forward (models/metrabs.py:75-85) incl. heatmap_to_image / heatmap_to_metric
+ * (models/util.py:6-33): features NHWC -> coords2d [B,J,2] px, coords3d_rel [B,J,3] mm (fp32). */
+int mtb_head_decode(mtb_handle* h, const void* features, int batch, float* coords2d, float* coords3d_rel,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ptu.soft_argmax (ptu.py:54-75), standalone over materialised logits (config c5 / roofline sweep).
+ * BDJHW: logits [B,D,J,H,W] -> out [B,J,3] = (x,y,z) in [0,1];  with depth == 0: logits [B,J,H,W] -> out
+ * [B,J,2].  BHWN: logits [B,H,W,J*(1+D)] -> out2d [B,J,2] and out3d [B,J,3] (either may be NULL). */
+int mtb_softargmax(const void* logits, int dtype, int layout, int batch, int n_joints, int depth, int height,
+                   int width, float* out2d, float* out3d, void* stream);
+
+/* ptu3d.reconstruct_absolute (ptu3d.py:9-33) with reconstruct_ref_fullpersp (:56-105), is_within_fov
+ * (:113-121), back_project (:108-110).  scratch: >= mtb_reconstruct_scratch_bytes(batch) bytes. */
+size_t mtb_reconstruct_scratch_bytes(int batch);
+int mtb_reconstruct_absolute(mtb_handle* h, const float* coords2d, const float* coords3d_rel,
+                             const float* intrinsics, int batch, float* coords3d_abs, void* scratch,
+                             void* stream);
+
+/* Metrabs.forward (models/metrabs.py:47-64): crops [B,3,S,S] fp32 + intrinsics [B,3,3] fp32 -> [B,J,3] fp32. */
+int mtb_forward(mtb_handle* h, const float* crops, const float* intrinsics, int batch, float* coords3d_abs,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call for HOST buffers (the reference-facing end-to-end path): pinned or pageable host crops/intrinsics
+ * in, host joints out; H2D/D2H copies and the forward are enqueued on `stream`, then the stream is
+ * synchronised.  The library keeps a device staging area sized by the largest batch seen. */
+int mtb_forward_host(mtb_handle* h, const float* host_crops, const float* host_intrinsics, int batch,
+                     float* host_coords3d_abs, void* stream);
+
+/* Multi-GPU: crops shard across ranks; one all-gather of the decoded joints over NVLink.
+ * mtb_comm_* wrap a NCCL communicator owned by the handle (libnccl is dlopen'ed). */
+int mtb_comm_unique_id(void* id128 /* host, 128 bytes */);
+int mtb_comm_init(mtb_handle* h, const void* id128, int rank, int world_size);
+int mtb_allgather_joints(mtb_handle* h, const float* local, int floats_per_rank, float* all, void* stream);
+
+/* Introspection for tests / profiling. */
+int mtb_num_ops(const mtb_handle* h);
+const char* mtb_op_name(const mtb_handle* h, int op);
+/* Runs the first `n_ops` backbone ops and copies that op's NHWC output (as fp32) to `out` (device). */
+int mtb_debug_run_ops(mtb_handle* h, const float* crops, int batch, int n_ops, float* out, size_t out_floats,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int mtb_op_output_shape(const mtb_handle* h, int op, int* height, int* width, int* channels);
+/* Number of kernels the last mtb_forward / mtb_backbone_forward / ... call on this handle launched. */
+int64_t mtb_last_launch_count(const mtb_handle* h);
+double mtb_backbone_flops_per_crop(const mtb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METRABS_B200_H_ */

@@ -1,0 +1,358 @@
+// CUDA-core (fp32 FMA) convolution kernels over NHWC activations: the fp32 parity mode of the backbone
+// (MTB_PRECISION_FP32) and the fallback for layers that are not GEMM-shaped (stem with Cin=3, depthwise).
+// Reference semantics: explicit zero pad then VALID conv (backbones/efficientnet.py:1127-1161), BN folded into
+// weight+bias at load time, activation and residual add fused in the epilogue.
+#pragma once
+#include "common.cuh"
+
+namespace mtb {
+
+struct ConvParams {
+  const void* in;        // [B,Hin,Win,Cin]
+  const void* res;       // optional residual [B,Hout,Wout,Cout]
+  void* out;             // [B,Hout,Wout,Cout]
+  const float* w;        // [R*S*Cin][Cout]  (k = (r*S+s)*Cin + c)
+  const float* bias;     // [Cout]
+  const float* a_scale;  // optional per-(b,cin) multiplier of the input (squeeze-excitation), [B][Cin]
+  int B, Hin, Win, Cin, Hout, Wout, Cout, R, S, stride, dil, pad_t, pad_l, act;
+};
+
+// ----------------------------------------------------------------------------------------------------------
+// implicit-GEMM conv: M = B*Hout*Wout pixels, N = Cout, K = R*S*Cin.  Requires Cin % 4 == 0, Cout % 4 == 0.
+// ----------------------------------------------------------------------------------------------------------
+template <int BM, int BN, int TM, int TN, typename TIn, typename TOut>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+conv_igemm_kernel(ConvParams p) {
+  constexpr int BK = 16;
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int A_LD = (BM * BK / 4) / NT;  // float4 loads of A per thread per tile
+  constexpr int B_LD = (BK * BN / 4) / NT;
+  static_assert(A_LD >= 1 && B_LD >= 1, "tile too small for the thread count");
+  constexpr int GM = TM / 4, GN = TN / 4;            // 4-wide groups per thread
+  constexpr int GSM = (BM / TM) * 4, GSN = (BN / TN) * 4;  // group strides
+
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int M = p.B * p.Hout * p.Wout;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const TIn* __restrict__ in = reinterpret_cast<const TIn*>(p.in);
+
+  // per-thread A rows
+  int a_row[A_LD], a_kq[A_LD], a_ih0[A_LD], a_iw0[A_LD], a_b[A_LD];
+  bool a_ok[A_LD];
+#pragma unroll
+  for (int i = 0; i < A_LD; ++i) {
+    int idx = tid + i * NT;
+    a_row[i] = idx >> 2;
+    a_kq[i] = idx & 3;
+    int m = m0 + a_row[i];
+    a_ok[i] = m < M;
+    int mm = a_ok[i] ? m : 0;
+    int b = mm / (p.Hout * p.Wout);
+    int r = mm - b * p.Hout * p.Wout;
+    int oh = r / p.Wout, ow = r - oh * p.Wout;
+    a_b[i] = b;
+    a_ih0[i] = oh * p.stride - p.pad_t;
+    a_iw0[i] = ow * p.stride - p.pad_l;
+  }
+  int b_krow[B_LD], b_n[B_LD];
+#pragma unroll
+  for (int i = 0; i < B_LD; ++i) {
+    int idx = tid + i * NT;
+    b_krow[i] = idx / (BN / 4);
+    b_n[i] = (idx % (BN / 4)) * 4;
+  }
+
+  const int cchunks = (p.Cin + BK - 1) / BK;
+  const int T = p.R * p.S * cchunks;
+
+  float4 ra[A_LD], rb[B_LD];
+  auto load_tile = [&](int t) {
+    int tap = t / cchunks;
+    int c0 = (t - tap * cchunks) * BK;
+    int r = tap / p.S, s = tap - r * p.S;
+#pragma unroll
+    for (int i = 0; i < A_LD; ++i) {
+      int ih = a_ih0[i] + r * p.dil, iw = a_iw0[i] + s * p.dil;
+      int c = c0 + a_kq[i] * 4;
+      bool ok = a_ok[i] && ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win && c < p.Cin;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) {
+        v = load4<TIn>(in + ((size_t)(a_b[i] * p.Hin + ih) * p.Win + iw) * p.Cin + c);
+        if (p.a_scale) {
+          float4 sc = *reinterpret_cast<const float4*>(p.a_scale + (size_t)a_b[i] * p.Cin + c);
+          v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+        }
+      }
+      ra[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < B_LD; ++i) {
+      int c = c0 + b_krow[i];
+      int n = n0 + b_n[i];
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < p.Cin && n < p.Cout) v = *reinterpret_cast<const float4*>(p.w + (size_t)(tap * p.Cin + c) * p.Cout + n);
+      rb[i] = v;
+    }
+  };
+  auto store_tile = [&]() {
+#pragma unroll
+    for (int i = 0; i < A_LD; ++i) {
+      int k = a_kq[i] * 4;
+      As[k + 0][a_row[i]] = ra[i].x;
+      As[k + 1][a_row[i]] = ra[i].y;
+      As[k + 2][a_row[i]] = ra[i].z;
+      As[k + 3][a_row[i]] = ra[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < B_LD; ++i) *reinterpret_cast<float4*>(&Bs[b_krow[i]][b_n[i]]) = rb[i];
+  };
+
+  const int ty = tid / (BN / TN), tx = tid % (BN / TN);
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  load_tile(0);
+  store_tile();
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    if (t + 1 < T) load_tile(t + 1);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int g = 0; g < GM; ++g) {
+        float4 v = *reinterpret_cast<const float4*>(&As[kk][ty * 4 + g * GSM]);
+        a[g * 4 + 0] = v.x; a[g * 4 + 1] = v.y; a[g * 4 + 2] = v.z; a[g * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int g = 0; g < GN; ++g) {
+        float4 v = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4 + g * GSN]);
+        b[g * 4 + 0] = v.x; b[g * 4 + 1] = v.y; b[g * 4 + 2] = v.z; b[g * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+    if (t + 1 < T) {
+      store_tile();
+      __syncthreads();
+    }
+  }
+
+  // epilogue: bias + activation (+ residual)
+  TOut* __restrict__ out = reinterpret_cast<TOut*>(p.out);
+  const TOut* __restrict__ res = reinterpret_cast<const TOut*>(p.res);
+#pragma unroll
+  for (int gi = 0; gi < GM; ++gi)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int m = m0 + ty * 4 + gi * GSM + i;
+      if (m >= M) continue;
+#pragma unroll
+      for (int gj = 0; gj < GN; ++gj) {
+        int n = n0 + tx * 4 + gj * GSN;
+        if (n >= p.Cout) continue;
+        float4 bv = *reinterpret_cast<const float4*>(p.bias + n);
+        float4 v;
+        v.x = apply_act(acc[gi * 4 + i][gj * 4 + 0] + bv.x, p.act);
+        v.y = apply_act(acc[gi * 4 + i][gj * 4 + 1] + bv.y, p.act);
+        v.z = apply_act(acc[gi * 4 + i][gj * 4 + 2] + bv.z, p.act);
+        v.w = apply_act(acc[gi * 4 + i][gj * 4 + 3] + bv.w, p.act);
+        size_t o = (size_t)m * p.Cout + n;
+        if (res) {
+          float4 rv = load4<TOut>(res + o);
+          v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+        }
+        store4<TOut>(out + o, v);
+      }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// depthwise conv, NHWC, one thread per (pixel, 4 channels).  w: [R*S][C], C % 4 == 0.
+// ----------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv_kernel(ConvParams p) {
+  const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
+  T* __restrict__ out = reinterpret_cast<T*>(p.out);
+  const int C4 = p.Cout >> 2;
+  const size_t total = (size_t)p.B * p.Hout * p.Wout * C4;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(idx % C4) * 4;
+    size_t pix = idx / C4;
+    int ow = (int)(pix % p.Wout);
+    size_t t = pix / p.Wout;
+    int oh = (int)(t % p.Hout);
+    int b = (int)(t / p.Hout);
+    float4 acc = *reinterpret_cast<const float4*>(p.bias + c);
+    for (int r = 0; r < p.R; ++r) {
+      int ih = oh * p.stride - p.pad_t + r * p.dil;
+      if (ih < 0 || ih >= p.Hin) continue;
+      for (int s = 0; s < p.S; ++s) {
+        int iw = ow * p.stride - p.pad_l + s * p.dil;
+        if (iw < 0 || iw >= p.Win) continue;
+        float4 v = load4<T>(in + ((size_t)(b * p.Hin + ih) * p.Win + iw) * p.Cin + c);
+        float4 wv = *reinterpret_cast<const float4*>(p.w + (size_t)(r * p.S + s) * p.Cout + c);
+        acc.x = fmaf(v.x, wv.x, acc.x);
+        acc.y = fmaf(v.y, wv.y, acc.y);
+        acc.z = fmaf(v.z, wv.z, acc.z);
+        acc.w = fmaf(v.w, wv.w, acc.w);
+      }
+    }
+    acc.x = apply_act(acc.x, p.act);
+    acc.y = apply_act(acc.y, p.act);
+    acc.z = apply_act(acc.z, p.act);
+    acc.w = apply_act(acc.w, p.act);
+    store4<T>(out + pix * p.Cout + c, acc);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// stem: direct conv for tiny Cin (3) reading the caller's NCHW fp32 crops, with the per-channel input affine
+// (PreprocLayer x*2-1, backbones/efficientnet.py:1185) applied to in-bounds pixels only (pad happens AFTER
+// preprocessing in the reference), writing NHWC.  w: [R*S*Cin][Cout], one thread per (pixel, 4 out channels).
+// ----------------------------------------------------------------------------------------------------------
+struct StemParams {
+  const float* in;  // [B,Cin,Hin,Win]
+  void* out;        // [B,Hout,Wout,Cout]
+  const float* w;
+  const float* bias;
+  float pre_scale[4], pre_shift[4];
+  int B, Hin, Win, Cin, Hout, Wout, Cout, R, S, stride, pad_t, pad_l, act;
+};
+
+template <typename TOut>
+__global__ void __launch_bounds__(256) stem_conv_kernel(StemParams p) {
+  extern __shared__ float sw[];  // weights [R*S*Cin][Cout] + bias [Cout]
+  const int K = p.R * p.S * p.Cin;
+  for (int i = threadIdx.x; i < K * p.Cout; i += blockDim.x) sw[i] = p.w[i];
+  float* sb = sw + K * p.Cout;
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sb[i] = p.bias[i];
+  __syncthreads();
+  TOut* __restrict__ out = reinterpret_cast<TOut*>(p.out);
+  const int C4 = p.Cout >> 2;
+  const size_t total = (size_t)p.B * p.Hout * p.Wout * C4;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(idx % C4) * 4;
+    size_t pix = idx / C4;
+    int ow = (int)(pix % p.Wout);
+    size_t t = pix / p.Wout;
+    int oh = (int)(t % p.Hout);
+    int b = (int)(t / p.Hout);
+    float4 acc = *reinterpret_cast<const float4*>(sb + c);
+    for (int r = 0; r < p.R; ++r) {
+      int ih = oh * p.stride - p.pad_t + r;
+      if (ih < 0 || ih >= p.Hin) continue;
+      for (int s = 0; s < p.S; ++s) {
+        int iw = ow * p.stride - p.pad_l + s;
+        if (iw < 0 || iw >= p.Win) continue;
+        for (int ci = 0; ci < p.Cin; ++ci) {
+          float v = __ldg(p.in + ((size_t)(b * p.Cin + ci) * p.Hin + ih) * p.Win + iw) * p.pre_scale[ci] + p.pre_shift[ci];
+          float4 wv = *reinterpret_cast<const float4*>(sw + (size_t)((r * p.S + s) * p.Cin + ci) * p.Cout + c);
+          acc.x = fmaf(v, wv.x, acc.x);
+          acc.y = fmaf(v, wv.y, acc.y);
+          acc.z = fmaf(v, wv.z, acc.z);
+          acc.w = fmaf(v, wv.w, acc.w);
+        }
+      }
+    }
+    acc.x = apply_act(acc.x, p.act);
+    acc.y = apply_act(acc.y, p.act);
+    acc.z = apply_act(acc.z, p.act);
+    acc.w = apply_act(acc.w, p.act);
+    store4<TOut>(out + pix * p.Cout + c, acc);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// global average pool over the spatial axes (squeeze of squeeze-excitation): in [B,P,C] -> mean [B,C] fp32.
+// grid (ceil(C/128), B), block (32, 8).
+// ----------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) pool_mean_kernel(const T* __restrict__ in, float* __restrict__ out, int P, int C) {
+  __shared__ float4 red[8][32];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int b = blockIdx.y;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    const T* base = in + (size_t)b * P * C + c;
+    for (int px = threadIdx.y; px < P; px += 8) {
+      float4 v = load4<T>(base + (size_t)px * C);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float4 s = red[0][threadIdx.x];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      float4 v = red[i][threadIdx.x];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float inv = 1.0f / (float)P;
+    *reinterpret_cast<float4*>(out + (size_t)b * C + c) = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+  }
+}
+
+// max pool (ResNet stem, metrabs_tf/backbones/resnet.py:187-193), NHWC, pad value = -inf.
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_kernel(ConvParams p) {
+  const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
+  T* __restrict__ out = reinterpret_cast<T*>(p.out);
+  const int C4 = p.Cout >> 2;
+  const size_t total = (size_t)p.B * p.Hout * p.Wout * C4;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(idx % C4) * 4;
+    size_t pix = idx / C4;
+    int ow = (int)(pix % p.Wout);
+    size_t t = pix / p.Wout;
+    int oh = (int)(t % p.Hout);
+    int b = (int)(t / p.Hout);
+    float4 acc = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int r = 0; r < p.R; ++r) {
+      int ih = oh * p.stride - p.pad_t + r;
+      if (ih < 0 || ih >= p.Hin) continue;
+      for (int s = 0; s < p.S; ++s) {
+        int iw = ow * p.stride - p.pad_l + s;
+        if (iw < 0 || iw >= p.Win) continue;
+        float4 v = load4<T>(in + ((size_t)(b * p.Hin + ih) * p.Win + iw) * p.Cin + c);
+        acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
+      }
+    }
+    store4<T>(out + pix * p.Cout + c, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- launchers
+template <typename TIn, typename TOut>
+inline cudaError_t launch_conv_igemm(const ConvParams& p, cudaStream_t st) {
+  const int M = p.B * p.Hout * p.Wout;
+  if (p.Cout > 64 && M >= 128 * 148) {
+    dim3 grid((M + 127) / 128, (p.Cout + 127) / 128);
+    conv_igemm_kernel<128, 128, 8, 8, TIn, TOut><<<grid, 256, 0, st>>>(p);
+  } else if (M >= 128 * 148) {
+    dim3 grid((M + 127) / 128, (p.Cout + 63) / 64);
+    conv_igemm_kernel<128, 64, 8, 4, TIn, TOut><<<grid, 256, 0, st>>>(p);
+  } else {
+    dim3 grid((M + 63) / 64, (p.Cout + 63) / 64);
+    conv_igemm_kernel<64, 64, 4, 4, TIn, TOut><<<grid, 256, 0, st>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+inline int grid_for(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  size_t cap = 148 * 16;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+}  // namespace mtb

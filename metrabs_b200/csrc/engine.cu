@@ -1,0 +1,918 @@
+// libmetrabs_b200.so - engine: handle, weight arena (BN folding + repack), op plan, forward executor, C ABI.
+// See include/metrabs_b200.h for the contract and the reference file:line each entry point replaces.
+#include "../../include/metrabs_b200.h"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_simt.cuh"
+#include "decode.cuh"
+#include "tc_gemm.cuh"
+
+using namespace mtb;
+
+namespace {
+
+std::string g_error;
+
+enum OpType { OP_STEM = 0, OP_CONV = 1, OP_DW = 2, OP_POOL = 3, OP_MAXPOOL = 4 };
+enum { BUF_FEATURES = -2, BUF_NONE = -1, BUF_SMALL0 = 4 };  // 0..3 big activation buffers, 4..6 small [B,C]
+constexpr int kNumBig = 4, kNumSmall = 3;
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+struct Op {
+  OpType type;
+  std::string name;     // reference key prefix of the layer
+  std::string wkey;     // conv weight key
+  std::string bnkey;    // BN key prefix ("" = none)
+  std::string biaskey;  // conv bias key ("" = none)
+  int in_buf = 0, out_buf = 0, res_buf = BUF_NONE, scale_buf = BUF_NONE;
+  int Hin = 1, Win = 1, Cin = 0, Hout = 1, Wout = 1, Cout = 0;
+  int R = 1, S = 1, stride = 1, dil = 1, pad_t = 0, pad_l = 0, act = ACT_NONE;
+  bool depthwise = false;
+  bool small_io = false;  // squeeze-excitation FCs on [B,1,1,C] fp32 tensors
+  float bn_eps = 1e-3f;
+  float* d_w = nullptr;     // fp32 [R*S*Cin][Cout]  (dw: [R*S][C])
+  float* d_bias = nullptr;  // fp32 [Cout]
+  TcWeights tc;             // bf16 K-major copy + TMA descriptor state for the tcgen05 path
+  double flops = 0;         // 2*MACs per crop
+};
+
+}  // namespace
+
+struct mtb_handle {
+  mtb_config cfg;
+  std::map<std::string, HostTensor> raw;
+  std::vector<Op> ops;
+  Op head;
+  bool finalized = false;
+  mutable std::string err;
+  std::vector<void*> dev_allocs;
+  // geometry
+  int feat_side = 0, feat_c = 0;
+  size_t big_elems_per_crop = 0;   // capacity of one big buffer, elements per crop
+  int small_c = 0;                 // capacity of one small buffer, floats per crop
+  int64_t launches = 0;
+  double flops_per_crop = 0;
+  // host-path staging
+  void* stage = nullptr;
+  size_t stage_bytes = 0;
+  int stage_batch = 0;
+  // NCCL (dlopen'ed)
+  void* nccl_lib = nullptr;
+  void* nccl_comm = nullptr;
+  int nccl_world = 0;
+};
+
+namespace {
+
+int fail(const mtb_handle* h, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  g_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                               \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+      return fail(h, MTB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline size_t elem_size(const mtb_handle* h) { return h->cfg.precision == MTB_PRECISION_BF16_TC ? 2 : 4; }
+
+// ------------------------------------------------------------------------------------------- plan building
+struct Planner {
+  mtb_handle* h;
+  int H, W, C;       // current activation
+  int cur = BUF_NONE;
+  size_t max_elems = 0;
+  int max_small = 0;
+
+  int pick(std::initializer_list<int> busy) {
+    for (int i = 0; i < kNumBig; ++i)
+      if (std::find(busy.begin(), busy.end(), i) == busy.end()) return i;
+    return 0;
+  }
+  void track(int h_, int w_, int c_) { max_elems = std::max(max_elems, (size_t)h_ * w_ * c_); }
+
+  // conv with explicit begin pad; output size = floor((in + pad_total - eff_k)/stride) + 1
+  Op& conv(const std::string& name, int cout, int k, int stride, int pad_beg, int pad_total, int act, int in_buf,
+           int out_buf, bool depthwise = false, int dil = 1) {
+    Op op;
+    op.type = depthwise ? OP_DW : OP_CONV;
+    op.name = name;
+    op.wkey = name + ".0.weight";
+    op.bnkey = name + ".1";
+    op.Hin = H; op.Win = W; op.Cin = C; op.Cout = cout;
+    op.R = op.S = k; op.stride = stride; op.dil = dil; op.pad_t = op.pad_l = pad_beg; op.act = act;
+    int eff = k + (k - 1) * (dil - 1);
+    op.Hout = (H + pad_total - eff) / stride + 1;
+    op.Wout = (W + pad_total - eff) / stride + 1;
+    op.depthwise = depthwise;
+    op.in_buf = in_buf; op.out_buf = out_buf;
+    op.flops = 2.0 * op.Hout * op.Wout * cout * k * k * (depthwise ? 1 : C);
+    H = op.Hout; W = op.Wout; C = cout;
+    track(H, W, C);
+    h->ops.push_back(op);
+    return h->ops.back();
+  }
+};
+
+void plan_effnet(mtb_handle* h) {
+  // EfficientNet.features (backbones/efficientnet.py:286-324) with PreprocLayer (:1181-1186) folded in the stem
+  const mtb_config& c = h->cfg;
+  Planner P{h, c.proc_side, c.proc_side, 3};
+  const std::string pre = "backbone.1";
+  {
+    Op op;
+    op.type = OP_STEM;
+    op.name = pre + ".0";
+    op.wkey = op.name + ".0.weight";
+    op.bnkey = op.name + ".1";
+    op.Hin = op.Win = c.proc_side; op.Cin = 3; op.Cout = c.stages[0].cin;
+    op.R = op.S = 3; op.stride = 2; op.pad_t = op.pad_l = 1; op.act = ACT_SILU;
+    op.Hout = op.Wout = (c.proc_side + 2 - 3) / 2 + 1;
+    op.in_buf = BUF_NONE; op.out_buf = 0;
+    op.flops = 2.0 * op.Hout * op.Wout * op.Cout * 27;
+    P.H = op.Hout; P.W = op.Wout; P.C = op.Cout; P.cur = 0;
+    P.track(P.H, P.W, P.C);
+    h->ops.push_back(op);
+  }
+  for (int si = 0; si < c.n_stages; ++si) {
+    const mtb_stage& st = c.stages[si];
+    for (int bi = 0; bi < st.layers; ++bi) {
+      const bool first = bi == 0;
+      const int cin = first ? st.cin : st.cout;
+      const int stride = first ? st.stride : 1;
+      const int shift = (first && st.bottomright) ? 1 : 0;
+      const bool residual = stride == 1 && cin == st.cout;
+      const int cexp = cin * st.expand;
+      const int k = st.kernel;
+      const int pad_beg = (k - 1) / 2 - shift, pad_total = k - 1;  // fixed_padding_layer (:1127-1161)
+      char key[64];
+      snprintf(key, sizeof(key), "%s.%d.%d.block", pre.c_str(), si + 1, bi);
+      const std::string kb = key;
+      const int x_in = P.cur;
+      if (st.block == 0) {  // FusedMBConv (:176-234)
+        if (st.expand != 1) {
+          int t1 = P.pick({x_in});
+          P.conv(kb + ".0", cexp, k, stride, pad_beg, pad_total, ACT_SILU, x_in, t1);
+          int t2 = P.pick({x_in, t1});
+          Op& pr = P.conv(kb + ".1", st.cout, 1, 1, 0, 0, ACT_NONE, t1, t2);
+          if (residual) pr.res_buf = x_in;
+          P.cur = t2;
+        } else {
+          int t1 = P.pick({x_in});
+          Op& cv = P.conv(kb + ".0", st.cout, k, stride, pad_beg, pad_total, ACT_SILU, x_in, t1);
+          if (residual) cv.res_buf = x_in;
+          P.cur = t1;
+        }
+      } else {  // MBConv (:110-173)
+        int i = 0;
+        int t1 = x_in;
+        if (st.expand != 1) {
+          t1 = P.pick({x_in});
+          P.conv(kb + "." + std::to_string(i), cexp, 1, 1, 0, 0, ACT_SILU, x_in, t1);
+          ++i;
+        }
+        int t2 = P.pick({x_in, t1});
+        P.conv(kb + "." + std::to_string(i), cexp, k, stride, pad_beg, pad_total, ACT_SILU, t1, t2, true);
+        ++i;
+        // squeeze-excitation: avgpool -> fc1 + SiLU -> fc2 + sigmoid -> scale (folded into the projection's A load)
+        const int csq = std::max(1, cin / 4);
+        const std::string se = kb + "." + std::to_string(i);
+        {
+          Op op;
+          op.type = OP_POOL; op.name = se + ".avgpool";
+          op.Hin = P.H; op.Win = P.W; op.Cin = op.Cout = cexp;
+          op.in_buf = t2; op.out_buf = BUF_SMALL0;
+          h->ops.push_back(op);
+          Op f1;
+          f1.type = OP_CONV; f1.name = se + ".fc1"; f1.wkey = se + ".fc1.weight"; f1.biaskey = se + ".fc1.bias";
+          f1.Cin = cexp; f1.Cout = csq; f1.act = ACT_SILU; f1.small_io = true;
+          f1.in_buf = BUF_SMALL0; f1.out_buf = BUF_SMALL0 + 1;
+          f1.flops = 2.0 * cexp * csq;
+          h->ops.push_back(f1);
+          Op f2;
+          f2.type = OP_CONV; f2.name = se + ".fc2"; f2.wkey = se + ".fc2.weight"; f2.biaskey = se + ".fc2.bias";
+          f2.Cin = csq; f2.Cout = cexp; f2.act = ACT_SIGMOID; f2.small_io = true;
+          f2.in_buf = BUF_SMALL0 + 1; f2.out_buf = BUF_SMALL0 + 2;
+          f2.flops = 2.0 * cexp * csq;
+          h->ops.push_back(f2);
+          P.max_small = std::max(P.max_small, cexp);
+        }
+        ++i;
+        int t3 = P.pick({x_in, t2});
+        Op& pr = P.conv(kb + "." + std::to_string(i), st.cout, 1, 1, 0, 0, ACT_NONE, t2, t3);
+        pr.scale_buf = BUF_SMALL0 + 2;
+        if (residual) pr.res_buf = x_in;
+        P.cur = t3;
+      }
+    }
+  }
+  {
+    char key[64];
+    snprintf(key, sizeof(key), "%s.%d", pre.c_str(), c.n_stages + 1);
+    Op& last = P.conv(key, c.last_channel, 1, 1, 0, 0, ACT_SILU, P.cur, BUF_FEATURES);  // :319-324
+    (void)last;
+  }
+  h->feat_side = P.H;
+  h->feat_c = P.C;
+  h->big_elems_per_crop = P.max_elems;
+  h->small_c = std::max(P.max_small, 4);
+}
+
+int plan(mtb_handle* h) {
+  const mtb_config& c = h->cfg;
+  h->ops.clear();
+  switch (c.arch) {
+    case MTB_ARCH_EFFNET: plan_effnet(h); break;
+    case MTB_ARCH_HEAD_ONLY:
+      h->feat_side = c.proc_side / c.stride_test;
+      h->feat_c = c.feature_channels;
+      h->big_elems_per_crop = 0;
+      h->small_c = 4;
+      break;
+    default: return fail(h, MTB_ERR_UNSUPPORTED, "arch %d is not built yet", c.arch);
+  }
+  h->flops_per_crop = 0;
+  for (auto& op : h->ops) {
+    op.bn_eps = 1e-3f;
+    h->flops_per_crop += op.flops;
+  }
+  // head: MetrabsHeads.conv_final, 1x1 conv with bias (models/metrabs.py:73)
+  Op& hd = h->head;
+  hd = Op();
+  hd.type = OP_CONV;
+  hd.name = "heatmap_heads.conv_final";
+  hd.wkey = hd.name + ".weight";
+  hd.biaskey = hd.name + ".bias";
+  hd.Hin = hd.Win = hd.Hout = hd.Wout = h->feat_side;
+  hd.Cin = h->feat_c;
+  hd.Cout = (c.n_joints * (1 + c.depth) + 3) / 4 * 4;  // channels padded to a multiple of 4 with zero weights (J=122: 1098 -> 1100)
+  hd.act = ACT_NONE;
+  hd.flops = 2.0 * hd.Hout * hd.Wout * hd.Cin * hd.Cout;
+  return MTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+const HostTensor* find(const mtb_handle* h, const std::string& k) {
+  auto it = h->raw.find(k);
+  return it == h->raw.end() ? nullptr : &it->second;
+}
+
+int upload(mtb_handle* h, const void* host, size_t bytes, void** dev) {
+  CUDA_TRY(h, cudaMalloc(dev, bytes));
+  h->dev_allocs.push_back(*dev);
+  CUDA_TRY(h, cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice));
+  return MTB_OK;
+}
+
+int prepare_op_weights(mtb_handle* h, Op& op) {
+  if (op.type == OP_POOL || op.type == OP_MAXPOOL) return MTB_OK;
+  const HostTensor* w = find(h, op.wkey);
+  if (!w) return fail(h, MTB_ERR_MISSING_WEIGHT, "missing weight '%s'", op.wkey.c_str());
+  const int cin_g = op.depthwise ? 1 : op.Cin;
+  const int64_t expect[4] = {op.Cout, cin_g, op.R, op.S};
+  if (w->shape.size() != 4 || !std::equal(expect, expect + 4, w->shape.begin()))
+    return fail(h, MTB_ERR_INVALID_ARG, "weight '%s' has the wrong shape (want [%d,%d,%d,%d])", op.wkey.c_str(),
+                op.Cout, cin_g, op.R, op.S);
+  std::vector<double> scale(op.Cout, 1.0), shift(op.Cout, 0.0);
+  if (!op.biaskey.empty()) {
+    const HostTensor* b = find(h, op.biaskey);
+    if (!b) return fail(h, MTB_ERR_MISSING_WEIGHT, "missing weight '%s'", op.biaskey.c_str());
+    for (int n = 0; n < op.Cout; ++n) shift[n] = b->data[n];
+  }
+  if (!op.bnkey.empty()) {
+    const HostTensor *g = find(h, op.bnkey + ".weight"), *b = find(h, op.bnkey + ".bias"),
+                     *m = find(h, op.bnkey + ".running_mean"), *v = find(h, op.bnkey + ".running_var");
+    if (!g || !b || !m || !v) return fail(h, MTB_ERR_MISSING_WEIGHT, "missing batch-norm tensors '%s.*'", op.bnkey.c_str());
+    for (int n = 0; n < op.Cout; ++n) {
+      double s = (double)g->data[n] / std::sqrt((double)v->data[n] + (double)op.bn_eps);
+      scale[n] = s;
+      shift[n] = (shift[n] - (double)m->data[n]) * s + (double)b->data[n];
+    }
+  }
+  const int K = op.R * op.S * cin_g;
+  std::vector<float> wk((size_t)K * op.Cout), bias(op.Cout);
+  for (int n = 0; n < op.Cout; ++n) {
+    bias[n] = (float)shift[n];
+    for (int c = 0; c < cin_g; ++c)
+      for (int r = 0; r < op.R; ++r)
+        for (int s = 0; s < op.S; ++s) {
+          double v = (double)w->data[(((size_t)n * cin_g + c) * op.R + r) * op.S + s] * scale[n];
+          wk[((size_t)(r * op.S + s) * cin_g + c) * op.Cout + n] = (float)v;
+        }
+  }
+  int rc = upload(h, wk.data(), wk.size() * 4, (void**)&op.d_w);
+  if (rc) return rc;
+  rc = upload(h, bias.data(), bias.size() * 4, (void**)&op.d_bias);
+  if (rc) return rc;
+  if (h->cfg.precision == MTB_PRECISION_BF16_TC && tc_eligible(op.type == OP_CONV, op.depthwise, op.small_io, op.R,
+                                                               op.stride, op.Cin, op.Cout)) {
+    const char* e = tc_prepare_weights(op.tc, wk.data(), bias.data(), K, op.Cout, op.R, op.S, op.Cin, h->dev_allocs);
+    if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 weight prep for '%s': %s", op.name.c_str(), e);
+  }
+  return MTB_OK;
+}
+
+// --------------------------------------------------------------------------------------------- workspace
+struct Workspace {
+  char* base;
+  size_t big_stride, small_stride;
+  size_t off_small, off_features, off_logits, off_c2d, off_c3d, off_n2d, off_partial, total;
+};
+
+Workspace layout(const mtb_handle* h, int B, void* base) {
+  Workspace w;
+  w.base = (char*)base;
+  const size_t es = elem_size(h);
+  w.big_stride = align_up(h->big_elems_per_crop * (size_t)B * es, 1024);
+  w.small_stride = align_up((size_t)h->small_c * B * 4, 1024);
+  size_t o = w.big_stride * kNumBig;
+  w.off_small = o; o += w.small_stride * kNumSmall;
+  const size_t P = (size_t)h->feat_side * h->feat_side;
+  w.off_features = o; o += align_up(P * h->feat_c * B * es, 1024);
+  const int N = (h->cfg.n_joints * (1 + h->cfg.depth) + 3) / 4 * 4;
+  w.off_logits = o; o += align_up(P * N * B * 4, 1024);
+  w.off_c2d = o; o += align_up((size_t)B * h->cfg.n_joints * 2 * 4, 1024);
+  w.off_c3d = o; o += align_up((size_t)B * h->cfg.n_joints * 3 * 4, 1024);
+  w.off_n2d = o; o += align_up((size_t)B * h->cfg.n_joints * 2 * 4, 1024);
+  w.off_partial = o; o += align_up((size_t)B * 2 * 8, 1024);
+  w.total = o;
+  return w;
+}
+
+void* buf_ptr(const Workspace& w, int id, void* features) {
+  if (id == BUF_FEATURES) return features;
+  if (id < 0) return nullptr;
+  if (id < kNumBig) return w.base + w.big_stride * id;
+  return w.base + w.off_small + w.small_stride * (id - BUF_SMALL0);
+}
+
+// ---------------------------------------------------------------------------------------------- executor
+template <typename T>
+int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Workspace& ws, void* features,
+             cudaStream_t st) {
+  switch (op.type) {
+    case OP_STEM: {
+      StemParams p;
+      p.in = crops; p.out = buf_ptr(ws, op.out_buf, features); p.w = op.d_w; p.bias = op.d_bias;
+      for (int i = 0; i < 4; ++i) { p.pre_scale[i] = 2.f; p.pre_shift[i] = -1.f; }  // PreprocLayer x*2-1
+      p.B = B; p.Hin = op.Hin; p.Win = op.Win; p.Cin = op.Cin; p.Hout = op.Hout; p.Wout = op.Wout; p.Cout = op.Cout;
+      p.R = op.R; p.S = op.S; p.stride = op.stride; p.pad_t = op.pad_t; p.pad_l = op.pad_l; p.act = op.act;
+      size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
+      size_t smem = ((size_t)op.R * op.S * op.Cin + 1) * op.Cout * 4;
+      stem_conv_kernel<T><<<grid_for(total, 256), 256, smem, st>>>(p);
+      h->launches++;
+      break;
+    }
+    case OP_CONV:
+    case OP_DW:
+    case OP_MAXPOOL: {
+      ConvParams p;
+      p.in = buf_ptr(ws, op.in_buf, features);
+      p.out = buf_ptr(ws, op.out_buf, features);
+      p.res = buf_ptr(ws, op.res_buf, features);
+      p.a_scale = (const float*)buf_ptr(ws, op.scale_buf, features);
+      p.w = op.d_w; p.bias = op.d_bias;
+      p.B = B; p.Hin = op.Hin; p.Win = op.Win; p.Cin = op.Cin; p.Hout = op.Hout; p.Wout = op.Wout; p.Cout = op.Cout;
+      p.R = op.R; p.S = op.S; p.stride = op.stride; p.dil = op.dil; p.pad_t = op.pad_t; p.pad_l = op.pad_l; p.act = op.act;
+      if (op.type == OP_DW) {
+        size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
+        dwconv_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
+      } else if (op.type == OP_MAXPOOL) {
+        size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
+        maxpool_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
+      } else if (op.small_io) {
+        cudaError_t e = launch_conv_igemm<float, float>(p, st);
+        if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "launch %s: %s", op.name.c_str(), cudaGetErrorString(e));
+      } else if (op.tc.ready) {
+        const char* e = tc_conv_launch(op.tc, p, st);
+        if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 launch %s: %s", op.name.c_str(), e);
+      } else {
+        cudaError_t e = launch_conv_igemm<T, T>(p, st);
+        if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "launch %s: %s", op.name.c_str(), cudaGetErrorString(e));
+      }
+      h->launches++;
+      break;
+    }
+    case OP_POOL: {
+      dim3 grid((op.Cin + 127) / 128, B), block(32, 8);
+      pool_mean_kernel<T><<<grid, block, 0, st>>>((const T*)buf_ptr(ws, op.in_buf, features),
+                                                   (float*)buf_ptr(ws, op.out_buf, features), op.Hin * op.Win, op.Cin);
+      h->launches++;
+      break;
+    }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "launch %s: %s", op.name.c_str(), cudaGetErrorString(e));
+  return MTB_OK;
+}
+
+int run_op(mtb_handle* h, const Op& op, const float* crops, int B, const Workspace& ws, void* features, cudaStream_t st) {
+  if (h->cfg.precision == MTB_PRECISION_BF16_TC) return run_op_t<__nv_bfloat16>(h, op, crops, B, ws, features, st);
+  return run_op_t<float>(h, op, crops, B, ws, features, st);
+}
+
+int check_common(mtb_handle* h, int B, size_t ws_bytes, const void* workspace) {
+  if (!h) return fail(nullptr, MTB_ERR_INVALID_ARG, "null handle");
+  if (!h->finalized) return fail(h, MTB_ERR_NOT_FINALIZED, "mtb_finalize_weights has not been called");
+  if (B <= 0) return fail(h, MTB_ERR_INVALID_ARG, "batch must be positive (got %d)", B);
+  if (!workspace || ws_bytes < layout(h, B, nullptr).total)
+    return fail(h, MTB_ERR_WORKSPACE, "workspace too small: need %zu bytes for batch %d, got %zu",
+                layout(h, B, nullptr).total, B, ws_bytes);
+  return MTB_OK;
+}
+
+DecodeScale make_scale(const mtb_config& c) {
+  // heatmap_to_image / heatmap_to_metric (models/util.py:6-33), inference => stride_test
+  DecodeScale s;
+  int last = c.proc_side - 1;
+  int last_rc = last - (last % c.stride_test);
+  float add = 0.f;
+  if (c.centered_stride) add += (float)(c.stride_test / 2);
+  if (c.legacy_centered_stride_bug) add += (float)(c.stride_test / 2);
+  s.img_mul = (float)last_rc;
+  s.img_add = add;
+  s.met_mul = (float)last_rc * c.box_size_mm / (float)c.proc_side;
+  s.met_add = add * c.box_size_mm / (float)c.proc_side;
+  s.z_mul = c.box_size_mm;
+  s.apply = 1;
+  return s;
+}
+
+template <typename T>
+int launch_softargmax_bhwn(const void* logits, float* out2d, float* out3d, int B, int J, int D, int H, int W,
+                           int ld, DecodeScale sc, cudaStream_t st) {
+  const int N = J * (1 + D);
+  size_t smem = ((size_t)N + 4 * 128) * sizeof(float4);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(softargmax_bhwn_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  softargmax_bhwn_kernel<T><<<B, 512, smem, st>>>((const T*)logits, out2d, out3d, J, D, H, W, ld, sc);
+  return (int)cudaGetLastError();
+}
+
+int head_decode_impl(mtb_handle* h, const void* features, int B, float* c2d, float* c3d, const Workspace& ws,
+                     cudaStream_t st) {
+  const mtb_config& c = h->cfg;
+  const Op& op = h->head;
+  if (op.tc.ready) {
+    // fused: 1x1-conv GEMM on tcgen05 with the soft-argmax reduction in the epilogue; logits never reach HBM
+    const char* e = tc_head_launch(op.tc, features, B, h->feat_side, h->feat_side, c.n_joints, c.depth, make_scale(c),
+                                   c2d, c3d, st);
+    if (e) return fail(h, MTB_ERR_CUDA, "fused head: %s", e);
+    h->launches++;
+    return MTB_OK;
+  }
+  ConvParams p;
+  p.in = features; p.out = ws.base + ws.off_logits; p.res = nullptr; p.a_scale = nullptr;
+  p.w = op.d_w; p.bias = op.d_bias;
+  p.B = B; p.Hin = p.Hout = op.Hin; p.Win = p.Wout = op.Win; p.Cin = op.Cin; p.Cout = op.Cout;
+  p.R = p.S = 1; p.stride = 1; p.dil = 1; p.pad_t = p.pad_l = 0; p.act = ACT_NONE;
+  cudaError_t e = c.precision == MTB_PRECISION_BF16_TC ? launch_conv_igemm<__nv_bfloat16, float>(p, st)
+                                                       : launch_conv_igemm<float, float>(p, st);
+  if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "head conv: %s", cudaGetErrorString(e));
+  int rc = launch_softargmax_bhwn<float>(p.out, c2d, c3d, B, c.n_joints, c.depth, op.Hin, op.Win, op.Cout, make_scale(c), st);
+  if (rc) return fail(h, MTB_ERR_CUDA, "softargmax: %s", cudaGetErrorString((cudaError_t)rc));
+  h->launches += 2;
+  return MTB_OK;
+}
+
+int recon_impl(mtb_handle* h, const float* c2d, const float* c3d, const float* K, int B, float* out, float* n2d,
+               double* partial, cudaStream_t st) {
+  const mtb_config& c = h->cfg;
+  ReconParams p;
+  p.c2d = c2d; p.c3d = c3d; p.K = K; p.out = out; p.partial = partial; p.n2d = n2d;
+  p.B = B; p.J = c.n_joints;
+  float offset = c.centered_stride ? 0.f : -(float)c.stride_train / 2.f;  // is_within_fov (ptu3d.py:113-121)
+  p.fov_lower = (float)c.stride_train * 0.75f + offset;
+  p.fov_upper = (float)c.proc_side - (float)c.stride_train * 0.75f + offset;
+  p.use_mix = c.mix_3d_inside_fov >= 0.f;
+  p.mix = c.mix_3d_inside_fov;
+  recon_pass1_kernel<<<B, 128, 0, st>>>(p);
+  recon_pass2_kernel<<<B, 128, 0, st>>>(p);
+  h->launches += 2;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "reconstruct: %s", cudaGetErrorString(e));
+  return MTB_OK;
+}
+
+__global__ void to_float_kernel(const __nv_bfloat16* in, float* out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+
+// =================================================================================================== C ABI
+extern "C" {
+
+const char* mtb_version(void) { return "metrabs_b200 0.1 (sm_100a)"; }
+
+const char* mtb_last_error(const mtb_handle* h) { return h ? h->err.c_str() : g_error.c_str(); }
+
+int mtb_create(const mtb_config* cfg, mtb_handle** out) {
+  if (!cfg || !out) return fail(nullptr, MTB_ERR_INVALID_ARG, "null argument");
+  if (cfg->abi_version != MTB_ABI_VERSION)
+    return fail(nullptr, MTB_ERR_INVALID_ARG, "ABI version mismatch: header %d, caller %d", MTB_ABI_VERSION, cfg->abi_version);
+  if (cfg->weak_perspective)
+    return fail(nullptr, MTB_ERR_UNSUPPORTED, "weak_perspective reconstruction is not functional in the reference (ptu.py:30,42)");
+  if (cfg->n_joints <= 0 || cfg->depth < 1 || cfg->proc_side <= 0 || cfg->stride_test <= 0 || cfg->stride_train <= 0)
+    return fail(nullptr, MTB_ERR_INVALID_ARG, "invalid geometry (n_joints=%d depth=%d proc_side=%d stride=%d)", cfg->n_joints,
+                cfg->depth, cfg->proc_side, cfg->stride_test);
+  if (cfg->arch == MTB_ARCH_EFFNET && (cfg->n_stages <= 0 || cfg->n_stages > MTB_MAX_STAGES))
+    return fail(nullptr, MTB_ERR_INVALID_ARG, "n_stages out of range");
+  if (cfg->precision != MTB_PRECISION_FP32 && cfg->precision != MTB_PRECISION_BF16_TC)
+    return fail(nullptr, MTB_ERR_INVALID_ARG, "unknown precision %d", cfg->precision);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, MTB_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, MTB_ERR_INVALID_ARG, "device %d out of range", cfg->device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+    return fail(nullptr, MTB_ERR_CUDA, "device %d is not sm_100 (compute capability %d.%d)", cfg->device, prop.major, prop.minor);
+  mtb_handle* h = new mtb_handle();
+  h->cfg = *cfg;
+  int rc = plan(h);
+  if (rc) {
+    g_error = h->err;
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return MTB_OK;
+}
+
+int mtb_destroy(mtb_handle* h) {
+  if (!h) return MTB_OK;
+  DeviceGuard g(h->cfg.device);
+  for (void* p : h->dev_allocs) cudaFree(p);
+  if (h->stage) cudaFree(h->stage);
+  if (h->nccl_comm && h->nccl_lib) {
+    typedef int (*destroy_t)(void*);
+    destroy_t f = (destroy_t)dlsym(h->nccl_lib, "ncclCommDestroy");
+    if (f) f(h->nccl_comm);
+  }
+  delete h;
+  return MTB_OK;
+}
+
+int mtb_load_weight(mtb_handle* h, const char* name, const void* data, int dtype, const int64_t* shape, int ndim) {
+  if (!h || !name || !data || (ndim > 0 && !shape)) return fail(h, MTB_ERR_INVALID_ARG, "null argument");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    t.shape.push_back(shape[i]);
+    n *= (size_t)shape[i];
+  }
+  t.data.resize(n);
+  switch (dtype) {
+    case MTB_DTYPE_F32: memcpy(t.data.data(), data, n * 4); break;
+    case MTB_DTYPE_BF16: {
+      const uint16_t* s = (const uint16_t*)data;
+      for (size_t i = 0; i < n; ++i) {
+        uint32_t u = (uint32_t)s[i] << 16;
+        memcpy(&t.data[i], &u, 4);
+      }
+      break;
+    }
+    case MTB_DTYPE_F16: {
+      const __half* s = (const __half*)data;
+      for (size_t i = 0; i < n; ++i) t.data[i] = __half2float(s[i]);
+      break;
+    }
+    case MTB_DTYPE_I64: {
+      const int64_t* s = (const int64_t*)data;
+      for (size_t i = 0; i < n; ++i) t.data[i] = (float)s[i];
+      break;
+    }
+    default: return fail(h, MTB_ERR_INVALID_ARG, "unknown dtype %d for '%s'", dtype, name);
+  }
+  h->raw[name] = std::move(t);
+  h->finalized = false;
+  return MTB_OK;
+}
+
+int mtb_finalize_weights(mtb_handle* h) {
+  if (!h) return fail(nullptr, MTB_ERR_INVALID_ARG, "null handle");
+  DeviceGuard g(h->cfg.device);
+  for (void* p : h->dev_allocs) cudaFree(p);
+  h->dev_allocs.clear();
+  for (auto& op : h->ops) {
+    int rc = prepare_op_weights(h, op);
+    if (rc) return rc;
+  }
+  {
+    Op& hd = h->head;
+    const HostTensor* w = find(h, hd.wkey);
+    if (!w) return fail(h, MTB_ERR_MISSING_WEIGHT, "missing weight '%s'", hd.wkey.c_str());
+    const int n_real = h->cfg.n_joints * (1 + h->cfg.depth);
+    if (w->shape.size() != 4 || w->shape[0] != n_real || w->shape[1] != hd.Cin)
+      return fail(h, MTB_ERR_INVALID_ARG, "'%s' must be [%d,%d,1,1]", hd.wkey.c_str(), n_real, hd.Cin);
+    const HostTensor* hb = find(h, hd.biaskey);
+    if (!hb || (int)hb->data.size() != n_real) return fail(h, MTB_ERR_MISSING_WEIGHT, "missing weight '%s'", hd.biaskey.c_str());
+    if (n_real != hd.Cout) {  // zero-pad the output channels
+      HostTensor wp = *w, bp = *hb;
+      wp.data.resize((size_t)hd.Cout * hd.Cin, 0.f);
+      wp.shape[0] = hd.Cout;
+      bp.data.resize(hd.Cout, 0.f);
+      bp.shape[0] = hd.Cout;
+      h->raw[hd.wkey] = wp;
+      h->raw[hd.biaskey] = bp;
+      w = find(h, hd.wkey);
+    }
+    int rc = prepare_op_weights(h, hd);
+    if (rc) return rc;
+    if (h->cfg.precision == MTB_PRECISION_BF16_TC) {
+      const char* e = tc_prepare_head(hd.tc, w->data.data(), find(h, hd.biaskey)->data.data(), hd.Cin, n_real, h->dev_allocs);
+      if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 head weight prep: %s", e);
+    }
+  }
+  h->raw.clear();
+  h->finalized = true;
+  return MTB_OK;
+}
+
+size_t mtb_workspace_bytes(const mtb_handle* h, int batch) {
+  if (!h || batch <= 0) return 0;
+  return layout(h, batch, nullptr).total;
+}
+
+int mtb_feature_shape(const mtb_handle* h, int* hw_side, int* channels) {
+  if (!h) return fail(nullptr, MTB_ERR_INVALID_ARG, "null handle");
+  if (hw_side) *hw_side = h->feat_side;
+  if (channels) *channels = h->feat_c;
+  return MTB_OK;
+}
+
+int mtb_backbone_forward(mtb_handle* h, const float* crops, int batch, void* features, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  int rc = check_common(h, batch, workspace_bytes, workspace);
+  if (rc) return rc;
+  if (!crops || !features) return fail(h, MTB_ERR_INVALID_ARG, "null crops/features");
+  if (h->ops.empty()) return fail(h, MTB_ERR_UNSUPPORTED, "this handle has no backbone (head-only)");
+  DeviceGuard g(h->cfg.device);
+  h->launches = 0;
+  Workspace ws = layout(h, batch, workspace);
+  for (const Op& op : h->ops) {
+    rc = run_op(h, op, crops, batch, ws, features, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return MTB_OK;
+}
+
+int mtb_head_decode(mtb_handle* h, const void* features, int batch, float* coords2d, float* coords3d_rel,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(h, batch, workspace_bytes, workspace);
+  if (rc) return rc;
+  if (!features || !coords2d || !coords3d_rel) return fail(h, MTB_ERR_INVALID_ARG, "null argument");
+  DeviceGuard g(h->cfg.device);
+  h->launches = 0;
+  Workspace ws = layout(h, batch, workspace);
+  return head_decode_impl(h, features, batch, coords2d, coords3d_rel, ws, (cudaStream_t)stream);
+}
+
+int mtb_softargmax(const void* logits, int dtype, int layout_, int batch, int n_joints, int depth, int height,
+                   int width, float* out2d, float* out3d, void* stream) {
+  if (!logits || batch <= 0 || n_joints <= 0 || depth < 0 || height <= 0 || width <= 0)
+    return fail(nullptr, MTB_ERR_INVALID_ARG, "invalid soft-argmax arguments");
+  if (dtype != MTB_DTYPE_F32 && dtype != MTB_DTYPE_BF16) return fail(nullptr, MTB_ERR_UNSUPPORTED, "soft-argmax dtype must be f32 or bf16");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (layout_ == MTB_LAYOUT_BDJHW) {
+    const bool two_d = depth == 0;
+    float* out = two_d ? out2d : out3d;
+    if (!out) return fail(nullptr, MTB_ERR_INVALID_ARG, "null output");
+    const int D = two_d ? 1 : depth;
+    const bool vec = (width % 4 == 0) && (((uintptr_t)logits) % 16 == 0);
+    const int rows = batch * n_joints;
+    if (dtype == MTB_DTYPE_F32) {
+      if (vec) softargmax_bdjhw_kernel<float, 4><<<rows, 256, 0, st>>>((const float*)logits, out, n_joints, D, height, width, two_d);
+      else softargmax_bdjhw_kernel<float, 1><<<rows, 256, 0, st>>>((const float*)logits, out, n_joints, D, height, width, two_d);
+    } else {
+      if (vec) softargmax_bdjhw_kernel<__nv_bfloat16, 4><<<rows, 256, 0, st>>>((const __nv_bfloat16*)logits, out, n_joints, D, height, width, two_d);
+      else softargmax_bdjhw_kernel<__nv_bfloat16, 1><<<rows, 256, 0, st>>>((const __nv_bfloat16*)logits, out, n_joints, D, height, width, two_d);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, MTB_ERR_CUDA, "softargmax launch: %s", cudaGetErrorString(e));
+    return MTB_OK;
+  }
+  if (layout_ == MTB_LAYOUT_BHWN) {
+    DecodeScale sc{};
+    sc.apply = 0;
+    int rc = dtype == MTB_DTYPE_F32
+                 ? launch_softargmax_bhwn<float>(logits, out2d, out3d, batch, n_joints, depth, height, width, n_joints * (1 + depth), sc, st)
+                 : launch_softargmax_bhwn<__nv_bfloat16>(logits, out2d, out3d, batch, n_joints, depth, height, width, n_joints * (1 + depth), sc, st);
+    if (rc) return fail(nullptr, MTB_ERR_CUDA, "softargmax launch: %s", cudaGetErrorString((cudaError_t)rc));
+    return MTB_OK;
+  }
+  return fail(nullptr, MTB_ERR_INVALID_ARG, "unknown layout %d", layout_);
+}
+
+size_t mtb_reconstruct_scratch_bytes(int batch) {
+  return batch <= 0 ? 0 : align_up((size_t)batch * 2 * 8, 256) + (size_t)batch * 4096 * 2 * 4;
+}
+
+int mtb_reconstruct_absolute(mtb_handle* h, const float* coords2d, const float* coords3d_rel, const float* intrinsics,
+                             int batch, float* coords3d_abs, void* scratch, void* stream) {
+  if (!h) return fail(nullptr, MTB_ERR_INVALID_ARG, "null handle");
+  if (!coords2d || !coords3d_rel || !intrinsics || !coords3d_abs || !scratch || batch <= 0)
+    return fail(h, MTB_ERR_INVALID_ARG, "null/invalid argument");
+  if (h->cfg.n_joints > 4096) return fail(h, MTB_ERR_UNSUPPORTED, "more than 4096 joints");
+  DeviceGuard g(h->cfg.device);
+  h->launches = 0;
+  double* partial = (double*)scratch;
+  float* n2d = (float*)((char*)scratch + align_up((size_t)batch * 2 * 8, 256));
+  return recon_impl(h, coords2d, coords3d_rel, intrinsics, batch, coords3d_abs, n2d, partial, (cudaStream_t)stream);
+}
+
+int mtb_forward(mtb_handle* h, const float* crops, const float* intrinsics, int batch, float* coords3d_abs,
+                void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(h, batch, workspace_bytes, workspace);
+  if (rc) return rc;
+  if (!crops || !intrinsics || !coords3d_abs) return fail(h, MTB_ERR_INVALID_ARG, "null argument");
+  if (h->ops.empty()) return fail(h, MTB_ERR_UNSUPPORTED, "this handle has no backbone (head-only)");
+  DeviceGuard g(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  h->launches = 0;
+  Workspace ws = layout(h, batch, workspace);
+  void* features = ws.base + ws.off_features;
+  for (const Op& op : h->ops) {
+    rc = run_op(h, op, crops, batch, ws, features, st);
+    if (rc) return rc;
+  }
+  float* c2d = (float*)(ws.base + ws.off_c2d);
+  float* c3d = (float*)(ws.base + ws.off_c3d);
+  rc = head_decode_impl(h, features, batch, c2d, c3d, ws, st);
+  if (rc) return rc;
+  return recon_impl(h, c2d, c3d, intrinsics, batch, coords3d_abs, (float*)(ws.base + ws.off_n2d),
+                    (double*)(ws.base + ws.off_partial), st);
+}
+
+int mtb_forward_host(mtb_handle* h, const float* host_crops, const float* host_intrinsics, int batch,
+                     float* host_coords3d_abs, void* stream) {
+  if (!h) return fail(nullptr, MTB_ERR_INVALID_ARG, "null handle");
+  if (!h->finalized) return fail(h, MTB_ERR_NOT_FINALIZED, "mtb_finalize_weights has not been called");
+  if (!host_crops || !host_intrinsics || !host_coords3d_abs || batch <= 0) return fail(h, MTB_ERR_INVALID_ARG, "null/invalid argument");
+  DeviceGuard g(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t S = h->cfg.proc_side;
+  const size_t crops_b = align_up((size_t)batch * 3 * S * S * 4, 1024), k_b = align_up((size_t)batch * 9 * 4, 1024),
+               out_b = align_up((size_t)batch * h->cfg.n_joints * 3 * 4, 1024);
+  const size_t ws_b = layout(h, batch, nullptr).total;
+  const size_t need = crops_b + k_b + out_b + ws_b;
+  if (need > h->stage_bytes) {  // grows only when a larger batch than ever before arrives
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    if (h->stage) cudaFree(h->stage);
+    h->stage = nullptr;
+    h->stage_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&h->stage, need));
+    h->stage_bytes = need;
+  }
+  char* base = (char*)h->stage;
+  float* d_crops = (float*)base;
+  float* d_k = (float*)(base + crops_b);
+  float* d_out = (float*)(base + crops_b + k_b);
+  void* d_ws = base + crops_b + k_b + out_b;
+  CUDA_TRY(h, cudaMemcpyAsync(d_crops, host_crops, (size_t)batch * 3 * S * S * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(d_k, host_intrinsics, (size_t)batch * 9 * 4, cudaMemcpyHostToDevice, st));
+  int rc = mtb_forward(h, d_crops, d_k, batch, d_out, d_ws, ws_b, stream);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(host_coords3d_abs, d_out, (size_t)batch * h->cfg.n_joints * 3 * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return MTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- NCCL
+typedef struct { char internal[128]; } nccl_uid;
+static void* open_nccl() {
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    void* l = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (l) return l;
+  }
+  return nullptr;
+}
+
+int mtb_comm_unique_id(void* id128) {
+  if (!id128) return fail(nullptr, MTB_ERR_INVALID_ARG, "null id");
+  void* lib = open_nccl();
+  if (!lib) return fail(nullptr, MTB_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+  typedef int (*fn_t)(nccl_uid*);
+  fn_t f = (fn_t)dlsym(lib, "ncclGetUniqueId");
+  if (!f) return fail(nullptr, MTB_ERR_NCCL, "ncclGetUniqueId not found");
+  int rc = f((nccl_uid*)id128);
+  if (rc) return fail(nullptr, MTB_ERR_NCCL, "ncclGetUniqueId failed (%d)", rc);
+  return MTB_OK;
+}
+
+int mtb_comm_init(mtb_handle* h, const void* id128, int rank, int world_size) {
+  if (!h || !id128 || rank < 0 || rank >= world_size) return fail(h, MTB_ERR_INVALID_ARG, "invalid communicator arguments");
+  DeviceGuard g(h->cfg.device);
+  if (!h->nccl_lib) h->nccl_lib = open_nccl();
+  if (!h->nccl_lib) return fail(h, MTB_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+  typedef int (*fn_t)(void**, int, nccl_uid, int);
+  fn_t f = (fn_t)dlsym(h->nccl_lib, "ncclCommInitRank");
+  if (!f) return fail(h, MTB_ERR_NCCL, "ncclCommInitRank not found");
+  nccl_uid id;
+  memcpy(&id, id128, sizeof(id));
+  int rc = f(&h->nccl_comm, world_size, id, rank);
+  if (rc) return fail(h, MTB_ERR_NCCL, "ncclCommInitRank failed (%d)", rc);
+  h->nccl_world = world_size;
+  return MTB_OK;
+}
+
+int mtb_allgather_joints(mtb_handle* h, const float* local, int floats_per_rank, float* all, void* stream) {
+  if (!h || !local || !all || floats_per_rank <= 0) return fail(h, MTB_ERR_INVALID_ARG, "invalid all-gather arguments");
+  if (!h->nccl_comm) return fail(h, MTB_ERR_NCCL, "mtb_comm_init has not been called");
+  DeviceGuard g(h->cfg.device);
+  typedef int (*fn_t)(const void*, void*, size_t, int, void*, cudaStream_t);
+  static fn_t f = nullptr;
+  if (!f) f = (fn_t)dlsym(h->nccl_lib, "ncclAllGather");
+  if (!f) return fail(h, MTB_ERR_NCCL, "ncclAllGather not found");
+  int rc = f(local, all, (size_t)floats_per_rank, /*ncclFloat32*/ 7, h->nccl_comm, (cudaStream_t)stream);
+  if (rc) return fail(h, MTB_ERR_NCCL, "ncclAllGather failed (%d)", rc);
+  return MTB_OK;
+}
+
+// ---------------------------------------------------------------------------------------- introspection
+int mtb_num_ops(const mtb_handle* h) { return h ? (int)h->ops.size() : 0; }
+
+const char* mtb_op_name(const mtb_handle* h, int op) {
+  if (!h || op < 0 || op >= (int)h->ops.size()) return "";
+  return h->ops[op].name.c_str();
+}
+
+int mtb_op_output_shape(const mtb_handle* h, int op, int* height, int* width, int* channels) {
+  if (!h || op < 0 || op >= (int)h->ops.size()) return fail(h, MTB_ERR_INVALID_ARG, "op index out of range");
+  const Op& o = h->ops[op];
+  if (height) *height = (o.type == OP_POOL || o.small_io) ? 1 : o.Hout;
+  if (width) *width = (o.type == OP_POOL || o.small_io) ? 1 : o.Wout;
+  if (channels) *channels = o.Cout;
+  return MTB_OK;
+}
+
+int mtb_debug_run_ops(mtb_handle* h, const float* crops, int batch, int n_ops, float* out, size_t out_floats,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(h, batch, workspace_bytes, workspace);
+  if (rc) return rc;
+  if (n_ops <= 0 || n_ops > (int)h->ops.size() || !out || !crops) return fail(h, MTB_ERR_INVALID_ARG, "invalid debug arguments");
+  DeviceGuard g(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws = layout(h, batch, workspace);
+  void* features = ws.base + ws.off_features;
+  for (int i = 0; i < n_ops; ++i) {
+    rc = run_op(h, h->ops[i], crops, batch, ws, features, st);
+    if (rc) return rc;
+  }
+  const Op& o = h->ops[n_ops - 1];
+  const bool small = o.type == OP_POOL || o.small_io;
+  size_t n = (size_t)batch * (small ? 1 : (size_t)o.Hout * o.Wout) * o.Cout;
+  if (n > out_floats) return fail(h, MTB_ERR_INVALID_ARG, "debug output buffer too small (%zu > %zu)", n, out_floats);
+  void* src = buf_ptr(ws, o.out_buf, features);
+  if (small || h->cfg.precision == MTB_PRECISION_FP32) {
+    CUDA_TRY(h, cudaMemcpyAsync(out, src, n * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    to_float_kernel<<<grid_for(n, 256), 256, 0, st>>>((const __nv_bfloat16*)src, out, n);
+  }
+  return MTB_OK;
+}
+
+int64_t mtb_last_launch_count(const mtb_handle* h) { return h ? h->launches : 0; }
+double mtb_backbone_flops_per_crop(const mtb_handle* h) { return h ? h->flops_per_crop : 0.0; }
+
+}  // extern "C"

@@ -1,0 +1,30 @@
+"""Shared builders for the GPU parity tests: the oracle side (oracle/port.py state_dict + forward) and the device
+side (metrabs_b200.Metrabs behind the C ABI) on identical weights and inputs."""
+import dataclasses
+import types
+
+import torch
+
+import metrabs_b200
+from metrabs_b200.backbones import efficientnet as E
+from metrabs_b200.models.metrabs import Metrabs
+from oracle import port
+
+SIZES = {'efficientnetv2-tiny': 'tiny', 'efficientnetv2-s': 's', 'efficientnetv2-m': 'm', 'efficientnetv2-l': 'l'}
+
+
+def joint_info(n):
+    return types.SimpleNamespace(names=[f'j{i}' for i in range(n)], stick_figure_edges=[(0, 1)], n_joints=n)
+
+
+def device_model(name, pcfg: port.PathConfig, n_joints, sd, precision='fp32'):
+    cfg = metrabs_b200.Config(**{k: v for k, v in dataclasses.asdict(pcfg).items()}, precision=precision)
+    metrabs_b200.set_config(cfg)
+    bb = E.EfficientNet(SIZES[name])
+    m = Metrabs(torch.nn.Sequential(E.PreprocLayer(), bb.features), joint_info(n_joints)).eval()
+    m.load_state_dict(sd, strict=True)
+    return m.cuda()
+
+
+def rel_err(a, b):
+    return port.relative_error(a.detach().float().cpu(), torch.as_tensor(b).float().cpu())

@@ -158,6 +158,14 @@ const char* mtb_op_name(const mtb_handle* h, int op);
 int mtb_debug_run_ops(mtb_handle* h, const float* crops, int batch, int n_ops, float* out, size_t out_floats,
                       void* workspace, size_t workspace_bytes, void* stream);
 int mtb_op_output_shape(const mtb_handle* h, int op, int* height, int* width, int* channels);
+/* CUDA-event profiler (bench.py's live roofline measurement): between begin and end, every kernel launch of the
+ * classes selected by `class_mask` (bit i = class i) is bracketed by cudaEventRecord on the launching stream.
+ * mtb_profile_end synchronises those events and returns, per class, the summed device time (ms), algorithmic
+ * FLOPs, algorithmic bytes and launch count; arrays must hold mtb_num_kernel_classes() entries. */
+int mtb_profile_begin(mtb_handle* h, unsigned class_mask);
+int mtb_profile_end(mtb_handle* h, double* ms, double* flops, double* bytes, int64_t* launches);
+int mtb_num_kernel_classes(void);
+const char* mtb_kernel_class_name(int cls);
 /* Number of kernels the last mtb_forward / mtb_backbone_forward / ... call on this handle launched. */
 int64_t mtb_last_launch_count(const mtb_handle* h);
 double mtb_backbone_flops_per_crop(const mtb_handle* h);

@@ -62,6 +62,11 @@ _SIGNATURES = {
                                     C.c_size_t, C.c_void_p]),
     'mtb_op_output_shape': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.POINTER(C.c_int)]),
+    'mtb_profile_begin': (C.c_int, [C.c_void_p, C.c_uint]),
+    'mtb_profile_end': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_int64)]),
+    'mtb_num_kernel_classes': (C.c_int, []),
+    'mtb_kernel_class_name': (C.c_char_p, [C.c_int]),
     'mtb_last_launch_count': (C.c_int64, [C.c_void_p]),
     'mtb_backbone_flops_per_crop': (C.c_double, [C.c_void_p]),
 }

@@ -25,6 +25,13 @@ namespace {
 std::string g_error;
 
 enum OpType { OP_STEM = 0, OP_CONV = 1, OP_DW = 2, OP_POOL = 3, OP_MAXPOOL = 4 };
+// kernel classes for the CUDA-event profiler (mtb_profile_begin / mtb_profile_end)
+enum KClass { KC_STEM = 0, KC_IGEMM_SIMT = 1, KC_DWCONV = 2, KC_POOL = 3, KC_SE_FC = 4, KC_TC_GEMM = 5, KC_TC_CONV3 = 6,
+              KC_HEAD_FUSED = 7, KC_HEAD_CONV_SIMT = 8, KC_SOFTARGMAX = 9, KC_RECON = 10, KC_OTHER = 11, KC_COUNT = 12 };
+const char* kKClassNames[KC_COUNT] = {"stem_conv_kernel", "conv_igemm_kernel", "dwconv_kernel", "pool_mean_kernel",
+                                      "se_fc(conv_igemm_kernel)", "tc_gemm_kernel", "tc_conv3x3_kernel",
+                                      "tc_head_softargmax_kernel", "head_conv(conv_igemm_kernel)",
+                                      "softargmax_bhwn_kernel", "recon_pass1+2_kernel", "other"};
 enum { BUF_FEATURES = -2, BUF_NONE = -1, BUF_SMALL0 = 4 };  // 0..3 big activation buffers, 4..6 small [B,C]
 constexpr int kNumBig = 4, kNumSmall = 3;
 
@@ -44,6 +51,7 @@ struct Op {
   int R = 1, S = 1, stride = 1, dil = 1, pad_t = 0, pad_l = 0, act = ACT_NONE;
   bool depthwise = false;
   bool small_io = false;  // squeeze-excitation FCs on [B,1,1,C] fp32 tensors
+  bool pad_ok = false;    // weight tensor may be smaller than [Cout,Cin]: channels zero-padded to a multiple of 4
   float bn_eps = 1e-3f;
   float* d_w = nullptr;     // fp32 [R*S*Cin][Cout]  (dw: [R*S][C])
   float* d_bias = nullptr;  // fp32 [Cout]
@@ -71,6 +79,12 @@ struct mtb_handle {
   void* stage = nullptr;
   size_t stage_bytes = 0;
   int stage_batch = 0;
+  // profiler
+  unsigned prof_mask = 0;
+  std::vector<cudaEvent_t> prof_events;  // pairs
+  std::vector<int> prof_cls;
+  std::vector<double> prof_flops, prof_bytes;
+  size_t prof_used = 0;
   // NCCL (dlopen'ed)
   void* nccl_lib = nullptr;
   void* nccl_comm = nullptr;
@@ -199,7 +213,8 @@ void plan_effnet(mtb_handle* h) {
         P.conv(kb + "." + std::to_string(i), cexp, k, stride, pad_beg, pad_total, ACT_SILU, t1, t2, true);
         ++i;
         // squeeze-excitation: avgpool -> fc1 + SiLU -> fc2 + sigmoid -> scale (folded into the projection's A load)
-        const int csq = std::max(1, cin / 4);
+        const int csq_real = std::max(1, cin / 4);
+        const int csq = (csq_real + 3) / 4 * 4;  // hidden channels zero-padded to a multiple of 4 (128-bit accesses)
         const std::string se = kb + "." + std::to_string(i);
         {
           Op op;
@@ -209,15 +224,15 @@ void plan_effnet(mtb_handle* h) {
           h->ops.push_back(op);
           Op f1;
           f1.type = OP_CONV; f1.name = se + ".fc1"; f1.wkey = se + ".fc1.weight"; f1.biaskey = se + ".fc1.bias";
-          f1.Cin = cexp; f1.Cout = csq; f1.act = ACT_SILU; f1.small_io = true;
+          f1.Cin = cexp; f1.Cout = csq; f1.act = ACT_SILU; f1.small_io = true; f1.pad_ok = true;
           f1.in_buf = BUF_SMALL0; f1.out_buf = BUF_SMALL0 + 1;
-          f1.flops = 2.0 * cexp * csq;
+          f1.flops = 2.0 * cexp * csq_real;
           h->ops.push_back(f1);
           Op f2;
           f2.type = OP_CONV; f2.name = se + ".fc2"; f2.wkey = se + ".fc2.weight"; f2.biaskey = se + ".fc2.bias";
-          f2.Cin = csq; f2.Cout = cexp; f2.act = ACT_SIGMOID; f2.small_io = true;
+          f2.Cin = csq; f2.Cout = cexp; f2.act = ACT_SIGMOID; f2.small_io = true; f2.pad_ok = true;
           f2.in_buf = BUF_SMALL0 + 1; f2.out_buf = BUF_SMALL0 + 2;
-          f2.flops = 2.0 * cexp * csq;
+          f2.flops = 2.0 * cexp * csq_real;
           h->ops.push_back(f2);
           P.max_small = std::max(P.max_small, cexp);
         }
@@ -294,14 +309,20 @@ int prepare_op_weights(mtb_handle* h, Op& op) {
   if (!w) return fail(h, MTB_ERR_MISSING_WEIGHT, "missing weight '%s'", op.wkey.c_str());
   const int cin_g = op.depthwise ? 1 : op.Cin;
   const int64_t expect[4] = {op.Cout, cin_g, op.R, op.S};
-  if (w->shape.size() != 4 || !std::equal(expect, expect + 4, w->shape.begin()))
+  bool shape_ok = w->shape.size() == 4 && std::equal(expect, expect + 4, w->shape.begin());
+  if (!shape_ok && op.pad_ok && w->shape.size() == 4 && w->shape[2] == op.R && w->shape[3] == op.S &&
+      w->shape[0] <= op.Cout && w->shape[0] > op.Cout - 4 && w->shape[1] <= cin_g && w->shape[1] > cin_g - 4)
+    shape_ok = true;
+  if (!shape_ok)
     return fail(h, MTB_ERR_INVALID_ARG, "weight '%s' has the wrong shape (want [%d,%d,%d,%d])", op.wkey.c_str(),
                 op.Cout, cin_g, op.R, op.S);
+  const int n_real = (int)w->shape[0], c_real = (int)w->shape[1];
   std::vector<double> scale(op.Cout, 1.0), shift(op.Cout, 0.0);
   if (!op.biaskey.empty()) {
     const HostTensor* b = find(h, op.biaskey);
     if (!b) return fail(h, MTB_ERR_MISSING_WEIGHT, "missing weight '%s'", op.biaskey.c_str());
-    for (int n = 0; n < op.Cout; ++n) shift[n] = b->data[n];
+    if ((int)b->data.size() != n_real) return fail(h, MTB_ERR_INVALID_ARG, "bias '%s' has the wrong size", op.biaskey.c_str());
+    for (int n = 0; n < n_real; ++n) shift[n] = b->data[n];
   }
   if (!op.bnkey.empty()) {
     const HostTensor *g = find(h, op.bnkey + ".weight"), *b = find(h, op.bnkey + ".bias"),
@@ -314,13 +335,13 @@ int prepare_op_weights(mtb_handle* h, Op& op) {
     }
   }
   const int K = op.R * op.S * cin_g;
-  std::vector<float> wk((size_t)K * op.Cout), bias(op.Cout);
-  for (int n = 0; n < op.Cout; ++n) {
+  std::vector<float> wk((size_t)K * op.Cout, 0.f), bias(op.Cout, 0.f);
+  for (int n = 0; n < n_real; ++n) {
     bias[n] = (float)shift[n];
-    for (int c = 0; c < cin_g; ++c)
+    for (int c = 0; c < c_real; ++c)
       for (int r = 0; r < op.R; ++r)
         for (int s = 0; s < op.S; ++s) {
-          double v = (double)w->data[(((size_t)n * cin_g + c) * op.R + r) * op.S + s] * scale[n];
+          double v = (double)w->data[(((size_t)n * c_real + c) * op.R + r) * op.S + s] * scale[n];
           wk[((size_t)(r * op.S + s) * cin_g + c) * op.Cout + n] = (float)v;
         }
   }
@@ -370,10 +391,61 @@ void* buf_ptr(const Workspace& w, int id, void* features) {
   return w.base + w.off_small + w.small_stride * (id - BUF_SMALL0);
 }
 
+// ---------------------------------------------------------------------------------------------- profiler
+struct ProfScope {
+  mtb_handle* h;
+  cudaStream_t st;
+  bool on;
+  ProfScope(mtb_handle* h_, int cls, double flops, double bytes, cudaStream_t st_) : h(h_), st(st_) {
+    on = (h->prof_mask >> cls) & 1u;
+    if (!on) return;
+    if (h->prof_used + 2 > h->prof_events.size()) {
+      for (int i = 0; i < 2; ++i) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->prof_events.push_back(e);
+      }
+    }
+    h->prof_cls.push_back(cls);
+    h->prof_flops.push_back(flops);
+    h->prof_bytes.push_back(bytes);
+    cudaEventRecord(h->prof_events[h->prof_used], st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(h->prof_events[h->prof_used + 1], st);
+    h->prof_used += 2;
+  }
+};
+
+int op_class(const Op& op) {
+  switch (op.type) {
+    case OP_STEM: return KC_STEM;
+    case OP_DW: return KC_DWCONV;
+    case OP_POOL: return KC_POOL;
+    case OP_MAXPOOL: return KC_OTHER;
+    default: break;
+  }
+  if (op.small_io) return KC_SE_FC;
+  if (op.tc.ready) return op.R == 1 ? KC_TC_GEMM : KC_TC_CONV3;
+  return KC_IGEMM_SIMT;
+}
+
+double op_bytes(const mtb_handle* h, const Op& op, int B) {
+  const double es = op.small_io ? 4.0 : (double)elem_size(h);
+  double in = (double)B * op.Hin * op.Win * op.Cin * (op.type == OP_STEM ? 4.0 : es);
+  double out = (double)B * op.Hout * op.Wout * op.Cout * es;
+  if (op.type == OP_POOL) out = (double)B * op.Cout * 4.0;
+  double res = op.res_buf != BUF_NONE ? out : 0.0;
+  double w = (op.type == OP_POOL || op.type == OP_MAXPOOL) ? 0.0 : (double)op.R * op.S * (op.depthwise ? 1 : op.Cin) * op.Cout * (op.tc.ready ? 2.0 : 4.0);
+  return in + out + res + w;
+}
+
 // ---------------------------------------------------------------------------------------------- executor
 template <typename T>
 int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Workspace& ws, void* features,
              cudaStream_t st) {
+  ProfScope prof(h, op_class(op), op.flops * B, op_bytes(h, op, B), st);
   switch (op.type) {
     case OP_STEM: {
       StemParams p;
@@ -479,8 +551,12 @@ int head_decode_impl(mtb_handle* h, const void* features, int B, float* c2d, flo
                      cudaStream_t st) {
   const mtb_config& c = h->cfg;
   const Op& op = h->head;
+  const double P = (double)h->feat_side * h->feat_side;
+  const double feat_bytes = (double)B * P * op.Cin * elem_size(h);
+  const double out_bytes = (double)B * c.n_joints * 5 * 4;
   if (op.tc.ready) {
     // fused: 1x1-conv GEMM on tcgen05 with the soft-argmax reduction in the epilogue; logits never reach HBM
+    ProfScope prof(h, KC_HEAD_FUSED, op.flops * B, feat_bytes + (double)op.Cin * op.Cout * 2 + out_bytes, st);
     const char* e = tc_head_launch(op.tc, features, B, h->feat_side, h->feat_side, c.n_joints, c.depth, make_scale(c),
                                    c2d, c3d, st);
     if (e) return fail(h, MTB_ERR_CUDA, "fused head: %s", e);
@@ -492,9 +568,15 @@ int head_decode_impl(mtb_handle* h, const void* features, int B, float* c2d, flo
   p.w = op.d_w; p.bias = op.d_bias;
   p.B = B; p.Hin = p.Hout = op.Hin; p.Win = p.Wout = op.Win; p.Cin = op.Cin; p.Cout = op.Cout;
   p.R = p.S = 1; p.stride = 1; p.dil = 1; p.pad_t = p.pad_l = 0; p.act = ACT_NONE;
-  cudaError_t e = c.precision == MTB_PRECISION_BF16_TC ? launch_conv_igemm<__nv_bfloat16, float>(p, st)
-                                                       : launch_conv_igemm<float, float>(p, st);
+  const double logit_bytes = (double)B * P * op.Cout * 4;
+  cudaError_t e;
+  {
+    ProfScope prof(h, KC_HEAD_CONV_SIMT, op.flops * B, feat_bytes + (double)op.Cin * op.Cout * 4 + logit_bytes, st);
+    e = c.precision == MTB_PRECISION_BF16_TC ? launch_conv_igemm<__nv_bfloat16, float>(p, st)
+                                             : launch_conv_igemm<float, float>(p, st);
+  }
   if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "head conv: %s", cudaGetErrorString(e));
+  ProfScope prof(h, KC_SOFTARGMAX, 0.0, logit_bytes + out_bytes, st);
   int rc = launch_softargmax_bhwn<float>(p.out, c2d, c3d, B, c.n_joints, c.depth, op.Hin, op.Win, op.Cout, make_scale(c), st);
   if (rc) return fail(h, MTB_ERR_CUDA, "softargmax: %s", cudaGetErrorString((cudaError_t)rc));
   h->launches += 2;
@@ -512,6 +594,7 @@ int recon_impl(mtb_handle* h, const float* c2d, const float* c3d, const float* K
   p.fov_upper = (float)c.proc_side - (float)c.stride_train * 0.75f + offset;
   p.use_mix = c.mix_3d_inside_fov >= 0.f;
   p.mix = c.mix_3d_inside_fov;
+  ProfScope prof(h, KC_RECON, 0.0, (double)B * c.n_joints * 8 * 4 + (double)B * 36, st);
   recon_pass1_kernel<<<B, 128, 0, st>>>(p);
   recon_pass2_kernel<<<B, 128, 0, st>>>(p);
   h->launches += 2;
@@ -583,6 +666,7 @@ int mtb_destroy(mtb_handle* h) {
   DeviceGuard g(h->cfg.device);
   for (void* p : h->dev_allocs) cudaFree(p);
   if (h->stage) cudaFree(h->stage);
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->nccl_comm && h->nccl_lib) {
     typedef int (*destroy_t)(void*);
     destroy_t f = (destroy_t)dlsym(h->nccl_lib, "ncclCommDestroy");
@@ -798,6 +882,7 @@ int mtb_forward_host(mtb_handle* h, const float* host_crops, const float* host_i
   if (need > h->stage_bytes) {  // grows only when a larger batch than ever before arrives
     CUDA_TRY(h, cudaStreamSynchronize(st));
     if (h->stage) cudaFree(h->stage);
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     h->stage = nullptr;
     h->stage_bytes = 0;
     CUDA_TRY(h, cudaMalloc(&h->stage, need));
@@ -911,6 +996,41 @@ int mtb_debug_run_ops(mtb_handle* h, const float* crops, int batch, int n_ops, f
   }
   return MTB_OK;
 }
+
+int mtb_profile_begin(mtb_handle* h, unsigned class_mask) {
+  if (!h) return fail(nullptr, MTB_ERR_INVALID_ARG, "null handle");
+  h->prof_mask = class_mask;
+  h->prof_used = 0;
+  h->prof_cls.clear();
+  h->prof_flops.clear();
+  h->prof_bytes.clear();
+  return MTB_OK;
+}
+
+int mtb_profile_end(mtb_handle* h, double* ms, double* flops, double* bytes, int64_t* launches) {
+  if (!h || !ms || !flops || !bytes || !launches) return fail(h, MTB_ERR_INVALID_ARG, "null argument");
+  DeviceGuard g(h->cfg.device);
+  for (int i = 0; i < KC_COUNT; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
+  for (size_t i = 0; i < h->prof_cls.size(); ++i) {
+    CUDA_TRY(h, cudaEventSynchronize(h->prof_events[2 * i + 1]));
+    float t = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&t, h->prof_events[2 * i], h->prof_events[2 * i + 1]));
+    int cls = h->prof_cls[i];
+    ms[cls] += t;
+    flops[cls] += h->prof_flops[i];
+    bytes[cls] += h->prof_bytes[i];
+    launches[cls] += (cls == KC_RECON) ? 2 : 1;
+  }
+  h->prof_mask = 0;
+  h->prof_used = 0;
+  h->prof_cls.clear();
+  h->prof_flops.clear();
+  h->prof_bytes.clear();
+  return MTB_OK;
+}
+
+int mtb_num_kernel_classes(void) { return KC_COUNT; }
+const char* mtb_kernel_class_name(int cls) { return (cls >= 0 && cls < KC_COUNT) ? kKClassNames[cls] : ""; }
 
 int64_t mtb_last_launch_count(const mtb_handle* h) { return h ? h->launches : 0; }
 double mtb_backbone_flops_per_crop(const mtb_handle* h) { return h ? h->flops_per_crop : 0.0; }

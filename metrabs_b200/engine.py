@@ -190,6 +190,21 @@ class Engine:
                                       ws.numel(), _stream_ptr(self.device)), self._h)
         return out
 
+    def profile_begin(self, classes=None):
+        """Brackets every launch of the selected kernel classes (None = all) with CUDA events on the launch stream."""
+        n = lib().mtb_num_kernel_classes()
+        mask = (1 << n) - 1 if classes is None else sum(1 << c for c in classes)
+        check(lib().mtb_profile_begin(self._h, mask), self._h)
+
+    def profile_end(self):
+        """-> {class name: dict(ms, flops, bytes, launches)} for the classes that launched."""
+        n = lib().mtb_num_kernel_classes()
+        ms, fl, by = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+        la = (C.c_int64 * n)()
+        check(lib().mtb_profile_end(self._h, ms, fl, by, la), self._h)
+        return {lib().mtb_kernel_class_name(i).decode(): dict(cls=i, ms=ms[i], flops=fl[i], bytes=by[i], launches=la[i])
+                for i in range(n) if la[i] > 0}
+
     @property
     def last_launch_count(self):
         return int(lib().mtb_last_launch_count(self._h))

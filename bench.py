@@ -128,10 +128,58 @@ def synthetic(batch, side, seed):
     return crops, k
 
 
+def effective_cores():
+    """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota (a container that
+    reports 128 logical CPUs but is throttled to a few makes torch-cpu oversubscribe badly)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        with open('/sys/fs/cgroup/cpu.max') as f:
+            quota, period = f.read().split()
+        if quota != 'max':
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        try:
+            with open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us') as f:
+                quota = int(f.read())
+            with open('/sys/fs/cgroup/cpu/cpu.cfs_period_us') as f:
+                period = int(f.read())
+            if quota > 0:
+                n = max(1, min(n, int(quota / period + 0.5)))
+        except Exception:
+            pass
+    return n
+
+
+def best_thread_count():
+    """All the host threads torch-cpu can actually USE: probes a small forward at a few thread counts and keeps the
+    fastest (on shared hosts 'all logical CPUs' can be 100x slower than a moderate count)."""
+    import argparse as _ap
+    from oracle import port
+    eff = effective_cores()
+    cands = sorted({eff, min(eff, 64), min(eff, 32), min(eff, 16), min(eff, 8)}, reverse=True)
+    pa = _ap.Namespace(size='s', side=128, joints=24, precision='fp32')
+    model = build_model(pa, None)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    pcfg = port.PathConfig(proc_side=128)
+    spec = port.effnet_spec(NAMES['s'])
+    crops, k = synthetic(2, 128, 0)
+    best, best_t = cands[-1], float('inf')
+    with torch.inference_mode():
+        for n in cands:
+            torch.set_num_threads(n)
+            port.metrabs_forward(sd, spec, pcfg, 24, crops, k)
+            t0 = time.perf_counter()
+            port.metrabs_forward(sd, spec, pcfg, 24, crops, k)
+            dt = time.perf_counter() - t0
+            if dt < best_t:
+                best, best_t = n, dt
+    return best
+
+
 def cpu_reference_forward(args, n_crops, iters, warmup):
     """The reference's CPU path (oracle port, torch-cpu fp32, all host threads) on `n_crops` synthetic crops."""
     from oracle import port
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(best_thread_count())
     model = build_model(args, None)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     pcfg = port.PathConfig(proc_side=args.side)

@@ -50,7 +50,10 @@ typedef enum { MTB_ARCH_EFFNET = 0, MTB_ARCH_RESNET50 = 1, MTB_ARCH_MOBILENETV3_
 /* Arithmetic of the conv/GEMM kernels.  FP32: CUDA-core fp32 FMA everywhere (the 1e-3 parity mode).
  * BF16_TC: bf16 operands on tcgen05 tensor cores with fp32 accumulation in TMEM, bf16 activations in HBM
  * (the throughput mode; the reference itself deploys under fp16 autocast, multiperson_model.py:241). */
-typedef enum { MTB_PRECISION_FP32 = 0, MTB_PRECISION_BF16_TC = 1 } mtb_precision;
+typedef enum { MTB_PRECISION_FP32 = 0, MTB_PRECISION_BF16_TC = 1,
+               /* verification mode: same bf16 storage and bf16-rounded weights as BF16_TC, but every conv on CUDA
+                * cores (fp32 FMA) - lets tests separate tensor-core kernel bugs from bf16 rounding effects */
+               MTB_PRECISION_BF16_SIMT = 2 } mtb_precision;
 
 /* Layout of a logits tensor handed to the standalone soft-argmax. */
 typedef enum {
@@ -158,6 +161,14 @@ const char* mtb_op_name(const mtb_handle* h, int op);
 int mtb_debug_run_ops(mtb_handle* h, const float* crops, int batch, int n_ops, float* out, size_t out_floats,
                       void* workspace, size_t workspace_bytes, void* stream);
 int mtb_op_output_shape(const mtb_handle* h, int op, int* height, int* width, int* channels);
+int mtb_op_input_shape(const mtb_handle* h, int op, int* height, int* width, int* channels, int* has_residual,
+                       int* has_scale);
+/* Runs ONE backbone op in isolation on caller-provided fp32 NHWC device tensors (converted to the handle's
+ * storage type): in [B,Hin,Win,Cin] (the stem takes NCHW crops), optional residual [B,Hout,Wout,Cout] and
+ * squeeze-excitation scale [B,Cin]; out receives [B,Hout,Wout,Cout] as fp32.  Lets tests compare the tcgen05
+ * kernels with the CUDA-core kernels on identical inputs. */
+int mtb_debug_run_op(mtb_handle* h, int op_index, const float* in, const float* res, const float* scale, int batch,
+                     float* out, size_t out_floats, void* workspace, size_t workspace_bytes, void* stream);
 /* CUDA-event profiler (bench.py's live roofline measurement): between begin and end, every kernel launch of the
  * classes selected by `class_mask` (bit i = class i) is bracketed by cudaEventRecord on the launching stream.
  * mtb_profile_end synchronises those events and returns, per class, the summed device time (ms), algorithmic

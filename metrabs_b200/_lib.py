@@ -7,7 +7,7 @@ MTB_ABI_VERSION = 1
 MTB_MAX_STAGES = 16
 
 ARCH_EFFNET, ARCH_RESNET50, ARCH_MOBILENETV3_SMALL, ARCH_HEAD_ONLY = 0, 1, 2, 3
-PRECISION_FP32, PRECISION_BF16_TC = 0, 1
+PRECISION_FP32, PRECISION_BF16_TC, PRECISION_BF16_SIMT = 0, 1, 2
 DTYPE_F32, DTYPE_BF16, DTYPE_F16, DTYPE_I64 = 0, 1, 2, 3
 LAYOUT_BDJHW, LAYOUT_BHWN = 0, 1
 
@@ -62,6 +62,10 @@ _SIGNATURES = {
                                     C.c_size_t, C.c_void_p]),
     'mtb_op_output_shape': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.POINTER(C.c_int)]),
+    'mtb_op_input_shape': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'mtb_debug_run_op': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                   C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     'mtb_profile_begin': (C.c_int, [C.c_void_p, C.c_uint]),
     'mtb_profile_end': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                   C.POINTER(C.c_int64)]),

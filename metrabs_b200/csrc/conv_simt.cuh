@@ -14,6 +14,9 @@ struct ConvParams {
   const float* w;        // [R*S*Cin][Cout]  (k = (r*S+s)*Cin + c)
   const float* bias;     // [Cout]
   const float* a_scale;  // optional per-(b,cin) multiplier of the input (squeeze-excitation), [B][Cin]
+  const float* a_bias = nullptr;  // optional per-cin bias + activation applied to the input on load (the producer was a
+  int a_act = 0;                  //   split-K GEMM that left raw sums: squeeze-excitation fc1 -> fc2)
+  int ksplit = 1;                 // > 1: blockIdx.z owns a K slice and atomically adds raw sums into a zeroed fp32 output
   int B, Hin, Win, Cin, Hout, Wout, Cout, R, S, stride, dil, pad_t, pad_l, act;
 };
 
@@ -66,7 +69,9 @@ conv_igemm_kernel(ConvParams p) {
   }
 
   const int cchunks = (p.Cin + BK - 1) / BK;
-  const int T = p.R * p.S * cchunks;
+  const int T_all = p.R * p.S * cchunks;
+  const int t_begin = (int)((long long)T_all * blockIdx.z / p.ksplit);
+  const int T = (int)((long long)T_all * (blockIdx.z + 1) / p.ksplit);
 
   float4 ra[A_LD], rb[B_LD];
   auto load_tile = [&](int t) {
@@ -84,6 +89,11 @@ conv_igemm_kernel(ConvParams p) {
         if (p.a_scale) {
           float4 sc = *reinterpret_cast<const float4*>(p.a_scale + (size_t)a_b[i] * p.Cin + c);
           v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+        }
+        if (p.a_bias) {
+          float4 ab = *reinterpret_cast<const float4*>(p.a_bias + c);
+          v.x = apply_act(v.x + ab.x, p.a_act); v.y = apply_act(v.y + ab.y, p.a_act);
+          v.z = apply_act(v.z + ab.z, p.a_act); v.w = apply_act(v.w + ab.w, p.a_act);
         }
       }
       ra[i] = v;
@@ -117,10 +127,12 @@ conv_igemm_kernel(ConvParams p) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  load_tile(0);
-  store_tile();
+  if (t_begin < T) {
+    load_tile(t_begin);
+    store_tile();
+  }
   __syncthreads();
-  for (int t = 0; t < T; ++t) {
+  for (int t = t_begin; t < T; ++t) {
     if (t + 1 < T) load_tile(t + 1);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
@@ -160,6 +172,16 @@ conv_igemm_kernel(ConvParams p) {
       for (int gj = 0; gj < GN; ++gj) {
         int n = n0 + tx * 4 + gj * GSN;
         if (n >= p.Cout) continue;
+        if (p.ksplit > 1) {  // raw partial sums; bias/activation are applied by the consumer (a_bias / a_act)
+          if constexpr (sizeof(TOut) == 4) {
+            float* o = reinterpret_cast<float*>(out) + (size_t)m * p.Cout + n;
+            atomicAdd(o + 0, acc[gi * 4 + i][gj * 4 + 0]);
+            atomicAdd(o + 1, acc[gi * 4 + i][gj * 4 + 1]);
+            atomicAdd(o + 2, acc[gi * 4 + i][gj * 4 + 2]);
+            atomicAdd(o + 3, acc[gi * 4 + i][gj * 4 + 3]);
+          }
+          continue;
+        }
         float4 bv = *reinterpret_cast<const float4*>(p.bias + n);
         float4 v;
         v.x = apply_act(acc[gi * 4 + i][gj * 4 + 0] + bv.x, p.act);
@@ -343,7 +365,7 @@ inline cudaError_t launch_conv_igemm(const ConvParams& p, cudaStream_t st) {
     dim3 grid((M + 127) / 128, (p.Cout + 63) / 64);
     conv_igemm_kernel<128, 64, 8, 4, TIn, TOut><<<grid, 256, 0, st>>>(p);
   } else {
-    dim3 grid((M + 63) / 64, (p.Cout + 63) / 64);
+    dim3 grid((M + 63) / 64, (p.Cout + 63) / 64, p.ksplit);
     conv_igemm_kernel<64, 64, 4, 4, TIn, TOut><<<grid, 256, 0, st>>>(p);
   }
   return cudaGetLastError();

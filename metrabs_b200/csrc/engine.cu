@@ -51,6 +51,9 @@ struct Op {
   int R = 1, S = 1, stride = 1, dil = 1, pad_t = 0, pad_l = 0, act = ACT_NONE;
   bool depthwise = false;
   bool small_io = false;  // squeeze-excitation FCs on [B,1,1,C] fp32 tensors
+  int ksplit = 1;          // split-K (squeeze-excitation fc1): raw sums, bias/act deferred to the consumer
+  int a_bias_from = -1;    // op index whose bias (+ a_act) is applied to THIS op's input on load
+  int a_act = ACT_NONE;
   bool pad_ok = false;    // weight tensor may be smaller than [Cout,Cin]: channels zero-padded to a multiple of 4
   float bn_eps = 1e-3f;
   float* d_w = nullptr;     // fp32 [R*S*Cin][Cout]  (dw: [R*S][C])
@@ -112,7 +115,8 @@ int fail(const mtb_handle* h, int code, const char* fmt, ...) {
   } while (0)
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-inline size_t elem_size(const mtb_handle* h) { return h->cfg.precision == MTB_PRECISION_BF16_TC ? 2 : 4; }
+inline bool is_bf16(const mtb_handle* h) { return h->cfg.precision != MTB_PRECISION_FP32; }
+inline size_t elem_size(const mtb_handle* h) { return is_bf16(h) ? 2 : 4; }
 
 // ------------------------------------------------------------------------------------------- plan building
 struct Planner {
@@ -227,12 +231,15 @@ void plan_effnet(mtb_handle* h) {
           f1.Cin = cexp; f1.Cout = csq; f1.act = ACT_SILU; f1.small_io = true; f1.pad_ok = true;
           f1.in_buf = BUF_SMALL0; f1.out_buf = BUF_SMALL0 + 1;
           f1.flops = 2.0 * cexp * csq_real;
+          f1.ksplit = std::min(32, std::max(1, cexp / 64));  // K = cexp is long and M = batch is short: split K over CTAs
           h->ops.push_back(f1);
+          const int f1_index = (int)h->ops.size() - 1;
           Op f2;
           f2.type = OP_CONV; f2.name = se + ".fc2"; f2.wkey = se + ".fc2.weight"; f2.biaskey = se + ".fc2.bias";
           f2.Cin = csq; f2.Cout = cexp; f2.act = ACT_SIGMOID; f2.small_io = true; f2.pad_ok = true;
           f2.in_buf = BUF_SMALL0 + 1; f2.out_buf = BUF_SMALL0 + 2;
           f2.flops = 2.0 * cexp * csq_real;
+          if (f1.ksplit > 1) { f2.a_bias_from = f1_index; f2.a_act = ACT_SILU; }
           h->ops.push_back(f2);
           P.max_small = std::max(P.max_small, cexp);
         }
@@ -345,12 +352,14 @@ int prepare_op_weights(mtb_handle* h, Op& op) {
           wk[((size_t)(r * op.S + s) * cin_g + c) * op.Cout + n] = (float)v;
         }
   }
+  const bool tc_like = tc_eligible(op.type == OP_CONV, op.depthwise, op.small_io, op.R, op.stride, op.Cin, op.Cout);
+  if (is_bf16(h) && tc_like)  // both bf16 modes see the same bf16-rounded GEMM weights
+    for (float& v : wk) v = __bfloat162float(host_bf16(v));
   int rc = upload(h, wk.data(), wk.size() * 4, (void**)&op.d_w);
   if (rc) return rc;
   rc = upload(h, bias.data(), bias.size() * 4, (void**)&op.d_bias);
   if (rc) return rc;
-  if (h->cfg.precision == MTB_PRECISION_BF16_TC && tc_eligible(op.type == OP_CONV, op.depthwise, op.small_io, op.R,
-                                                               op.stride, op.Cin, op.Cout)) {
+  if (h->cfg.precision == MTB_PRECISION_BF16_TC && tc_like && !tc_disabled()) {
     const char* e = tc_prepare_weights(op.tc, wk.data(), bias.data(), K, op.Cout, op.R, op.S, op.Cin, h->dev_allocs);
     if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 weight prep for '%s': %s", op.name.c_str(), e);
   }
@@ -375,7 +384,7 @@ Workspace layout(const mtb_handle* h, int B, void* base) {
   const size_t P = (size_t)h->feat_side * h->feat_side;
   w.off_features = o; o += align_up(P * h->feat_c * B * es, 1024);
   const int N = (h->cfg.n_joints * (1 + h->cfg.depth) + 3) / 4 * 4;
-  w.off_logits = o; o += align_up(P * N * B * 4, 1024);
+  w.off_logits = o; o += align_up(std::max<size_t>(P, 4) * N * B * 4, 1024);  // also the fused head's state scratch
   w.off_c2d = o; o += align_up((size_t)B * h->cfg.n_joints * 2 * 4, 1024);
   w.off_c3d = o; o += align_up((size_t)B * h->cfg.n_joints * 3 * 4, 1024);
   w.off_n2d = o; o += align_up((size_t)B * h->cfg.n_joints * 2 * 4, 1024);
@@ -477,9 +486,22 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
         size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
         maxpool_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
       } else if (op.small_io) {
+        if (op.ksplit > 1) {
+          p.ksplit = op.ksplit;
+          cudaMemsetAsync(p.out, 0, (size_t)B * op.Cout * 4, st);
+        }
+        if (op.a_bias_from >= 0) {
+          p.a_bias = h->ops[op.a_bias_from].d_bias;
+          p.a_act = op.a_act;
+        }
         cudaError_t e = launch_conv_igemm<float, float>(p, st);
         if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "launch %s: %s", op.name.c_str(), cudaGetErrorString(e));
       } else if (op.tc.ready) {
+        if (op.scale_buf != BUF_NONE) {  // squeeze-excitation scale applied in place ahead of the tensor-core projection
+          const char* e = tc_se_scale_launch(const_cast<void*>(p.in), p.a_scale, B, op.Hin * op.Win, op.Cin, st);
+          if (e) return fail(h, MTB_ERR_CUDA, "se scale %s: %s", op.name.c_str(), e);
+          h->launches++;
+        }
         const char* e = tc_conv_launch(op.tc, p, st);
         if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 launch %s: %s", op.name.c_str(), e);
       } else {
@@ -503,7 +525,7 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
 }
 
 int run_op(mtb_handle* h, const Op& op, const float* crops, int B, const Workspace& ws, void* features, cudaStream_t st) {
-  if (h->cfg.precision == MTB_PRECISION_BF16_TC) return run_op_t<__nv_bfloat16>(h, op, crops, B, ws, features, st);
+  if (is_bf16(h)) return run_op_t<__nv_bfloat16>(h, op, crops, B, ws, features, st);
   return run_op_t<float>(h, op, crops, B, ws, features, st);
 }
 
@@ -558,9 +580,9 @@ int head_decode_impl(mtb_handle* h, const void* features, int B, float* c2d, flo
     // fused: 1x1-conv GEMM on tcgen05 with the soft-argmax reduction in the epilogue; logits never reach HBM
     ProfScope prof(h, KC_HEAD_FUSED, op.flops * B, feat_bytes + (double)op.Cin * op.Cout * 2 + out_bytes, st);
     const char* e = tc_head_launch(op.tc, features, B, h->feat_side, h->feat_side, c.n_joints, c.depth, make_scale(c),
-                                   c2d, c3d, st);
+                                   c2d, c3d, ws.base + ws.off_logits, st);
     if (e) return fail(h, MTB_ERR_CUDA, "fused head: %s", e);
-    h->launches++;
+    h->launches += 2;
     return MTB_OK;
   }
   ConvParams p;
@@ -572,7 +594,7 @@ int head_decode_impl(mtb_handle* h, const void* features, int B, float* c2d, flo
   cudaError_t e;
   {
     ProfScope prof(h, KC_HEAD_CONV_SIMT, op.flops * B, feat_bytes + (double)op.Cin * op.Cout * 4 + logit_bytes, st);
-    e = c.precision == MTB_PRECISION_BF16_TC ? launch_conv_igemm<__nv_bfloat16, float>(p, st)
+    e = is_bf16(h) ? launch_conv_igemm<__nv_bfloat16, float>(p, st)
                                              : launch_conv_igemm<float, float>(p, st);
   }
   if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "head conv: %s", cudaGetErrorString(e));
@@ -608,6 +630,11 @@ __global__ void to_float_kernel(const __nv_bfloat16* in, float* out, size_t n) {
     out[i] = __bfloat162float(in[i]);
 }
 
+__global__ void from_float_kernel(const float* in, __nv_bfloat16* out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) {
@@ -640,7 +667,7 @@ int mtb_create(const mtb_config* cfg, mtb_handle** out) {
                 cfg->depth, cfg->proc_side, cfg->stride_test);
   if (cfg->arch == MTB_ARCH_EFFNET && (cfg->n_stages <= 0 || cfg->n_stages > MTB_MAX_STAGES))
     return fail(nullptr, MTB_ERR_INVALID_ARG, "n_stages out of range");
-  if (cfg->precision != MTB_PRECISION_FP32 && cfg->precision != MTB_PRECISION_BF16_TC)
+  if (cfg->precision < MTB_PRECISION_FP32 || cfg->precision > MTB_PRECISION_BF16_SIMT)
     return fail(nullptr, MTB_ERR_INVALID_ARG, "unknown precision %d", cfg->precision);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -743,8 +770,17 @@ int mtb_finalize_weights(mtb_handle* h) {
     int rc = prepare_op_weights(h, hd);
     if (rc) return rc;
     if (h->cfg.precision == MTB_PRECISION_BF16_TC) {
-      const char* e = tc_prepare_head(hd.tc, w->data.data(), find(h, hd.biaskey)->data.data(), hd.Cin, n_real, h->dev_allocs);
-      if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 head weight prep: %s", e);
+      int bnp, cpt, npt;
+      if (tc_head_plan(h->feat_side * h->feat_side, &bnp, &cpt, &npt)) {
+        // the ORIGINAL (unpadded) [n_real][C] weight: the fused kernel masks rows itself
+        std::vector<float> w0((size_t)n_real * hd.Cin), b0(n_real);
+        for (int n = 0; n < n_real; ++n) {
+          b0[n] = find(h, hd.biaskey)->data[n];
+          for (int cc = 0; cc < hd.Cin; ++cc) w0[(size_t)n * hd.Cin + cc] = w->data[(size_t)n * hd.Cin + cc];
+        }
+        const char* e = tc_prepare_head(hd.tc, w0.data(), b0.data(), hd.Cin, n_real, h->dev_allocs);
+        if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 head weight prep: %s", e);
+      }
     }
   }
   h->raw.clear();
@@ -989,7 +1025,7 @@ int mtb_debug_run_ops(mtb_handle* h, const float* crops, int batch, int n_ops, f
   size_t n = (size_t)batch * (small ? 1 : (size_t)o.Hout * o.Wout) * o.Cout;
   if (n > out_floats) return fail(h, MTB_ERR_INVALID_ARG, "debug output buffer too small (%zu > %zu)", n, out_floats);
   void* src = buf_ptr(ws, o.out_buf, features);
-  if (small || h->cfg.precision == MTB_PRECISION_FP32) {
+  if (small || !is_bf16(h)) {
     CUDA_TRY(h, cudaMemcpyAsync(out, src, n * 4, cudaMemcpyDeviceToDevice, st));
   } else {
     to_float_kernel<<<grid_for(n, 256), 256, 0, st>>>((const __nv_bfloat16*)src, out, n);
@@ -1031,6 +1067,59 @@ int mtb_profile_end(mtb_handle* h, double* ms, double* flops, double* bytes, int
 
 int mtb_num_kernel_classes(void) { return KC_COUNT; }
 const char* mtb_kernel_class_name(int cls) { return (cls >= 0 && cls < KC_COUNT) ? kKClassNames[cls] : ""; }
+
+int mtb_op_input_shape(const mtb_handle* h, int op, int* height, int* width, int* channels, int* has_residual, int* has_scale) {
+  if (!h || op < 0 || op >= (int)h->ops.size()) return fail(h, MTB_ERR_INVALID_ARG, "op index out of range");
+  const Op& o = h->ops[op];
+  if (height) *height = o.Hin;
+  if (width) *width = o.Win;
+  if (channels) *channels = o.Cin;
+  if (has_residual) *has_residual = o.res_buf != BUF_NONE;
+  if (has_scale) *has_scale = o.scale_buf != BUF_NONE;
+  return MTB_OK;
+}
+
+int mtb_debug_run_op(mtb_handle* h, int op_index, const float* in, const float* res, const float* scale, int batch,
+                     float* out, size_t out_floats, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(h, batch, workspace_bytes, workspace);
+  if (rc) return rc;
+  if (op_index < 0 || op_index >= (int)h->ops.size() || !in || !out) return fail(h, MTB_ERR_INVALID_ARG, "invalid debug arguments");
+  DeviceGuard g(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws = layout(h, batch, workspace);
+  Op o = h->ops[op_index];  // copy with overridden buffers
+  const bool small = o.type == OP_POOL || o.small_io;
+  const size_t n_in = (size_t)batch * o.Hin * o.Win * o.Cin;
+  const size_t n_out = (size_t)batch * (o.type == OP_POOL ? 1 : (size_t)o.Hout * o.Wout) * o.Cout;
+  if (n_out > out_floats) return fail(h, MTB_ERR_INVALID_ARG, "debug output buffer too small");
+  if ((o.res_buf != BUF_NONE) != (res != nullptr) || (o.scale_buf != BUF_NONE) != (scale != nullptr))
+    return fail(h, MTB_ERR_INVALID_ARG, "op %d: residual/scale inputs do not match the op (see mtb_op_input_shape)", op_index);
+  auto put = [&](const float* src, int buf, size_t n, bool as_f32) {
+    void* dst = buf_ptr(ws, buf, nullptr);
+    if (as_f32 || !is_bf16(h)) cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, st);
+    else from_float_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, (__nv_bfloat16*)dst, n);
+  };
+  const float* crops = nullptr;
+  if (o.type == OP_STEM) {
+    crops = in;
+  } else if (o.small_io) {
+    o.in_buf = BUF_SMALL0;
+    put(in, o.in_buf, n_in, true);
+  } else {
+    o.in_buf = 0;
+    put(in, 0, n_in, false);
+  }
+  if (res) { o.res_buf = 1; put(res, 1, n_out, false); }
+  if (scale) { o.scale_buf = BUF_SMALL0 + 2; put(scale, o.scale_buf, (size_t)batch * o.Cin, true); }
+  o.out_buf = (o.type == OP_POOL || o.small_io) ? BUF_SMALL0 + 1 : 2;
+  o.tc.cached_in = nullptr;  // the copy must not reuse a tensor map encoded for other buffers
+  rc = run_op(h, o, crops, batch, ws, nullptr, st);
+  if (rc) return rc;
+  void* src = buf_ptr(ws, o.out_buf, nullptr);
+  if (small || !is_bf16(h)) CUDA_TRY(h, cudaMemcpyAsync(out, src, n_out * 4, cudaMemcpyDeviceToDevice, st));
+  else to_float_kernel<<<grid_for(n_out, 256), 256, 0, st>>>((const __nv_bfloat16*)src, out, n_out);
+  return MTB_OK;
+}
 
 int64_t mtb_last_launch_count(const mtb_handle* h) { return h ? h->launches : 0; }
 double mtb_backbone_flops_per_crop(const mtb_handle* h) { return h ? h->flops_per_crop : 0.0; }

@@ -1,6 +1,23 @@
-// tcgen05 tensor-core path (placeholder until the GEMM kernels land): nothing is eligible, so BF16_TC mode runs
-// the CUDA-core kernels over bf16 storage.
+// tcgen05 tensor-core path (sm_100a): bf16 operands staged by TMA into 128B-swizzled shared memory, fp32
+// accumulators in TMEM, warp-specialised persistent kernels.
+//
+//   tc_conv_kernel   1x1 conv == GEMM  D[pixels, Cout] = A[pixels, Cin] * W[Cout, Cin]^T          (mode 0, 2D TMA)
+//                    3x3 stride-1 conv as implicit GEMM: per tap (r,s) the A tile is a shifted [8 x 16] pixel box
+//                    of the NHWC input fetched by a 4D TMA (out-of-bounds = the reference's explicit zero padding,
+//                    backbones/efficientnet.py:1127-1161)                                            (mode 1)
+//                    epilogue: TMEM -> registers, + folded-BN bias, SiLU, + residual, bf16 NHWC store.
+//   tc_head_kernel   MetrabsHeads (models/metrabs.py:75-85): swapped operands, D[channel, pixel] = W[N, C] * F^T,
+//                    so every epilogue thread owns one (d,j) channel and reduces its pixels in registers: the
+//                    J x D x H x W logits never leave the SM.
+//
+// Descriptor encodings follow the sm_100 UMMA formats (cute/arch/mma_sm100_desc.hpp in the vendored CUTLASS tree).
 #pragma once
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -9,14 +26,776 @@
 
 namespace mtb {
 
-struct TcWeights {
-  bool ready = false;
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug (wrong expect_tx bytes, missing commit) traps after ~seconds instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz
+      printf("metrabs_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread for the CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns: thread i of the warp gets TMEM lane (base_lane + i).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzled operand tile: rows of 64 bf16 (128 B); 8-row groups are 1024 B apart (SBO); LBO unused.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address, bits [0,14)
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                       // layout type: SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n.
+__host__ __device__ inline uint32_t umma_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------- conv/GEMM kernel
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4, TC_MAX_BN = 256;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;       // 16 KB
+constexpr int TC_B_BYTES = TC_MAX_BN * TC_BK * 2;   // 32 KB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_TILE_W = 16, TC_TILE_H = 8;        // spatial M tile of the 3x3 mode (16 x 8 = 128 pixels)
+
+struct TcConvParams {
+  void* out;
+  const void* res;
+  const float* bias;
+  int mode;     // 0: flat 1x1 (rows = B*H*W), 1: 3x3 stride 1 (spatial tiles)
+  int M;        // mode 0: number of rows
+  int Cout, Cin;
+  int bn, n_tiles, m_tiles, kchunks, taps;
+  int act;
+  int Hout, Wout, tiles_w, tiles_h, pad_t, pad_l, S;
+  uint32_t idesc;
 };
 
-inline bool tc_eligible(bool is_conv, bool depthwise, bool small_io, int k, int stride, int cin, int cout) { return false; }
-inline const char* tc_prepare_weights(TcWeights&, const float*, const float*, int, int, int, int, int, std::vector<void*>&) { return nullptr; }
-inline const char* tc_prepare_head(TcWeights&, const float*, const float*, int, int, std::vector<void*>&) { return nullptr; }
-inline const char* tc_conv_launch(const TcWeights&, const ConvParams&, cudaStream_t) { return "not built"; }
-inline const char* tc_head_launch(const TcWeights&, const void*, int, int, int, int, int, DecodeScale, float*, float*, cudaStream_t) { return "not built"; }
+__global__ void __launch_bounds__(256, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B needs 1024 B alignment
+  uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full = bars;                     // [TC_STAGES]
+  uint64_t* empty = bars + TC_STAGES;        // [TC_STAGES]
+  uint64_t* tmem_full = bars + 2 * TC_STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int num_kb = p.taps * p.kchunks;
+  const uint32_t stage_tx = TC_A_BYTES + (uint32_t)p.bn * TC_BK * 2;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m_blk = t / p.n_tiles, n_blk = t - m_blk * p.n_tiles;
+        int b = 0, oh0 = 0, ow0 = 0;
+        if (p.mode == 1) {
+          int tw = m_blk % p.tiles_w;
+          int th = (m_blk / p.tiles_w) % p.tiles_h;
+          b = m_blk / (p.tiles_w * p.tiles_h);
+          oh0 = th * TC_TILE_H - p.pad_t;
+          ow0 = tw * TC_TILE_W - p.pad_l;
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * TC_STAGE_BYTES;
+          uint8_t* sb = sa + TC_A_BYTES;
+          mbar_expect_tx(&full[stage], stage_tx);
+          if (p.mode == 0) {
+            tma_load_2d(sa, &tmA, &full[stage], kc * TC_BK, m_blk * TC_BM);
+          } else {
+            const int r = tap / p.S, s = tap - r * p.S;
+            tma_load_4d(sa, &tmA, &full[stage], kc * TC_BK, ow0 + s, oh0 + r, b);
+          }
+          tma_load_2d(sb, &tmB, &full[stage], tap * p.Cin + kc * TC_BK, n_blk * p.bn);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one elected thread) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_MAX_BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
+          const uint32_t sb = sa + TC_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            umma_bf16(d_tmem, umma_smem_desc(sa + k * 32), umma_smem_desc(sb + k * 32), p.idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) = tile rows =====
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    __nv_bfloat16* __restrict__ out = (__nv_bfloat16*)p.out;
+    const __nv_bfloat16* __restrict__ res = (const __nv_bfloat16*)p.res;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m_blk = t / p.n_tiles, n_blk = t - m_blk * p.n_tiles;
+      bool valid;
+      size_t off;
+      if (p.mode == 0) {
+        int m = m_blk * TC_BM + row;
+        valid = m < p.M;
+        off = (size_t)m * p.Cout;
+      } else {
+        int tw = m_blk % p.tiles_w;
+        int th = (m_blk / p.tiles_w) % p.tiles_h;
+        int b = m_blk / (p.tiles_w * p.tiles_h);
+        int oh = th * TC_TILE_H + row / TC_TILE_W, ow = tw * TC_TILE_W + row % TC_TILE_W;
+        valid = oh < p.Hout && ow < p.Wout;
+        off = ((size_t)(b * p.Hout + oh) * p.Wout + ow) * p.Cout;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_MAX_BN;
+      const int n0 = n_blk * p.bn;
+      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        const int n = n0 + c0;
+        if (valid && n < p.Cout) {  // Cout % 8 == 0: 8-column groups are all-or-nothing
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const int ng = n + g * 8;
+            if (ng < p.Cout) {
+              float4 b0 = *reinterpret_cast<const float4*>(p.bias + ng);
+              float4 b1 = *reinterpret_cast<const float4*>(p.bias + ng + 4);
+              float o[8];
+              o[0] = apply_act(v[g * 8 + 0] + b0.x, p.act); o[1] = apply_act(v[g * 8 + 1] + b0.y, p.act);
+              o[2] = apply_act(v[g * 8 + 2] + b0.z, p.act); o[3] = apply_act(v[g * 8 + 3] + b0.w, p.act);
+              o[4] = apply_act(v[g * 8 + 4] + b1.x, p.act); o[5] = apply_act(v[g * 8 + 5] + b1.y, p.act);
+              o[6] = apply_act(v[g * 8 + 6] + b1.z, p.act); o[7] = apply_act(v[g * 8 + 7] + b1.w, p.act);
+              if (res) {
+                uint4 rv = *reinterpret_cast<const uint4*>(res + off + ng);
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  float2 f = __bfloat1622float2(r2[i]);
+                  o[2 * i] += f.x;
+                  o[2 * i + 1] += f.y;
+                }
+              }
+              uint4 ov;
+              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+              *reinterpret_cast<uint4*>(out + off + ng) = ov;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// in-place squeeze-excitation scaling  x[b,p,c] *= s[b,c]  ahead of a tcgen05 projection GEMM
+__global__ void __launch_bounds__(256) se_scale_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ s, int P, int C,
+                                                       size_t total8) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (size_t)gridDim.x * blockDim.x) {
+    size_t e = i * 8;
+    int c = (int)(e % C);
+    int b = (int)(e / ((size_t)P * C));
+    uint4 v = *reinterpret_cast<uint4*>(x + e);
+    __nv_bfloat162* v2 = reinterpret_cast<__nv_bfloat162*>(&v);
+    const float4 s0 = *reinterpret_cast<const float4*>(s + (size_t)b * C + c);
+    const float4 s1 = *reinterpret_cast<const float4*>(s + (size_t)b * C + c + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = __bfloat1622float2(v2[k]);
+      v2[k] = __floats2bfloat162_rn(f.x * sc[2 * k], f.y * sc[2 * k + 1]);
+    }
+    *reinterpret_cast<uint4*>(x + e) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline tmap_encode_fn get_tmap_encode() {
+  static tmap_encode_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (tmap_encode_fn)p;
+  }
+  return fn;
+}
+
+// rank-2 bf16 tensor [rows][cols] (cols contiguous), box [box_rows][64], 128B swizzle, OOB -> 0
+inline const char* make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  tmap_encode_fn enc = get_tmap_encode();
+  if (!enc) return "cuTensorMapEncodeTiled unavailable";
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {TC_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(2d) failed";
+}
+// rank-4 bf16 NHWC tensor [B][H][W][C], box [1][TILE_H][TILE_W][64]
+inline const char* make_tmap_nhwc(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C) {
+  tmap_encode_fn enc = get_tmap_encode();
+  if (!enc) return "cuTensorMapEncodeTiled unavailable";
+  cuuint64_t dims[4] = {C, W, H, B};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {TC_BK, TC_TILE_W, TC_TILE_H, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(4d) failed";
+}
+
+struct TcWeights {
+  bool ready = false;
+  __nv_bfloat16* d_w = nullptr;  // [Cout][taps*Cin] K-major
+  float* d_bias = nullptr;       // [Cout]
+  int Cout = 0, Cin = 0, taps = 1, S = 1;
+  // head
+  int n_real = 0;
+  // per-shape launch state (A tensor map depends on the activation pointer and batch)
+  mutable CUtensorMap mapA, mapB;
+  mutable const void* cached_in = nullptr;
+  mutable int cached_B = -1, cached_bn = 0;
+};
+
+inline bool tc_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTB_DISABLE_TC");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+inline bool tc_eligible(bool is_conv, bool depthwise, bool small_io, int k, int stride, int cin, int cout) {
+  if (!is_conv || depthwise || small_io) return false;
+  if (cin % 8 != 0 || cout % 8 != 0) return false;
+  return stride == 1 && (k == 1 || k == 3);
+}
+
+inline __nv_bfloat16 host_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7FFFu + lsb;  // round to nearest even
+  uint16_t h = (uint16_t)(u >> 16);
+  __nv_bfloat16 out;
+  memcpy(&out, &h, 2);
+  return out;
+}
+
+// wk: fp32 [K = taps*Cin][Cout] (BN folded) -> bf16 [Cout][K]
+inline const char* tc_prepare_weights(TcWeights& w, const float* wk, const float* bias, int K, int cout, int R, int S, int cin,
+                                      std::vector<void*>& allocs) {
+  std::vector<__nv_bfloat16> t((size_t)K * cout);
+  for (int k = 0; k < K; ++k)
+    for (int n = 0; n < cout; ++n) t[(size_t)n * K + k] = host_bf16(wk[(size_t)k * cout + n]);
+  if (cudaMalloc((void**)&w.d_w, t.size() * 2) != cudaSuccess) return "cudaMalloc failed";
+  allocs.push_back(w.d_w);
+  if (cudaMemcpy(w.d_w, t.data(), t.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return "cudaMemcpy failed";
+  if (cudaMalloc((void**)&w.d_bias, (size_t)cout * 4) != cudaSuccess) return "cudaMalloc failed";
+  allocs.push_back(w.d_bias);
+  if (cudaMemcpy(w.d_bias, bias, (size_t)cout * 4, cudaMemcpyHostToDevice) != cudaSuccess) return "cudaMemcpy failed";
+  w.Cout = cout; w.Cin = cin; w.taps = R * S; w.S = S;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
+      return "cannot raise dynamic shared memory for tc_conv_kernel";
+    attr_set = true;
+  }
+  w.ready = true;
+  w.cached_in = nullptr;
+  w.cached_B = -1;
+  return nullptr;
+}
+
+inline int tc_pick_bn(int cout, int m_tiles, int num_kb) {
+  int best = 16;
+  double best_cost = 1e30;
+  for (int bn = 256; bn >= 16; bn -= 16) {
+    int nt = (cout + bn - 1) / bn;
+    long tiles = (long)m_tiles * nt;
+    long waves = (tiles + 147) / 148;
+    double cost = (double)waves * ((double)bn * (num_kb + 2) + 64.0);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, cudaStream_t st) {
+  TcConvParams q;
+  q.out = p.out; q.res = p.res; q.bias = w.d_bias;
+  q.mode = (p.R == 3) ? 1 : 0;
+  q.Cout = p.Cout; q.Cin = p.Cin; q.act = p.act;
+  q.taps = w.taps; q.S = w.S;
+  q.kchunks = (p.Cin + TC_BK - 1) / TC_BK;
+  q.Hout = p.Hout; q.Wout = p.Wout; q.pad_t = p.pad_t; q.pad_l = p.pad_l;
+  q.tiles_w = (p.Wout + TC_TILE_W - 1) / TC_TILE_W;
+  q.tiles_h = (p.Hout + TC_TILE_H - 1) / TC_TILE_H;
+  q.M = p.B * p.Hout * p.Wout;
+  q.m_tiles = q.mode == 0 ? (q.M + TC_BM - 1) / TC_BM : p.B * q.tiles_w * q.tiles_h;
+  const int bn = tc_pick_bn(p.Cout, q.m_tiles, q.taps * q.kchunks);
+  q.bn = bn;
+  q.n_tiles = (p.Cout + bn - 1) / bn;
+  q.idesc = umma_idesc_bf16(bn);
+  if (w.cached_in != p.in || w.cached_B != p.B || w.cached_bn != bn) {
+    const char* e = q.mode == 0 ? make_tmap_2d(&w.mapA, p.in, (uint64_t)q.M, (uint64_t)p.Cin, TC_BM)
+                                : make_tmap_nhwc(&w.mapA, p.in, p.B, p.Hin, p.Win, p.Cin);
+    if (e) return e;
+    e = make_tmap_2d(&w.mapB, w.d_w, (uint64_t)p.Cout, (uint64_t)w.taps * p.Cin, (uint32_t)bn);
+    if (e) return e;
+    w.cached_in = p.in;
+    w.cached_B = p.B;
+    w.cached_bn = bn;
+  }
+  const int total = q.m_tiles * q.n_tiles;
+  const int grid = total < 148 ? total : 148;
+  tc_conv_kernel<<<grid, 256, TC_SMEM_BYTES, st>>>(w.mapA, w.mapB, q);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+inline const char* tc_se_scale_launch(void* x, const float* s, int B, int P, int C, cudaStream_t st) {
+  size_t total8 = (size_t)B * P * C / 8;
+  se_scale_kernel<<<grid_for(total8, 256), 256, 0, st>>>((__nv_bfloat16*)x, s, P, C, total8);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+// ----------------------------------------------------------------------------------------- fused head kernel
+// MetrabsHeads.forward (models/metrabs.py:75-85) with ptu.soft_argmax (ptu.py:47-75) fused behind the 1x1 conv:
+//   D[n, pixel] = sum_c W[n, c] * F[pixel, c]        A = head weights [N_out][C] (M = channels, 128 per tile)
+//                                                     B = features     [B*P][C]  (N = pixels, <= 256 per MMA)
+// Epilogue thread <-> one channel n = J + d*J + j (or n = j < J for the 2D head): it adds the bias and keeps the
+// online-softmax state (max, sum e, sum e*x, sum e*y) of ITS pixels in registers, across the pixel tiles of a crop;
+// one float4 per (crop, channel) goes to a scratch, and head_finalize_kernel merges the D depth slices of every
+// joint (sum e*z = d * sum e), applies linspace(0,1,n) and heatmap_to_image / heatmap_to_metric.
+struct TcHeadParams {
+  float4* states;     // [B][n_out] (m, s, sx, sy)
+  const float* bias;  // [n_out]
+  int B, P, W, n_out, C;
+  int bnp;            // pixels per MMA (N)
+  int cpt;            // crops per tile when P <= 256, else 0
+  int npt;            // pixel tiles per crop when P > 256, else 1
+  int n_groups;       // crop groups
+  int m_tiles;        // ceil(n_out / 128)
+  int kblocks;        // ceil(C / 64)
+  uint32_t idesc;
+};
+
+__global__ void __launch_bounds__(256, 1)
+tc_head_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmF, const TcHeadParams p) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + TC_STAGES;
+  uint64_t* tmem_full = bars + 2 * TC_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmF);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int items = p.n_groups * p.m_tiles;
+  const uint32_t stage_tx = TC_A_BYTES + (uint32_t)p.bnp * TC_BK * 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int g = it / p.m_tiles, m_blk = it - g * p.m_tiles;
+        for (int pt = 0; pt < p.npt; ++pt) {
+          const int row0 = p.cpt > 0 ? g * p.bnp : g * p.P + pt * p.bnp;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * TC_STAGE_BYTES;
+            mbar_expect_tx(&full[stage], stage_tx);
+            tma_load_2d(sa, &tmW, &full[stage], kb * TC_BK, m_blk * TC_BM);
+            tma_load_2d(sa + TC_A_BYTES, &tmF, &full[stage], kb * TC_BK, row0);
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        for (int pt = 0; pt < p.npt; ++pt) {
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_MAX_BN;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
+            const uint32_t sb = sa + TC_A_BYTES;
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k)
+              umma_bf16(d_tmem, umma_smem_desc(sa + k * 32), umma_smem_desc(sb + k * 32), p.idesc, (kb | k) != 0);
+            umma_commit(&empty[stage]);
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tmem_full[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    constexpr float L2E = 1.4426950408889634f;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int g = it / p.m_tiles, m_blk = it - g * p.m_tiles;
+      const int n = m_blk * TC_BM + row;
+      const bool nvalid = n < p.n_out;
+      const float bias_n = nvalid ? p.bias[n] : 0.f;
+      int crop = p.cpt > 0 ? g * p.cpt : g;
+      int pix = 0, x = 0, y = 0;
+      float m = -INFINITY, s = 0.f, sx = 0.f, sy = 0.f;
+      for (int pt = 0; pt < p.npt; ++pt) {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_MAX_BN;
+        for (int c0 = 0; c0 < p.bnp; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+          if (pix + 16 <= p.P) {
+            // whole chunk inside one crop: one rescale, then 16 exps
+            float vm = v[0];
+#pragma unroll
+            for (int i = 1; i < 16; ++i) vm = fmaxf(vm, v[i]);
+            vm += bias_n;
+            if (vm > m) {
+              float f = exp2f((m - vm) * L2E);
+              s *= f; sx *= f; sy *= f;
+              m = vm;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float e = exp2f((v[i] + bias_n - m) * L2E);
+              s += e;
+              sx = fmaf(e, (float)x, sx);
+              sy = fmaf(e, (float)y, sy);
+              if (++x == p.W) { x = 0; ++y; }
+            }
+            pix += 16;
+            if (pix == p.P) {
+              if (nvalid && crop < p.B) p.states[(size_t)crop * p.n_out + n] = make_float4(m, s, sx, sy);
+              ++crop; pix = 0; x = 0; y = 0;
+              m = -INFINITY; s = 0.f; sx = 0.f; sy = 0.f;
+            }
+          } else {
+            // chunk straddles a crop boundary (P % 16 != 0): element-wise
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float vv = v[i] + bias_n;
+              if (vv > m) {
+                float f = exp2f((m - vv) * L2E);
+                s *= f; sx *= f; sy *= f;
+                m = vv;
+              }
+              float e = exp2f((vv - m) * L2E);
+              s += e;
+              sx = fmaf(e, (float)x, sx);
+              sy = fmaf(e, (float)y, sy);
+              if (++x == p.W) { x = 0; ++y; }
+              if (++pix == p.P) {
+                if (nvalid && crop < p.B) p.states[(size_t)crop * p.n_out + n] = make_float4(m, s, sx, sy);
+                ++crop; pix = 0; x = 0; y = 0;
+                m = -INFINITY; s = 0.f; sx = 0.f; sy = 0.f;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// merges the per-channel states of one crop into coords2d [J,2] (px) and coords3d_rel [J,3] (mm)
+__global__ void __launch_bounds__(128) head_finalize_kernel(const float4* __restrict__ states, float* __restrict__ out2d,
+                                                            float* __restrict__ out3d, int J, int D, int H, int W,
+                                                            DecodeScale sc) {
+  const int b = blockIdx.x;
+  const int n_out = J * (1 + D);
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    const float4* st = states + (size_t)b * n_out;
+    {
+      float4 c = st[j];
+      float x = soft_coord(c.z, c.y, W), y = soft_coord(c.w, c.y, H);
+      if (sc.apply) {
+        x = fmaf(x, sc.img_mul, sc.img_add);
+        y = fmaf(y, sc.img_mul, sc.img_add);
+      }
+      out2d[((size_t)b * J + j) * 2 + 0] = x;
+      out2d[((size_t)b * J + j) * 2 + 1] = y;
+    }
+    SoftState a;
+    soft_init(a);
+    for (int d = 0; d < D; ++d) {
+      float4 c = st[J + d * J + j];
+      SoftState bb;
+      bb.m = c.x; bb.s = c.y; bb.sx = c.z; bb.sy = c.w; bb.sz = c.y * (float)d;
+      soft_merge(a, bb);
+    }
+    float x = soft_coord(a.sx, a.s, W), y = soft_coord(a.sy, a.s, H), z = soft_coord(a.sz, a.s, D);
+    if (sc.apply) {
+      x = fmaf(x, sc.met_mul, sc.met_add);
+      y = fmaf(y, sc.met_mul, sc.met_add);
+      z = z * sc.z_mul;
+    }
+    out3d[((size_t)b * J + j) * 3 + 0] = x;
+    out3d[((size_t)b * J + j) * 3 + 1] = y;
+    out3d[((size_t)b * J + j) * 3 + 2] = z;
+  }
+}
+
+// w: fp32 [n_out][C] (torch conv weight [N,C,1,1]); returns nullptr on success.  Not eligible -> ready stays false.
+inline const char* tc_prepare_head(TcWeights& w, const float* wt, const float* bias, int C, int n_out, std::vector<void*>& allocs) {
+  if (tc_disabled() || C % 8 != 0) return nullptr;
+  std::vector<__nv_bfloat16> t((size_t)n_out * C);
+  for (size_t i = 0; i < t.size(); ++i) t[i] = host_bf16(wt[i]);
+  if (cudaMalloc((void**)&w.d_w, t.size() * 2) != cudaSuccess) return "cudaMalloc failed";
+  allocs.push_back(w.d_w);
+  if (cudaMemcpy(w.d_w, t.data(), t.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return "cudaMemcpy failed";
+  if (cudaMalloc((void**)&w.d_bias, (size_t)n_out * 4) != cudaSuccess) return "cudaMalloc failed";
+  allocs.push_back(w.d_bias);
+  if (cudaMemcpy(w.d_bias, bias, (size_t)n_out * 4, cudaMemcpyHostToDevice) != cudaSuccess) return "cudaMemcpy failed";
+  if (cudaFuncSetAttribute(tc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
+    return "cannot raise dynamic shared memory for tc_head_kernel";
+  const char* e = make_tmap_2d(&w.mapA, w.d_w, (uint64_t)n_out, (uint64_t)C, TC_BM);
+  if (e) return e;
+  w.Cout = n_out; w.Cin = C; w.n_real = n_out;
+  w.ready = true;
+  w.cached_in = nullptr;
+  w.cached_B = -1;
+  return nullptr;
+}
+
+// pixels-per-MMA plan; returns false when the feature map shape is not supported by the fused kernel
+inline bool tc_head_plan(int P, int* bnp, int* cpt, int* npt) {
+  if (P <= 256) {
+    for (int c = 256 / P; c >= 1; --c)
+      if ((c * P) % 16 == 0) {
+        *bnp = c * P; *cpt = c; *npt = 1;
+        return true;
+      }
+    return false;
+  }
+  if (P % 256 != 0) return false;
+  *bnp = 256; *cpt = 0; *npt = P / 256;
+  return true;
+}
+
+inline const char* tc_head_launch(const TcWeights& w, const void* features, int B, int H, int W, int J, int D, DecodeScale sc,
+                                  float* c2d, float* c3d, void* scratch, cudaStream_t st) {
+  TcHeadParams q;
+  q.states = (float4*)scratch;
+  q.bias = w.d_bias;
+  q.B = B; q.P = H * W; q.W = W; q.n_out = w.n_real; q.C = w.Cin;
+  if (!tc_head_plan(q.P, &q.bnp, &q.cpt, &q.npt)) return "unsupported feature map shape for the fused head";
+  q.n_groups = q.cpt > 0 ? (B + q.cpt - 1) / q.cpt : B;
+  q.m_tiles = (q.n_out + TC_BM - 1) / TC_BM;
+  q.kblocks = (q.C + TC_BK - 1) / TC_BK;
+  q.idesc = umma_idesc_bf16(q.bnp);
+  if (w.cached_in != features || w.cached_B != B) {
+    const char* e = make_tmap_2d(&w.mapB, features, (uint64_t)B * q.P, (uint64_t)q.C, (uint32_t)q.bnp);
+    if (e) return e;
+    w.cached_in = features;
+    w.cached_B = B;
+  }
+  const int items = q.n_groups * q.m_tiles;
+  tc_head_kernel<<<items < 148 ? items : 148, 256, TC_SMEM_BYTES, st>>>(w.mapA, w.mapB, q);
+  head_finalize_kernel<<<B, 128, 0, st>>>(q.states, c2d, c3d, J, D, H, W, sc);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
 
 }  // namespace mtb

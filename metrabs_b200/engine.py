@@ -1,6 +1,9 @@
 """Thin object wrapper over the C handle (``mtb_handle``): owns the torch-allocated workspace and output tensors,
 passes raw device pointers and the current CUDA stream to libmetrabs_b200.so."""
+import atexit
 import ctypes as C
+import sys
+import weakref
 
 import numpy as np
 import torch
@@ -20,7 +23,8 @@ def make_config(cfg, n_joints, stages=None, last_channel=0, arch=_lib.ARCH_EFFNE
     c = MtbConfig()
     c.abi_version = _lib.MTB_ABI_VERSION
     c.arch = arch
-    c.precision = {'fp32': _lib.PRECISION_FP32, 'bf16': _lib.PRECISION_BF16_TC}[cfg.precision]
+    c.precision = {'fp32': _lib.PRECISION_FP32, 'bf16': _lib.PRECISION_BF16_TC,
+                   'bf16_simt': _lib.PRECISION_BF16_SIMT}[cfg.precision]
     c.device = device
     c.proc_side = int(cfg.proc_side)
     c.stride_train = int(cfg.stride_train)
@@ -47,25 +51,40 @@ def make_config(cfg, n_joints, stages=None, last_channel=0, arch=_lib.ARCH_EFFNE
     return c
 
 
+_live_engines = weakref.WeakSet()
+
+
+@atexit.register
+def _destroy_all():
+    # release handles while the CUDA runtime is still alive (destructors at interpreter teardown run too late)
+    for e in list(_live_engines):
+        e.close()
+
+
 class Engine:
     def __init__(self, mtb_config):
         self._h = C.c_void_p()
         self.cfg = mtb_config
         self.device = torch.device('cuda', mtb_config.device)
         check(lib().mtb_create(C.byref(mtb_config), C.byref(self._h)))
+        _live_engines.add(self)
         self._ws = None
         self._scratch = None
         hw, ch = C.c_int(), C.c_int()
         check(lib().mtb_feature_shape(self._h, C.byref(hw), C.byref(ch)), self._h)
         self.feature_side, self.feature_channels = hw.value, ch.value
         self.n_joints, self.depth = mtb_config.n_joints, mtb_config.depth
-        self.feature_dtype = torch.bfloat16 if mtb_config.precision == _lib.PRECISION_BF16_TC else torch.float32
+        self.feature_dtype = torch.float32 if mtb_config.precision == _lib.PRECISION_FP32 else torch.bfloat16
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().mtb_destroy(self._h)
+            self._h = None
 
     def __del__(self):
         try:
-            if self._h:
-                lib().mtb_destroy(self._h)
-                self._h = None
+            if not sys.is_finalizing():
+                self.close()
         except Exception:
             pass
 
@@ -188,6 +207,29 @@ class Engine:
         ws = self.workspace(b)
         check(lib().mtb_debug_run_ops(self._h, crops.data_ptr(), b, n_ops, out.data_ptr(), out.numel(), ws.data_ptr(),
                                       ws.numel(), _stream_ptr(self.device)), self._h)
+        return out
+
+    def op_io(self, op):
+        """-> dict(in_shape=(H,W,C), out_shape=(H,W,C), residual=bool, scale=bool) of backbone op `op`."""
+        a = [C.c_int() for _ in range(5)]
+        check(lib().mtb_op_input_shape(self._h, op, *[C.byref(x) for x in a]), self._h)
+        o = [C.c_int() for _ in range(3)]
+        check(lib().mtb_op_output_shape(self._h, op, *[C.byref(x) for x in o]), self._h)
+        return dict(in_shape=(a[0].value, a[1].value, a[2].value), out_shape=(o[0].value, o[1].value, o[2].value),
+                    residual=bool(a[3].value), scale=bool(a[4].value))
+
+    def debug_run_op(self, op, x, res=None, scale=None):
+        """One op in isolation on fp32 device tensors (NHWC; the stem takes NCHW crops)."""
+        io = self.op_io(op)
+        b = x.shape[0]
+        out = torch.empty((b,) + io['out_shape'], dtype=torch.float32, device=self.device)
+        ws = self.workspace(b)
+        x = x.float().contiguous()
+        res = res.float().contiguous() if res is not None else None
+        scale = scale.float().contiguous() if scale is not None else None
+        check(lib().mtb_debug_run_op(self._h, op, x.data_ptr(), res.data_ptr() if res is not None else None,
+                                     scale.data_ptr() if scale is not None else None, b, out.data_ptr(), out.numel(),
+                                     ws.data_ptr(), ws.numel(), _stream_ptr(self.device)), self._h)
         return out
 
     def profile_begin(self, classes=None):

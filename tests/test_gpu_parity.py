@@ -200,5 +200,5 @@ def test_errors_are_loud(H):
     from metrabs_b200.backbones.efficientnet import stage_table
     stages, last = stage_table('tiny', True)
     eng = Engine(make_config(metrabs_b200.get_config(), 8, stages=stages, last_channel=last))
-    with pytest.raises(MetrabsB200Error, match='running_var'):
+    with pytest.raises(MetrabsB200Error, match='backbone.1.3.0.block.1.1'):
         eng.load_state_dict(sd)

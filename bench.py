@@ -73,9 +73,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
         self.proc.terminate()
@@ -84,7 +87,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        window = [ln for (t, ln) in self.lines if t0 is None or (t0 <= t <= t1 + 0.15)]
+        if not window:  # timed region shorter than the sampling period: use the samples taken under warm-up load
+            window = [ln for (_, ln) in self.lines[-3:]]
+        for ln in window:
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 9:
                 continue
@@ -259,6 +265,9 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     # warm-up; the first one with every kernel class bracketed by events to find the dominant class
     eng.profile_begin(None)
     step()
@@ -270,13 +279,11 @@ def run_b200(args):
     dom_cls = prof_all[dom_name]['cls']
     total_ms_all = sum(v['ms'] for v in prof_all.values())
 
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
     eng.profile_begin([dom_cls])
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = sampler.mark()
     ev0.record()
     launches = 0
     for _ in range(args.steps):
@@ -284,9 +291,10 @@ def run_b200(args):
         launches += eng.last_launch_count + (1 if world > 1 else 0)
     ev1.record()
     barrier()
+    t_end = sampler.mark()
     elapsed_ms = ev0.elapsed_time(ev1)
     prof_dom = eng.profile_end()[dom_name]
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
 
     # end-to-end through the host-buffer entry point (pinned host crops in, host joints out, every step)
     eng.forward_host(crops_h, k_h, out_h)
@@ -354,6 +362,8 @@ def run_b200(args):
 
 
 def main():
+    import faulthandler
+    faulthandler.enable()
     args = parse()
     if args.impl == 'reference':
         run_reference(args)

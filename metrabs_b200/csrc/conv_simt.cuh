@@ -238,6 +238,114 @@ __global__ void __launch_bounds__(256) dwconv_kernel(ConvParams p) {
 }
 
 // ----------------------------------------------------------------------------------------------------------
+// depthwise 3x3 (+ stride 2) + bias + activation + squeeze-excitation pooling, bf16 NHWC, 8 channels x 4 output
+// pixels per thread: every input column vector is loaded once per row and reused by the outputs it feeds
+// (18 / 27 16-byte loads per 4 outputs instead of 36), and the per-channel sums of the SE squeeze are reduced in the
+// block and added (already divided by Hout*Wout) to pooled[b][c] with one atomic per channel per block, so the
+// pooling pass never re-reads the tensor.  grid (ceil(C/256), ceil(strips/8), B), block (32, 8).
+// ----------------------------------------------------------------------------------------------------------
+template <int STRIDE>
+__global__ void __launch_bounds__(256) dwconv3x3_pool_bf16_kernel(ConvParams p, float* __restrict__ pooled) {
+  constexpr int OW = 4;                          // outputs per thread along W
+  constexpr int NCOL = (OW - 1) * STRIDE + 3;    // input columns feeding them
+  const __nv_bfloat16* __restrict__ in = reinterpret_cast<const __nv_bfloat16*>(p.in);
+  __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  const int C = p.Cout;
+  const int cv = blockIdx.x * 32 + threadIdx.x;  // channel vector (8 channels)
+  const int c = cv * 8;
+  const int strips_w = (p.Wout + OW - 1) / OW;
+  const int strip = blockIdx.y * 8 + threadIdx.y;
+  const int b = blockIdx.z;
+  const bool active = c < C && strip < strips_w * p.Hout;
+  float acc[OW][8];
+  float psum[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) psum[k] = 0.f;
+  if (active) {
+    const int oh = strip / strips_w;
+    const int ow0 = (strip - oh * strips_w) * OW;
+    float bias[8];
+    {
+      float4 b0 = *reinterpret_cast<const float4*>(p.bias + c), b1 = *reinterpret_cast<const float4*>(p.bias + c + 4);
+      bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+      bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+    }
+#pragma unroll
+    for (int i = 0; i < OW; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[i][k] = bias[k];
+    const int iw0 = ow0 * STRIDE - p.pad_l;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * STRIDE - p.pad_t + r;
+      if (ih < 0 || ih >= p.Hin) continue;
+      float w[3][8];
+#pragma unroll
+      for (int s_ = 0; s_ < 3; ++s_) {
+        const float* wp = p.w + (size_t)(r * 3 + s_) * C + c;
+        float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+        w[s_][0] = w0.x; w[s_][1] = w0.y; w[s_][2] = w0.z; w[s_][3] = w0.w;
+        w[s_][4] = w1.x; w[s_][5] = w1.y; w[s_][6] = w1.z; w[s_][7] = w1.w;
+      }
+      const __nv_bfloat16* rowp = in + ((size_t)(b * p.Hin + ih) * p.Win) * p.Cin + c;
+#pragma unroll
+      for (int x = 0; x < NCOL; ++x) {
+        const int iw = iw0 + x;
+        if (iw < 0 || iw >= p.Win) continue;
+        uint4 raw = *reinterpret_cast<const uint4*>(rowp + (size_t)iw * p.Cin);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 f = __bfloat1622float2(h2[k]);
+          v[2 * k] = f.x;
+          v[2 * k + 1] = f.y;
+        }
+#pragma unroll
+        for (int i = 0; i < OW; ++i) {
+          const int s_ = x - i * STRIDE;  // compile-time after unrolling
+          if (s_ >= 0 && s_ < 3) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[i][k] = fmaf(v[k], w[s_][k], acc[i][k]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < OW; ++i) {
+      const int ow = ow0 + i;
+      if (ow >= p.Wout) continue;
+      uint4 ov;
+      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float a0 = apply_act(acc[i][2 * k], p.act), a1 = apply_act(acc[i][2 * k + 1], p.act);
+        o2[k] = __floats2bfloat162_rn(a0, a1);
+        float2 back = __bfloat1622float2(o2[k]);  // pool what the next layer will actually read
+        psum[2 * k] += back.x;
+        psum[2 * k + 1] += back.y;
+      }
+      *reinterpret_cast<uint4*>(out + ((size_t)(b * p.Hout + oh) * p.Wout + ow) * C + c) = ov;
+    }
+  }
+  if (pooled) {
+    __shared__ float red[8][32][9];
+    for (int k = 0; k < 8; ++k) red[threadIdx.y][threadIdx.x][k] = psum[k];
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+      const float inv = 1.0f / (float)(p.Hout * p.Wout);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float t = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][k];
+        atomicAdd(pooled + (size_t)b * C + c + k, t * inv);
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
 // stem: direct conv for tiny Cin (3) reading the caller's NCHW fp32 crops, with the per-channel input affine
 // (PreprocLayer x*2-1, backbones/efficientnet.py:1185) applied to in-bounds pixels only (pad happens AFTER
 // preprocessing in the reference), writing NHWC.  w: [R*S*Cin][Cout], one thread per (pixel, 4 out channels).

@@ -51,6 +51,8 @@ struct Op {
   int R = 1, S = 1, stride = 1, dil = 1, pad_t = 0, pad_l = 0, act = ACT_NONE;
   bool depthwise = false;
   bool small_io = false;  // squeeze-excitation FCs on [B,1,1,C] fp32 tensors
+  bool fused_pool = false;  // bf16 modes: this depthwise op also produces the SE pooled means (next op is skipped)
+  bool res_first = false;  // residual added BEFORE the activation (ResNet); EfficientNet adds it after
   int ksplit = 1;          // split-K (squeeze-excitation fc1): raw sums, bias/act deferred to the consumer
   int a_bias_from = -1;    // op index whose bias (+ a_act) is applied to THIS op's input on load
   int a_act = ACT_NONE;
@@ -436,7 +438,7 @@ int op_class(const Op& op) {
     default: break;
   }
   if (op.small_io) return KC_SE_FC;
-  if (op.tc.ready) return op.R == 1 ? KC_TC_GEMM : KC_TC_CONV3;
+  if (op.tc.ready) return (op.R == 1 && op.stride == 1) ? KC_TC_GEMM : KC_TC_CONV3;
   return KC_IGEMM_SIMT;
 }
 
@@ -480,8 +482,25 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
       p.B = B; p.Hin = op.Hin; p.Win = op.Win; p.Cin = op.Cin; p.Hout = op.Hout; p.Wout = op.Wout; p.Cout = op.Cout;
       p.R = op.R; p.S = op.S; p.stride = op.stride; p.dil = op.dil; p.pad_t = op.pad_t; p.pad_l = op.pad_l; p.act = op.act;
       if (op.type == OP_DW) {
-        size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
-        dwconv_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
+        if (sizeof(T) == 2 && op.R == 3 && op.S == 3 && op.dil == 1 && op.Cout % 8 == 0 && (op.stride == 1 || op.stride == 2)) {
+          float* pooled = nullptr;
+          if (op.fused_pool) {
+            pooled = (float*)buf_ptr(ws, BUF_SMALL0, features);
+            cudaMemsetAsync(pooled, 0, (size_t)B * op.Cout * 4, st);
+          }
+          const int strips = op.Hout * ((op.Wout + 3) / 4);
+          dim3 grid((op.Cout / 8 + 31) / 32, (strips + 7) / 8, B), block(32, 8);
+          if (op.stride == 1) dwconv3x3_pool_bf16_kernel<1><<<grid, block, 0, st>>>(p, pooled);
+          else dwconv3x3_pool_bf16_kernel<2><<<grid, block, 0, st>>>(p, pooled);
+        } else {
+          size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
+          dwconv_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
+          if (op.fused_pool) {  // shapes the fused kernel does not cover: separate pooling pass
+            dim3 pg((op.Cout + 127) / 128, B), pb(32, 8);
+            pool_mean_kernel<T><<<pg, pb, 0, st>>>((const T*)p.out, (float*)buf_ptr(ws, BUF_SMALL0, features), op.Hout * op.Wout, op.Cout);
+            h->launches++;
+          }
+        }
       } else if (op.type == OP_MAXPOOL) {
         size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
         maxpool_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
@@ -502,7 +521,7 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
           if (e) return fail(h, MTB_ERR_CUDA, "se scale %s: %s", op.name.c_str(), e);
           h->launches++;
         }
-        const char* e = tc_conv_launch(op.tc, p, st);
+        const char* e = tc_conv_launch(op.tc, p, op.res_first, st);
         if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 launch %s: %s", op.name.c_str(), e);
       } else {
         cudaError_t e = launch_conv_igemm<T, T>(p, st);
@@ -525,6 +544,7 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
 }
 
 int run_op(mtb_handle* h, const Op& op, const float* crops, int B, const Workspace& ws, void* features, cudaStream_t st) {
+  if (op.type == OP_POOL && op.fused_pool) return MTB_OK;  // produced by the preceding depthwise kernel
   if (is_bf16(h)) return run_op_t<__nv_bfloat16>(h, op, crops, B, ws, features, st);
   return run_op_t<float>(h, op, crops, B, ws, features, st);
 }
@@ -744,6 +764,11 @@ int mtb_finalize_weights(mtb_handle* h) {
   DeviceGuard g(h->cfg.device);
   for (void* p : h->dev_allocs) cudaFree(p);
   h->dev_allocs.clear();
+  for (size_t i = 0; i + 1 < h->ops.size(); ++i) {
+    const bool fuse = is_bf16(h) && h->ops[i].type == OP_DW && h->ops[i + 1].type == OP_POOL;
+    h->ops[i].fused_pool = fuse;
+    h->ops[i + 1].fused_pool = fuse && h->ops[i + 1].type == OP_POOL;
+  }
   for (auto& op : h->ops) {
     int rc = prepare_op_weights(h, op);
     if (rc) return rc;
@@ -1113,6 +1138,7 @@ int mtb_debug_run_op(mtb_handle* h, int op_index, const float* in, const float* 
   if (scale) { o.scale_buf = BUF_SMALL0 + 2; put(scale, o.scale_buf, (size_t)batch * o.Cin, true); }
   o.out_buf = (o.type == OP_POOL || o.small_io) ? BUF_SMALL0 + 1 : 2;
   o.tc.cached_in = nullptr;  // the copy must not reuse a tensor map encoded for other buffers
+  o.fused_pool = false;      // in isolation a depthwise op does not pool and a pool op runs its own kernel
   rc = run_op(h, o, crops, batch, ws, nullptr, st);
   if (rc) return rc;
   void* src = buf_ptr(ws, o.out_buf, nullptr);

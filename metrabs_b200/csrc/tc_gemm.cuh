@@ -139,27 +139,64 @@ constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4, TC_MAX_BN = 256;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;       // 16 KB
 constexpr int TC_B_BYTES = TC_MAX_BN * TC_BK * 2;   // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TC_TILE_W = 16, TC_TILE_H = 8;        // spatial M tile of the 3x3 mode (16 x 8 = 128 pixels)
+constexpr int TC_OUT_BOX_BYTES = TC_BM * 64 * 2;    // one [128 rows x 64 cols] bf16 output box (TMA store), 16 KB
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 2 * TC_OUT_BOX_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_TILE_W = 16, TC_TILE_H = 8;        // spatial M tile (16 x 8 = 128 output pixels)
+constexpr int TC_THREADS = 384;                      // warps 0-3: TMA / MMA / TMEM alloc / idle, warps 4-11: epilogue
+constexpr int TC_EPI_THREADS = 256;
 
 struct TcConvParams {
-  void* out;
   const void* res;
   const float* bias;
-  int mode;     // 0: flat 1x1 (rows = B*H*W), 1: 3x3 stride 1 (spatial tiles)
+  int mode;     // 0: flat 1x1 stride 1 (rows = B*H*W, 2D maps), 1: spatial tiles (any RxS, stride 1/2, dilation; 4D maps)
   int M;        // mode 0: number of rows
   int Cout, Cin;
-  int bn, n_tiles, m_tiles, kchunks, taps;
-  int act;
-  int Hout, Wout, tiles_w, tiles_h, pad_t, pad_l, S;
-  uint32_t idesc;
+  int bn;       // N-tile stride, multiple of 64 (the MMA N of a tile is its valid width rounded up to 16)
+  int n_tiles, m_tiles, kchunks, taps;
+  int act, res_first;   // res_first: add the residual BEFORE the activation (ResNet), else after (EfficientNet)
+  int Hout, Wout, tiles_w, tiles_h, pad_t, pad_l, S, stride, dil;
 };
 
-__global__ void __launch_bounds__(256, 1)
-tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) {
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// epilogue activation with one MUFU op: SiLU(x) = h + h*tanh(h), h = x/2 (error ~2^-11, below bf16 resolution)
+__device__ __forceinline__ float tc_act(float x, int act) {
+  if (act == ACT_SILU) {
+    float h = 0.5f * x;
+    return fmaf(h, tanh_approx(h), h);
+  }
+  return apply_act(x, act);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const TcConvParams p) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B needs 1024 B alignment
-  uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint8_t* out_stage = smem + TC_STAGES * TC_STAGE_BYTES;                          // 2 x 16 KB output boxes
+  uint64_t* bars = (uint64_t*)(out_stage + 2 * TC_OUT_BOX_BYTES);
   uint64_t* full = bars;                     // [TC_STAGES]
   uint64_t* empty = bars + TC_STAGES;        // [TC_STAGES]
   uint64_t* tmem_full = bars + 2 * TC_STAGES;   // [2]
@@ -170,6 +207,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < TC_STAGES; ++i) {
@@ -178,7 +216,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], TC_EPI_THREADS / 32);
     }
     fence_barrier_init();
   }
@@ -199,13 +237,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int m_blk = t / p.n_tiles, n_blk = t - m_blk * p.n_tiles;
-        int b = 0, oh0 = 0, ow0 = 0;
+        int b = 0, ih0 = 0, iw0 = 0;
         if (p.mode == 1) {
           int tw = m_blk % p.tiles_w;
           int th = (m_blk / p.tiles_w) % p.tiles_h;
           b = m_blk / (p.tiles_w * p.tiles_h);
-          oh0 = th * TC_TILE_H - p.pad_t;
-          ow0 = tw * TC_TILE_W - p.pad_l;
+          ih0 = th * TC_TILE_H * p.stride - p.pad_t;
+          iw0 = tw * TC_TILE_W * p.stride - p.pad_l;
         }
         for (int kb = 0; kb < num_kb; ++kb) {
           const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
@@ -217,7 +255,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d(sa, &tmA, &full[stage], kc * TC_BK, m_blk * TC_BM);
           } else {
             const int r = tap / p.S, s = tap - r * p.S;
-            tma_load_4d(sa, &tmA, &full[stage], kc * TC_BK, ow0 + s, oh0 + r, b);
+            tma_load_4d(sa, &tmA, &full[stage], kc * TC_BK, iw0 + s * p.dil, ih0 + r * p.dil, b);
           }
           tma_load_2d(sb, &tmB, &full[stage], tap * p.Cin + kc * TC_BK, n_blk * p.bn);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -232,6 +270,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n_blk = t % p.n_tiles;
+        const int n_valid = min(p.bn, p.Cout - n_blk * p.bn);
+        const uint32_t idesc = umma_idesc_bf16((n_valid + 15) & ~15);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_MAX_BN;
@@ -242,7 +283,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sb = sa + TC_A_BYTES;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
-            umma_bf16(d_tmem, umma_smem_desc(sa + k * 32), umma_smem_desc(sb + k * 32), p.idesc, (kb | k) != 0);
+            umma_bf16(d_tmem, umma_smem_desc(sa + k * 32), umma_smem_desc(sb + k * 32), idesc, (kb | k) != 0);
           }
           umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -252,25 +293,32 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) = tile rows =====
-    const int q = warp - 4;
+    // ===== epilogue: 8 warps.  Warp w owns TMEM lanes [32(w%4), +32) = tile rows, and half (w-4)/4 of every 64-column
+    // chunk.  TMEM -> registers -> bias/act/residual -> bf16 -> 128B-swizzled smem box -> TMA store (coalesced, and
+    // tile tails are clipped by the tensor map). =====
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
+    const bool leader = threadIdx.x == 4 * 32;
     int acc = 0;
     uint32_t acc_phase = 0;
-    __nv_bfloat16* __restrict__ out = (__nv_bfloat16*)p.out;
+    uint32_t box_count = 0;
     const __nv_bfloat16* __restrict__ res = (const __nv_bfloat16*)p.res;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int m_blk = t / p.n_tiles, n_blk = t - m_blk * p.n_tiles;
+      const int n0 = n_blk * p.bn;
+      const int n_valid = min(p.bn, p.Cout - n0);
       bool valid;
       size_t off;
+      int tw = 0, th = 0, b = 0;
       if (p.mode == 0) {
         int m = m_blk * TC_BM + row;
         valid = m < p.M;
         off = (size_t)m * p.Cout;
       } else {
-        int tw = m_blk % p.tiles_w;
-        int th = (m_blk / p.tiles_w) % p.tiles_h;
-        int b = m_blk / (p.tiles_w * p.tiles_h);
+        tw = m_blk % p.tiles_w;
+        th = (m_blk / p.tiles_w) % p.tiles_h;
+        b = m_blk / (p.tiles_w * p.tiles_h);
         int oh = th * TC_TILE_H + row / TC_TILE_W, ow = tw * TC_TILE_W + row % TC_TILE_W;
         valid = oh < p.Hout && ow < p.Wout;
         off = ((size_t)(b * p.Hout + oh) * p.Wout + ow) * p.Cout;
@@ -278,47 +326,67 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_MAX_BN;
-      const int n0 = n_blk * p.bn;
-      for (int c0 = 0; c0 < p.bn; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + c0, v);
-        const int n = n0 + c0;
-        if (valid && n < p.Cout) {  // Cout % 8 == 0: 8-column groups are all-or-nothing
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int ng = n + g * 8;
-            if (ng < p.Cout) {
-              float4 b0 = *reinterpret_cast<const float4*>(p.bias + ng);
-              float4 b1 = *reinterpret_cast<const float4*>(p.bias + ng + 4);
-              float o[8];
-              o[0] = apply_act(v[g * 8 + 0] + b0.x, p.act); o[1] = apply_act(v[g * 8 + 1] + b0.y, p.act);
-              o[2] = apply_act(v[g * 8 + 2] + b0.z, p.act); o[3] = apply_act(v[g * 8 + 3] + b0.w, p.act);
-              o[4] = apply_act(v[g * 8 + 4] + b1.x, p.act); o[5] = apply_act(v[g * 8 + 5] + b1.y, p.act);
-              o[6] = apply_act(v[g * 8 + 6] + b1.z, p.act); o[7] = apply_act(v[g * 8 + 7] + b1.w, p.act);
-              if (res) {
-                uint4 rv = *reinterpret_cast<const uint4*>(res + off + ng);
-                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  float2 f = __bfloat1622float2(r2[i]);
-                  o[2 * i] += f.x;
-                  o[2 * i + 1] += f.y;
-                }
-              }
-              uint4 ov;
-              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
-              *reinterpret_cast<uint4*>(out + off + ng) = ov;
-            }
-          }
+      const int nchunks = (n_valid + 63) >> 6;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int c0 = ch * 64 + half * 32;  // this warp's 32 columns of the chunk
+        float v[32];
+        if (c0 < n_valid) {
+          tmem_ld16(taddr + c0, v);
+          if (c0 + 16 < n_valid) tmem_ld16(taddr + c0 + 16, v + 16);
         }
+        if (ch == nchunks - 1) {  // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        uint8_t* box = out_stage + (box_count & 1) * TC_OUT_BOX_BYTES;
+        // the TMA store that last read this box (2 boxes ago) must have finished reading shared memory
+        if (leader) tma_store_wait_read<1>();
+        named_bar_sync(1, TC_EPI_THREADS);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int cg = c0 + g * 8;  // 8-column group (Cout % 8 == 0: all-or-nothing)
+          uint4 ov = make_uint4(0u, 0u, 0u, 0u);
+          if (cg < n_valid) {
+            const int ng = n0 + cg;
+            float4 b0 = *reinterpret_cast<const float4*>(p.bias + ng);
+            float4 b1 = *reinterpret_cast<const float4*>(p.bias + ng + 4);
+            float o[8];
+            o[0] = v[g * 8 + 0] + b0.x; o[1] = v[g * 8 + 1] + b0.y; o[2] = v[g * 8 + 2] + b0.z; o[3] = v[g * 8 + 3] + b0.w;
+            o[4] = v[g * 8 + 4] + b1.x; o[5] = v[g * 8 + 5] + b1.y; o[6] = v[g * 8 + 6] + b1.z; o[7] = v[g * 8 + 7] + b1.w;
+            float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (res && valid) {
+              uint4 rv = *reinterpret_cast<const uint4*>(res + off + ng);
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float2 f = __bfloat1622float2(r2[i]);
+                r[2 * i] = f.x;
+                r[2 * i + 1] = f.y;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = p.res_first ? tc_act(o[i] + r[i], p.act) : tc_act(o[i], p.act) + r[i];
+            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+          }
+          // 128B swizzle: 16-byte chunk j of row r lives at chunk position j ^ (r & 7)
+          const int j = half * 4 + g;
+          *reinterpret_cast<uint4*>(box + row * 128 + ((j ^ (row & 7)) << 4)) = ov;
+        }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        named_bar_sync(1, TC_EPI_THREADS);
+        if (leader) {
+          if (p.mode == 0) tma_store_2d(&tmO, box, n0 + ch * 64, m_blk * TC_BM);
+          else tma_store_4d(&tmO, box, n0 + ch * 64, tw * TC_TILE_W, th * TC_TILE_H, b);
+          tma_store_commit();
+        }
+        ++box_count;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (leader) tma_store_wait_all();  // global writes complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -378,14 +446,15 @@ inline const char* make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, 
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(2d) failed";
 }
-// rank-4 bf16 NHWC tensor [B][H][W][C], box [1][TILE_H][TILE_W][64]
-inline const char* make_tmap_nhwc(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C) {
+// rank-4 bf16 NHWC tensor [B][H][W][C]; box = 64 channels x (TILE_W x TILE_H) pixels sampled every `stride` pixels
+// (element strides: to load N elements along a dimension with traversal stride s, boxDim = N*s)
+inline const char* make_tmap_nhwc(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t stride) {
   tmap_encode_fn enc = get_tmap_encode();
   if (!enc) return "cuTensorMapEncodeTiled unavailable";
   cuuint64_t dims[4] = {C, W, H, B};
   cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
-  cuuint32_t box[4] = {TC_BK, TC_TILE_W, TC_TILE_H, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {TC_BK, TC_TILE_W * stride, TC_TILE_H * stride, 1};
+  cuuint32_t estr[4] = {1, stride, stride, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -400,8 +469,9 @@ struct TcWeights {
   // head
   int n_real = 0;
   // per-shape launch state (A tensor map depends on the activation pointer and batch)
-  mutable CUtensorMap mapA, mapB;
+  mutable CUtensorMap mapA, mapB, mapO;
   mutable const void* cached_in = nullptr;
+  mutable const void* cached_out = nullptr;
   mutable int cached_B = -1, cached_bn = 0;
 };
 
@@ -417,7 +487,7 @@ inline bool tc_disabled() {
 inline bool tc_eligible(bool is_conv, bool depthwise, bool small_io, int k, int stride, int cin, int cout) {
   if (!is_conv || depthwise || small_io) return false;
   if (cin % 8 != 0 || cout % 8 != 0) return false;
-  return stride == 1 && (k == 1 || k == 3);
+  return (stride == 1 || stride == 2) && (k == 1 || k == 3);
 }
 
 inline __nv_bfloat16 host_bf16(float f) {
@@ -456,14 +526,17 @@ inline const char* tc_prepare_weights(TcWeights& w, const float* wk, const float
   return nullptr;
 }
 
+// N-tile stride (multiple of 64): fewest waves first, then least padded MMA work
 inline int tc_pick_bn(int cout, int m_tiles, int num_kb) {
-  int best = 16;
+  int best = 64;
   double best_cost = 1e30;
-  for (int bn = 256; bn >= 16; bn -= 16) {
+  for (int bn = 256; bn >= 64; bn -= 64) {
     int nt = (cout + bn - 1) / bn;
     long tiles = (long)m_tiles * nt;
     long waves = (tiles + 147) / 148;
-    double cost = (double)waves * ((double)bn * (num_kb + 2) + 64.0);
+    int last = cout - (nt - 1) * bn;                          // width of the ragged last tile
+    double avg_n = ((double)(nt - 1) * bn + ((last + 15) & ~15)) / nt;
+    double cost = (double)waves * (avg_n * (num_kb + 2) + 96.0);
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best = bn;
@@ -472,12 +545,12 @@ inline int tc_pick_bn(int cout, int m_tiles, int num_kb) {
   return best;
 }
 
-inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, cudaStream_t st) {
+inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool res_first, cudaStream_t st) {
   TcConvParams q;
-  q.out = p.out; q.res = p.res; q.bias = w.d_bias;
-  q.mode = (p.R == 3) ? 1 : 0;
-  q.Cout = p.Cout; q.Cin = p.Cin; q.act = p.act;
-  q.taps = w.taps; q.S = w.S;
+  q.res = p.res; q.bias = w.d_bias;
+  q.mode = (p.R == 1 && p.stride == 1) ? 0 : 1;
+  q.Cout = p.Cout; q.Cin = p.Cin; q.act = p.act; q.res_first = res_first ? 1 : 0;
+  q.taps = w.taps; q.S = w.S; q.stride = p.stride; q.dil = p.dil;
   q.kchunks = (p.Cin + TC_BK - 1) / TC_BK;
   q.Hout = p.Hout; q.Wout = p.Wout; q.pad_t = p.pad_t; q.pad_l = p.pad_l;
   q.tiles_w = (p.Wout + TC_TILE_W - 1) / TC_TILE_W;
@@ -487,20 +560,23 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, cudaS
   const int bn = tc_pick_bn(p.Cout, q.m_tiles, q.taps * q.kchunks);
   q.bn = bn;
   q.n_tiles = (p.Cout + bn - 1) / bn;
-  q.idesc = umma_idesc_bf16(bn);
-  if (w.cached_in != p.in || w.cached_B != p.B || w.cached_bn != bn) {
+  if (w.cached_in != p.in || w.cached_out != p.out || w.cached_B != p.B || w.cached_bn != bn) {
     const char* e = q.mode == 0 ? make_tmap_2d(&w.mapA, p.in, (uint64_t)q.M, (uint64_t)p.Cin, TC_BM)
-                                : make_tmap_nhwc(&w.mapA, p.in, p.B, p.Hin, p.Win, p.Cin);
+                                : make_tmap_nhwc(&w.mapA, p.in, p.B, p.Hin, p.Win, p.Cin, (uint32_t)p.stride);
     if (e) return e;
     e = make_tmap_2d(&w.mapB, w.d_w, (uint64_t)p.Cout, (uint64_t)w.taps * p.Cin, (uint32_t)bn);
     if (e) return e;
+    e = q.mode == 0 ? make_tmap_2d(&w.mapO, p.out, (uint64_t)q.M, (uint64_t)p.Cout, TC_BM)
+                    : make_tmap_nhwc(&w.mapO, p.out, p.B, p.Hout, p.Wout, p.Cout, 1);
+    if (e) return e;
     w.cached_in = p.in;
+    w.cached_out = p.out;
     w.cached_B = p.B;
     w.cached_bn = bn;
   }
   const int total = q.m_tiles * q.n_tiles;
   const int grid = total < 148 ? total : 148;
-  tc_conv_kernel<<<grid, 256, TC_SMEM_BYTES, st>>>(w.mapA, w.mapB, q);
+  tc_conv_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(w.mapA, w.mapB, w.mapO, q);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

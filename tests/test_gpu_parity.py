@@ -135,7 +135,8 @@ def test_tiny_model_golden(H, golden_dir, fname):
     c2d_b, c3d_b = m.heatmap_heads(feats.permute(0, 3, 1, 2))
     assert torch.equal(c2d_b, c2d) and torch.equal(c3d_b, c3d)
     out_h = eng.forward_host(crops.pin_memory(), k.pin_memory())
-    assert torch.equal(out_h, out.cpu())
+    # (not bit-equal run to run: the squeeze-excitation fc1 is a split-K GEMM with fp32 atomics)
+    assert H.rel_err(out_h, out) < 1e-5
     assert eng.last_launch_count > 0
 
 

@@ -175,6 +175,9 @@ int mtb_debug_run_op(mtb_handle* h, int op_index, const float* in, const float* 
  * FLOPs, algorithmic bytes and launch count; arrays must hold mtb_num_kernel_classes() entries. */
 int mtb_profile_begin(mtb_handle* h, unsigned class_mask);
 int mtb_profile_end(mtb_handle* h, double* ms, double* flops, double* bytes, int64_t* launches);
+/* Per-op view of the last profiling window: device ms per backbone op, its algorithmic FLOPs and bytes per crop and
+ * its kernel class; arrays hold mtb_num_ops() entries. */
+int mtb_profile_op_times(const mtb_handle* h, double* ms, double* flops_per_crop, double* bytes_per_crop, int* cls, int n);
 int mtb_num_kernel_classes(void);
 const char* mtb_kernel_class_name(int cls);
 /* Number of kernels the last mtb_forward / mtb_backbone_forward / ... call on this handle launched. */

@@ -69,6 +69,8 @@ _SIGNATURES = {
     'mtb_profile_begin': (C.c_int, [C.c_void_p, C.c_uint]),
     'mtb_profile_end': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                   C.POINTER(C.c_int64)]),
+    'mtb_profile_op_times': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_int), C.c_int]),
     'mtb_num_kernel_classes': (C.c_int, []),
     'mtb_kernel_class_name': (C.c_char_p, [C.c_int]),
     'mtb_last_launch_count': (C.c_int64, [C.c_void_p]),

@@ -10,6 +10,7 @@ arithmetic runs in libmetrabs_b200.so (stem / FusedMBConv / MBConv / SE kernels)
 import torch
 from torch import nn
 
+from metrabs_b200 import _lib
 from metrabs_b200.util import get_config
 
 _TABLES = {
@@ -58,6 +59,7 @@ class _Block(nn.Module):
 
 class Features(nn.Module):
     """Parameter tree of ``EfficientNet.features`` (children '0' stem, '1'..'n' stages, 'n+1' last conv)."""
+    arch = _lib.ARCH_EFFNET
 
     def __init__(self, stages, last_channel):
         super().__init__()

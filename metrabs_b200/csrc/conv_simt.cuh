@@ -16,7 +16,10 @@ struct ConvParams {
   const float* a_scale;  // optional per-(b,cin) multiplier of the input (squeeze-excitation), [B][Cin]
   const float* a_bias = nullptr;  // optional per-cin bias + activation applied to the input on load (the producer was a
   int a_act = 0;                  //   split-K GEMM that left raw sums: squeeze-excitation fc1 -> fc2)
-  int ksplit = 1;                 // > 1: blockIdx.z owns a K slice and atomically adds raw sums into a zeroed fp32 output
+  int res_first = 0;              // 1: add the residual BEFORE the activation (ResNet), 0: after (EfficientNet)
+  int ksplit = 1;                 // > 1: blockIdx.z owns a K slice and writes its raw partial sums to out + z*M*Cout (fp32)
+  int a_splits = 1;               // > 1: the input is such a stack of partial-sum slices; they are summed on load (in a
+  size_t a_split_stride = 0;      //   fixed order: deterministic, unlike atomics), then a_bias / a_act apply
   int B, Hin, Win, Cin, Hout, Wout, Cout, R, S, stride, dil, pad_t, pad_l, act;
 };
 
@@ -85,7 +88,12 @@ conv_igemm_kernel(ConvParams p) {
       bool ok = a_ok[i] && ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win && c < p.Cin;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ok) {
-        v = load4<TIn>(in + ((size_t)(a_b[i] * p.Hin + ih) * p.Win + iw) * p.Cin + c);
+        const TIn* ap = in + ((size_t)(a_b[i] * p.Hin + ih) * p.Win + iw) * p.Cin + c;
+        v = load4<TIn>(ap);
+        for (int z = 1; z < p.a_splits; ++z) {
+          float4 u = load4<TIn>(ap + (size_t)z * p.a_split_stride);
+          v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        }
         if (p.a_scale) {
           float4 sc = *reinterpret_cast<const float4*>(p.a_scale + (size_t)a_b[i] * p.Cin + c);
           v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
@@ -172,27 +180,23 @@ conv_igemm_kernel(ConvParams p) {
       for (int gj = 0; gj < GN; ++gj) {
         int n = n0 + tx * 4 + gj * GSN;
         if (n >= p.Cout) continue;
-        if (p.ksplit > 1) {  // raw partial sums; bias/activation are applied by the consumer (a_bias / a_act)
+        if (p.ksplit > 1) {  // raw partial sums of this K slice; the consumer sums the slices and applies bias/activation
           if constexpr (sizeof(TOut) == 4) {
-            float* o = reinterpret_cast<float*>(out) + (size_t)m * p.Cout + n;
-            atomicAdd(o + 0, acc[gi * 4 + i][gj * 4 + 0]);
-            atomicAdd(o + 1, acc[gi * 4 + i][gj * 4 + 1]);
-            atomicAdd(o + 2, acc[gi * 4 + i][gj * 4 + 2]);
-            atomicAdd(o + 3, acc[gi * 4 + i][gj * 4 + 3]);
+            float* o = reinterpret_cast<float*>(out) + ((size_t)blockIdx.z * M + m) * p.Cout + n;
+            *reinterpret_cast<float4*>(o) = make_float4(acc[gi * 4 + i][gj * 4 + 0], acc[gi * 4 + i][gj * 4 + 1],
+                                                        acc[gi * 4 + i][gj * 4 + 2], acc[gi * 4 + i][gj * 4 + 3]);
           }
           continue;
         }
         float4 bv = *reinterpret_cast<const float4*>(p.bias + n);
-        float4 v;
-        v.x = apply_act(acc[gi * 4 + i][gj * 4 + 0] + bv.x, p.act);
-        v.y = apply_act(acc[gi * 4 + i][gj * 4 + 1] + bv.y, p.act);
-        v.z = apply_act(acc[gi * 4 + i][gj * 4 + 2] + bv.z, p.act);
-        v.w = apply_act(acc[gi * 4 + i][gj * 4 + 3] + bv.w, p.act);
+        float4 v = make_float4(acc[gi * 4 + i][gj * 4 + 0] + bv.x, acc[gi * 4 + i][gj * 4 + 1] + bv.y,
+                               acc[gi * 4 + i][gj * 4 + 2] + bv.z, acc[gi * 4 + i][gj * 4 + 3] + bv.w);
         size_t o = (size_t)m * p.Cout + n;
-        if (res) {
-          float4 rv = load4<TOut>(res + o);
-          v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-        }
+        float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (res) rv = load4<TOut>(res + o);
+        if (p.res_first) { v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w; }
+        v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+        if (!p.res_first) { v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w; }
         store4<TOut>(out + o, v);
       }
     }
@@ -433,7 +437,8 @@ __global__ void __launch_bounds__(256) pool_mean_kernel(const T* __restrict__ in
   }
 }
 
-// max pool (ResNet stem, metrabs_tf/backbones/resnet.py:187-193), NHWC, pad value = -inf.
+// max pool (ResNet stem, metrabs_tf/backbones/resnet.py:187-193), NHWC.  The reference pads with ZeroPadding2D and
+// pools VALID, so an out-of-bounds tap contributes the value 0 to the max.
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_kernel(ConvParams p) {
   const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
@@ -450,11 +455,11 @@ __global__ void __launch_bounds__(256) maxpool_kernel(ConvParams p) {
     float4 acc = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     for (int r = 0; r < p.R; ++r) {
       int ih = oh * p.stride - p.pad_t + r;
-      if (ih < 0 || ih >= p.Hin) continue;
       for (int s = 0; s < p.S; ++s) {
         int iw = ow * p.stride - p.pad_l + s;
-        if (iw < 0 || iw >= p.Win) continue;
-        float4 v = load4<T>(in + ((size_t)(b * p.Hin + ih) * p.Win + iw) * p.Cin + c);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win)
+          v = load4<T>(in + ((size_t)(b * p.Hin + ih) * p.Win + iw) * p.Cin + c);
         acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
       }
     }

@@ -51,6 +51,7 @@ struct Op {
   int R = 1, S = 1, stride = 1, dil = 1, pad_t = 0, pad_l = 0, act = ACT_NONE;
   bool depthwise = false;
   bool small_io = false;  // squeeze-excitation FCs on [B,1,1,C] fp32 tensors
+  float pre_scale[3] = {2.f, 2.f, 2.f}, pre_shift[3] = {-1.f, -1.f, -1.f};  // stem input affine (PreprocLayer: x*2-1)
   bool fused_pool = false;  // bf16 modes: this depthwise op also produces the SE pooled means (next op is skipped)
   bool res_first = false;  // residual added BEFORE the activation (ResNet); EfficientNet adds it after
   int ksplit = 1;          // split-K (squeeze-excitation fc1): raw sums, bias/act deferred to the consumer
@@ -88,8 +89,11 @@ struct mtb_handle {
   unsigned prof_mask = 0;
   std::vector<cudaEvent_t> prof_events;  // pairs
   std::vector<int> prof_cls;
+  std::vector<int> prof_op;      // backbone op index of each timed launch (-1: head / decode / reconstruction)
+  int prof_cur_op = -1;
   std::vector<double> prof_flops, prof_bytes;
   size_t prof_used = 0;
+  std::vector<double> prof_op_ms;
   // NCCL (dlopen'ed)
   void* nccl_lib = nullptr;
   void* nccl_comm = nullptr;
@@ -134,6 +138,45 @@ struct Planner {
     return 0;
   }
   void track(int h_, int w_, int c_) { max_elems = std::max(max_elems, (size_t)h_ * w_ * c_); }
+
+  // Keras-named conv (TF-only backbones): explicit weight / bias / BN keys
+  Op& conv_k(const std::string& name, const std::string& wkey, const std::string& biaskey, const std::string& bnkey, int cout,
+             int k, int stride, int pad_beg, int pad_total, int act, int in_buf, int out_buf, bool depthwise = false,
+             int dil = 1, float eps = 1e-3f) {
+    Op& op = conv(name, cout, k, stride, pad_beg, pad_total, act, in_buf, out_buf, depthwise, dil);
+    op.wkey = wkey; op.biaskey = biaskey; op.bnkey = bnkey; op.bn_eps = eps;
+    return op;
+  }
+
+  // squeeze-excitation on the tensor in `buf` (H x W x C): pool + fc1 + fc2 -> scale in BUF_SMALL0+2
+  void squeeze_excite(const std::string& name, const std::string& fc1, const std::string& fc2, int csq_real, int buf,
+                      int act1, int act2) {
+    const int cexp = C;
+    const int csq = (csq_real + 3) / 4 * 4;  // hidden channels zero-padded to a multiple of 4 (128-bit accesses)
+    Op op;
+    op.type = OP_POOL; op.name = name + ".avgpool";
+    op.Hin = H; op.Win = W; op.Cin = op.Cout = cexp;
+    op.in_buf = buf; op.out_buf = BUF_SMALL0;
+    h->ops.push_back(op);
+    Op f1;
+    f1.type = OP_CONV; f1.name = name + ".fc1"; f1.wkey = fc1 + ".weight"; f1.biaskey = fc1 + ".bias";
+    f1.Cin = cexp; f1.Cout = csq; f1.act = act1; f1.small_io = true; f1.pad_ok = true;
+    f1.in_buf = BUF_SMALL0; f1.out_buf = BUF_SMALL0 + 1;
+    f1.flops = 2.0 * cexp * csq_real;
+    // K = cexp is long and M = batch is short: split K over CTAs; the ksplit partial slices [ksplit][B][csq] must fit
+    // the small buffer (capacity >= cexp floats per crop)
+    f1.ksplit = std::max(1, std::min({32, cexp / 64, cexp / csq}));
+    h->ops.push_back(f1);
+    const int f1_index = (int)h->ops.size() - 1;
+    Op f2;
+    f2.type = OP_CONV; f2.name = name + ".fc2"; f2.wkey = fc2 + ".weight"; f2.biaskey = fc2 + ".bias";
+    f2.Cin = csq; f2.Cout = cexp; f2.act = act2; f2.small_io = true; f2.pad_ok = true;
+    f2.in_buf = BUF_SMALL0 + 1; f2.out_buf = BUF_SMALL0 + 2;
+    f2.flops = 2.0 * cexp * csq_real;
+    if (f1.ksplit > 1) { f2.a_bias_from = f1_index; f2.a_act = act1; }
+    h->ops.push_back(f2);
+    max_small = std::max(max_small, cexp);
+  }
 
   // conv with explicit begin pad; output size = floor((in + pad_total - eff_k)/stride) + 1
   Op& conv(const std::string& name, int cout, int k, int stride, int pad_beg, int pad_total, int act, int in_buf,
@@ -219,32 +262,8 @@ void plan_effnet(mtb_handle* h) {
         P.conv(kb + "." + std::to_string(i), cexp, k, stride, pad_beg, pad_total, ACT_SILU, t1, t2, true);
         ++i;
         // squeeze-excitation: avgpool -> fc1 + SiLU -> fc2 + sigmoid -> scale (folded into the projection's A load)
-        const int csq_real = std::max(1, cin / 4);
-        const int csq = (csq_real + 3) / 4 * 4;  // hidden channels zero-padded to a multiple of 4 (128-bit accesses)
         const std::string se = kb + "." + std::to_string(i);
-        {
-          Op op;
-          op.type = OP_POOL; op.name = se + ".avgpool";
-          op.Hin = P.H; op.Win = P.W; op.Cin = op.Cout = cexp;
-          op.in_buf = t2; op.out_buf = BUF_SMALL0;
-          h->ops.push_back(op);
-          Op f1;
-          f1.type = OP_CONV; f1.name = se + ".fc1"; f1.wkey = se + ".fc1.weight"; f1.biaskey = se + ".fc1.bias";
-          f1.Cin = cexp; f1.Cout = csq; f1.act = ACT_SILU; f1.small_io = true; f1.pad_ok = true;
-          f1.in_buf = BUF_SMALL0; f1.out_buf = BUF_SMALL0 + 1;
-          f1.flops = 2.0 * cexp * csq_real;
-          f1.ksplit = std::min(32, std::max(1, cexp / 64));  // K = cexp is long and M = batch is short: split K over CTAs
-          h->ops.push_back(f1);
-          const int f1_index = (int)h->ops.size() - 1;
-          Op f2;
-          f2.type = OP_CONV; f2.name = se + ".fc2"; f2.wkey = se + ".fc2.weight"; f2.biaskey = se + ".fc2.bias";
-          f2.Cin = csq; f2.Cout = cexp; f2.act = ACT_SIGMOID; f2.small_io = true; f2.pad_ok = true;
-          f2.in_buf = BUF_SMALL0 + 1; f2.out_buf = BUF_SMALL0 + 2;
-          f2.flops = 2.0 * cexp * csq_real;
-          if (f1.ksplit > 1) { f2.a_bias_from = f1_index; f2.a_act = ACT_SILU; }
-          h->ops.push_back(f2);
-          P.max_small = std::max(P.max_small, cexp);
-        }
+        P.squeeze_excite(se, se + ".fc1", se + ".fc2", std::max(1, cin / 4), t2, ACT_SILU, ACT_SIGMOID);
         ++i;
         int t3 = P.pick({x_in, t2});
         Op& pr = P.conv(kb + "." + std::to_string(i), st.cout, 1, 1, 0, 0, ACT_NONE, t2, t3);
@@ -266,11 +285,179 @@ void plan_effnet(mtb_handle* h) {
   h->small_c = std::max(P.max_small, 4);
 }
 
+// ResNet-50 V1 at output stride `stride_test` (metrabs_tf/backbones/resnet.py:75-236 stem/pool, :239-319 bottleneck,
+// :601-666 stride/dilation plan; BN eps 1e-5 :71; every conv has a bias :270).  Key schema: Keras layer names,
+// "backbone.<layer>.{weight,bias}" / "backbone.<layer>.{weight,bias,running_mean,running_var}" in torch layout.
+int plan_resnet50(mtb_handle* h) {
+  const mtb_config& c = h->cfg;
+  if (c.stride_test != 8 && c.stride_test != 16 && c.stride_test != 32)
+    return fail(h, MTB_ERR_UNSUPPORTED, "ResNet-50: stride_test must be 8, 16 or 32 (got %d)", c.stride_test);
+  // get_strides_and_dilations(stride_test) (:601-618)
+  int strides[3] = {2, 2, 2}, dil_in[3] = {1, 1, 1}, dil_out[3] = {1, 1, 1};
+  bool brs[3] = {false, false, false};
+  int i_last = 0;
+  for (int s_ = c.stride_test; s_ > 8; s_ >>= 1) ++i_last;  // log2(stride) - 3
+  if (c.centered_stride) brs[i_last] = true;
+  for (int i = i_last + 1; i < 3; ++i) {
+    strides[i] = 1;
+    dil_in[i] = 1 << (i - (i_last + 1));
+    dil_out[i] = dil_in[i] * 2;
+  }
+  Planner P{h, c.proc_side, c.proc_side, 3};
+  const std::string pre = "backbone.";
+  const float eps = 1e-5f;
+  {
+    Op op;
+    op.type = OP_STEM;
+    op.name = pre + "conv1_conv";
+    op.wkey = op.name + ".weight"; op.biaskey = op.name + ".bias"; op.bnkey = pre + "conv1_bn"; op.bn_eps = eps;
+    op.Hin = op.Win = c.proc_side; op.Cin = 3; op.Cout = 64;
+    op.R = op.S = 7; op.stride = 2; op.pad_t = op.pad_l = 3; op.act = ACT_RELU;
+    op.Hout = op.Wout = (c.proc_side + 6 - 7) / 2 + 1;
+    const float mean[3] = {103.939f, 116.779f, 123.68f};  // caffe_preproc (builder.py:106-108): 255*x - mean, no channel swap
+    for (int i = 0; i < 3; ++i) { op.pre_scale[i] = 255.f; op.pre_shift[i] = -mean[i]; }
+    op.in_buf = BUF_NONE; op.out_buf = 0;
+    op.flops = 2.0 * op.Hout * op.Wout * 64 * 147;
+    P.H = op.Hout; P.W = op.Wout; P.C = 64; P.cur = 0;
+    P.track(P.H, P.W, P.C);
+    h->ops.push_back(op);
+    Op mp;  // ZeroPadding2D((1,1)) + MaxPooling2D(3, 2) (:187-193): the zero pad value takes part in the max
+    mp.type = OP_MAXPOOL; mp.name = pre + "pool1_pool";
+    mp.Hin = P.H; mp.Win = P.W; mp.Cin = mp.Cout = 64; mp.R = mp.S = 3; mp.stride = 2; mp.pad_t = mp.pad_l = 1;
+    mp.Hout = (P.H + 2 - 3) / 2 + 1; mp.Wout = (P.W + 2 - 3) / 2 + 1;
+    mp.in_buf = 0; mp.out_buf = 1;
+    P.H = mp.Hout; P.W = mp.Wout; P.cur = 1;
+    h->ops.push_back(mp);
+  }
+  const int counts[4] = {3, 4, 6, 3}, filters[4] = {64, 128, 256, 512};
+  for (int st = 0; st < 4; ++st) {
+    for (int bi = 0; bi < counts[st]; ++bi) {
+      const bool first = bi == 0;
+      // V1: stride on the first 1x1 and on the shortcut of block1; the 3x3 uses dil_out of its stack in EVERY block
+      const int stride = (st > 0 && first) ? strides[st - 1] : 1;
+      const int shift = (st > 0 && first && brs[st - 1]) ? 1 : 0;
+      const int dil = st == 0 ? dil_in[0] : dil_out[st - 1];
+      const int f = filters[st];
+      char nm[64];
+      snprintf(nm, sizeof(nm), "conv%d_block%d", st + 2, bi + 1);
+      const std::string b = pre + nm;
+      const int x_in = P.cur;
+      const int Hin = P.H, Win = P.W, Cin = P.C;
+      int sc = x_in;
+      if (first) {  // conv shortcut: strided 1x1 sampled at pixels shift::stride (Conv2DDenseSame semantics)
+        sc = P.pick({x_in});
+        P.conv_k(b + "_0_conv", b + "_0_conv.weight", b + "_0_conv.bias", b + "_0_bn", 4 * f, 1, stride, -shift, 0, ACT_NONE,
+                 x_in, sc, false, 1, eps);
+        Op& o = h->ops.back();
+        o.Hout = Hin / stride; o.Wout = Win / stride;
+        o.flops = 2.0 * o.Hout * o.Wout * o.Cout * Cin;
+        P.H = Hin; P.W = Win; P.C = Cin;  // the main branch restarts from the block input
+      }
+      int t1 = P.pick({x_in, sc});
+      P.conv_k(b + "_1_conv", b + "_1_conv.weight", b + "_1_conv.bias", b + "_1_bn", f, 1, stride, -shift, 0, ACT_RELU, x_in, t1,
+               false, 1, eps);
+      {
+        Op& o = h->ops.back();
+        o.Hout = Hin / stride; o.Wout = Win / stride;
+        o.flops = 2.0 * o.Hout * o.Wout * o.Cout * Cin;
+        P.H = o.Hout; P.W = o.Wout;
+      }
+      int t2 = P.pick({x_in, sc, t1});
+      P.conv_k(b + "_2_conv", b + "_2_conv.weight", b + "_2_conv.bias", b + "_2_bn", f, 3, 1, dil, 2 * dil, ACT_RELU, t1, t2,
+               false, dil, eps);
+      int t3 = P.pick({sc, t2});
+      const bool last = st == 3 && bi == counts[3] - 1;
+      Op& o3 = P.conv_k(b + "_3_conv", b + "_3_conv.weight", b + "_3_conv.bias", b + "_3_bn", 4 * f, 1, 1, 0, 0, ACT_RELU, t2,
+                        last ? BUF_FEATURES : t3, false, 1, eps);
+      o3.res_buf = sc;
+      o3.res_first = true;  // relu(shortcut + x)
+      P.cur = t3;
+    }
+  }
+  h->feat_side = P.H;
+  h->feat_c = P.C;
+  h->big_elems_per_crop = P.max_elems;
+  h->small_c = 4;
+  return MTB_OK;
+}
+
+// MobileNetV3-Small (metrabs_tf/backbones/mobilenet_v3.py:348-384 table, :490-553 block, :465-487 SE, :258-296 stem and
+// Conv_1 / Conv_2, :556-575 correct_pad; preprocessing 255*x then Rescaling(1/127.5, -1) = 2x-1, builder.py:116-117).
+int plan_mobilenetv3_small(mtb_handle* h) {
+  const mtb_config& c = h->cfg;
+  Planner P{h, c.proc_side, c.proc_side, 3};
+  const std::string pre = "backbone.";
+  {
+    Op op;
+    op.type = OP_STEM;
+    op.name = pre + "Conv";
+    op.wkey = op.name + ".weight"; op.bnkey = op.name + ".BatchNorm";
+    op.Hin = op.Win = c.proc_side; op.Cin = 3; op.Cout = 16;
+    op.R = op.S = 3; op.stride = 2; op.act = ACT_HSWISH;
+    op.Hout = op.Wout = (c.proc_side + 1) / 2;
+    // TF 'same' with stride 2: pad_total = max((out-1)*2 + 3 - in, 0), begin = pad_total / 2  (even input: (0,1))
+    const int pad_total = std::max((op.Hout - 1) * 2 + 3 - c.proc_side, 0);
+    op.pad_t = op.pad_l = pad_total / 2;
+    op.in_buf = BUF_NONE; op.out_buf = 0;
+    op.flops = 2.0 * op.Hout * op.Wout * 16 * 27;
+    P.H = op.Hout; P.W = op.Wout; P.C = 16; P.cur = 0;
+    P.track(P.H, P.W, P.C);
+    h->ops.push_back(op);
+  }
+  struct Row { int exp_ch, filters, k, stride; bool se; int act; bool br; };
+  const Row rows[11] = {{16, 16, 3, 2, true, ACT_RELU, false},     {72, 24, 3, 2, false, ACT_RELU, false},
+                        {88, 24, 3, 1, false, ACT_RELU, false},    {96, 40, 5, 2, true, ACT_HSWISH, false},
+                        {240, 40, 5, 1, true, ACT_HSWISH, false},  {240, 40, 5, 1, true, ACT_HSWISH, false},
+                        {120, 48, 5, 1, true, ACT_HSWISH, false},  {144, 48, 5, 1, true, ACT_HSWISH, false},
+                        {288, 96, 5, 2, true, ACT_HSWISH, true},   {576, 96, 5, 1, true, ACT_HSWISH, false},
+                        {576, 96, 5, 1, true, ACT_HSWISH, false}};
+  auto depth8 = [](double v) {  // _depth (:449-456)
+    int nv = std::max(8, (int)(v + 4) / 8 * 8);
+    if (nv < 0.9 * v) nv += 8;
+    return nv;
+  };
+  for (int bi = 0; bi < 11; ++bi) {
+    const Row& r = rows[bi];
+    const std::string b = pre + (bi == 0 ? std::string("expanded_conv") : "expanded_conv_" + std::to_string(bi));
+    const int x_in = P.cur, cin = P.C;
+    int t1 = x_in;
+    if (bi != 0) {
+      t1 = P.pick({x_in});
+      P.conv_k(b + ".expand", b + ".expand.weight", "", b + ".expand.BatchNorm", r.exp_ch, 1, 1, 0, 0, r.act, x_in, t1);
+    }
+    int t2 = P.pick({x_in, t1});
+    const int shift = (r.br && c.centered_stride) ? 1 : 0;
+    const int pad_total = r.k - 1, pad_beg = (r.k - 1) / 2 - (r.stride == 2 ? shift : 0);
+    P.conv_k(b + ".depthwise", b + ".depthwise.weight", "", b + ".depthwise.BatchNorm", r.exp_ch, r.k, r.stride, pad_beg, pad_total,
+             r.act, t1, t2, true);
+    if (r.se)
+      P.squeeze_excite(b + ".squeeze_excite", b + ".squeeze_excite.Conv", b + ".squeeze_excite.Conv_1", depth8(r.exp_ch * 0.25), t2,
+                       ACT_RELU, ACT_HSIGMOID);
+    int t3 = P.pick({x_in, t2});
+    Op& pr = P.conv_k(b + ".project", b + ".project.weight", "", b + ".project.BatchNorm", r.filters, 1, 1, 0, 0, ACT_NONE, t2, t3);
+    if (r.se) pr.scale_buf = BUF_SMALL0 + 2;
+    if (r.stride == 1 && cin == r.filters) pr.res_buf = x_in;
+    P.cur = t3;
+  }
+  {
+    int t1 = P.pick({P.cur});
+    P.conv_k(pre + "Conv_1", pre + "Conv_1.weight", "", pre + "Conv_1.BatchNorm", depth8(P.C * 6), 1, 1, 0, 0, ACT_HSWISH, P.cur, t1);
+    P.conv_k(pre + "Conv_2", pre + "Conv_2.weight", pre + "Conv_2.bias", "", 1024, 1, 1, 0, 0, ACT_HSWISH, t1, BUF_FEATURES);
+  }
+  h->feat_side = P.H;
+  h->feat_c = P.C;
+  h->big_elems_per_crop = P.max_elems;
+  h->small_c = std::max(P.max_small, 4);
+  return MTB_OK;
+}
+
 int plan(mtb_handle* h) {
   const mtb_config& c = h->cfg;
   h->ops.clear();
   switch (c.arch) {
     case MTB_ARCH_EFFNET: plan_effnet(h); break;
+    case MTB_ARCH_RESNET50: { int rc = plan_resnet50(h); if (rc) return rc; break; }
+    case MTB_ARCH_MOBILENETV3_SMALL: { int rc = plan_mobilenetv3_small(h); if (rc) return rc; break; }
     case MTB_ARCH_HEAD_ONLY:
       h->feat_side = c.proc_side / c.stride_test;
       h->feat_c = c.feature_channels;
@@ -280,10 +467,7 @@ int plan(mtb_handle* h) {
     default: return fail(h, MTB_ERR_UNSUPPORTED, "arch %d is not built yet", c.arch);
   }
   h->flops_per_crop = 0;
-  for (auto& op : h->ops) {
-    op.bn_eps = 1e-3f;
-    h->flops_per_crop += op.flops;
-  }
+  for (auto& op : h->ops) h->flops_per_crop += op.flops;
   // head: MetrabsHeads.conv_final, 1x1 conv with bias (models/metrabs.py:73)
   Op& hd = h->head;
   hd = Op();
@@ -418,6 +602,7 @@ struct ProfScope {
       }
     }
     h->prof_cls.push_back(cls);
+    h->prof_op.push_back(h->prof_cur_op);
     h->prof_flops.push_back(flops);
     h->prof_bytes.push_back(bytes);
     cudaEventRecord(h->prof_events[h->prof_used], st);
@@ -461,7 +646,8 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
     case OP_STEM: {
       StemParams p;
       p.in = crops; p.out = buf_ptr(ws, op.out_buf, features); p.w = op.d_w; p.bias = op.d_bias;
-      for (int i = 0; i < 4; ++i) { p.pre_scale[i] = 2.f; p.pre_shift[i] = -1.f; }  // PreprocLayer x*2-1
+      for (int i = 0; i < 3; ++i) { p.pre_scale[i] = op.pre_scale[i]; p.pre_shift[i] = op.pre_shift[i]; }
+      p.pre_scale[3] = 1.f; p.pre_shift[3] = 0.f;
       p.B = B; p.Hin = op.Hin; p.Win = op.Win; p.Cin = op.Cin; p.Hout = op.Hout; p.Wout = op.Wout; p.Cout = op.Cout;
       p.R = op.R; p.S = op.S; p.stride = op.stride; p.pad_t = op.pad_t; p.pad_l = op.pad_l; p.act = op.act;
       size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
@@ -481,8 +667,10 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
       p.w = op.d_w; p.bias = op.d_bias;
       p.B = B; p.Hin = op.Hin; p.Win = op.Win; p.Cin = op.Cin; p.Hout = op.Hout; p.Wout = op.Wout; p.Cout = op.Cout;
       p.R = op.R; p.S = op.S; p.stride = op.stride; p.dil = op.dil; p.pad_t = op.pad_t; p.pad_l = op.pad_l; p.act = op.act;
+      p.res_first = op.res_first ? 1 : 0;
       if (op.type == OP_DW) {
-        if (sizeof(T) == 2 && op.R == 3 && op.S == 3 && op.dil == 1 && op.Cout % 8 == 0 && (op.stride == 1 || op.stride == 2)) {
+        if (h->cfg.precision == MTB_PRECISION_BF16_TC && op.R == 3 && op.S == 3 && op.dil == 1 && op.Cout % 8 == 0 &&
+            (op.stride == 1 || op.stride == 2)) {
           float* pooled = nullptr;
           if (op.fused_pool) {
             pooled = (float*)buf_ptr(ws, BUF_SMALL0, features);
@@ -505,13 +693,13 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
         size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
         maxpool_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
       } else if (op.small_io) {
-        if (op.ksplit > 1) {
-          p.ksplit = op.ksplit;
-          cudaMemsetAsync(p.out, 0, (size_t)B * op.Cout * 4, st);
-        }
+        if (op.ksplit > 1) p.ksplit = op.ksplit;
         if (op.a_bias_from >= 0) {
-          p.a_bias = h->ops[op.a_bias_from].d_bias;
+          const Op& prod = h->ops[op.a_bias_from];
+          p.a_bias = prod.d_bias;
           p.a_act = op.a_act;
+          p.a_splits = prod.ksplit;
+          p.a_split_stride = (size_t)B * prod.Cout;
         }
         cudaError_t e = launch_conv_igemm<float, float>(p, st);
         if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "launch %s: %s", op.name.c_str(), cudaGetErrorString(e));
@@ -710,16 +898,24 @@ int mtb_create(const mtb_config* cfg, mtb_handle** out) {
 
 int mtb_destroy(mtb_handle* h) {
   if (!h) return MTB_OK;
-  DeviceGuard g(h->cfg.device);
-  for (void* p : h->dev_allocs) cudaFree(p);
-  if (h->stage) cudaFree(h->stage);
-  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
-  if (h->nccl_comm && h->nccl_lib) {
-    typedef int (*destroy_t)(void*);
-    destroy_t f = (destroy_t)dlsym(h->nccl_lib, "ncclCommDestroy");
-    if (f) f(h->nccl_comm);
+  const bool trace = getenv("MTB_TRACE_DESTROY") != nullptr;
+  if (trace) fprintf(stderr, "mtb_destroy: handle %p device %d allocs %zu events %zu stage %p\n", (void*)h, h->cfg.device,
+                     h->dev_allocs.size(), h->prof_events.size(), h->stage);
+  {
+    DeviceGuard g(h->cfg.device);
+    for (void* p : h->dev_allocs) cudaFree(p);
+    if (trace) fprintf(stderr, "mtb_destroy: weights freed\n");
+    if (h->stage) cudaFree(h->stage);
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    if (trace) fprintf(stderr, "mtb_destroy: events destroyed\n");
+    if (h->nccl_comm && h->nccl_lib) {
+      typedef int (*destroy_t)(void*);
+      destroy_t f = (destroy_t)dlsym(h->nccl_lib, "ncclCommDestroy");
+      if (f) f(h->nccl_comm);
+    }
   }
   delete h;
+  if (trace) fprintf(stderr, "mtb_destroy: done\n");
   return MTB_OK;
 }
 
@@ -764,10 +960,10 @@ int mtb_finalize_weights(mtb_handle* h) {
   DeviceGuard g(h->cfg.device);
   for (void* p : h->dev_allocs) cudaFree(p);
   h->dev_allocs.clear();
+  for (auto& op : h->ops) op.fused_pool = false;
   for (size_t i = 0; i + 1 < h->ops.size(); ++i) {
-    const bool fuse = is_bf16(h) && h->ops[i].type == OP_DW && h->ops[i + 1].type == OP_POOL;
-    h->ops[i].fused_pool = fuse;
-    h->ops[i + 1].fused_pool = fuse && h->ops[i + 1].type == OP_POOL;
+    const bool fuse = h->cfg.precision == MTB_PRECISION_BF16_TC && h->ops[i].type == OP_DW && h->ops[i + 1].type == OP_POOL;
+    if (fuse) h->ops[i].fused_pool = h->ops[i + 1].fused_pool = true;
   }
   for (auto& op : h->ops) {
     int rc = prepare_op_weights(h, op);
@@ -834,10 +1030,12 @@ int mtb_backbone_forward(mtb_handle* h, const float* crops, int batch, void* fea
   DeviceGuard g(h->cfg.device);
   h->launches = 0;
   Workspace ws = layout(h, batch, workspace);
-  for (const Op& op : h->ops) {
-    rc = run_op(h, op, crops, batch, ws, features, (cudaStream_t)stream);
+  for (size_t i = 0; i < h->ops.size(); ++i) {
+    h->prof_cur_op = (int)i;
+    rc = run_op(h, h->ops[i], crops, batch, ws, features, (cudaStream_t)stream);
     if (rc) return rc;
   }
+  h->prof_cur_op = -1;
   return MTB_OK;
 }
 
@@ -916,10 +1114,12 @@ int mtb_forward(mtb_handle* h, const float* crops, const float* intrinsics, int 
   h->launches = 0;
   Workspace ws = layout(h, batch, workspace);
   void* features = ws.base + ws.off_features;
-  for (const Op& op : h->ops) {
-    rc = run_op(h, op, crops, batch, ws, features, st);
+  for (size_t i = 0; i < h->ops.size(); ++i) {
+    h->prof_cur_op = (int)i;
+    rc = run_op(h, h->ops[i], crops, batch, ws, features, st);
     if (rc) return rc;
   }
+  h->prof_cur_op = -1;
   float* c2d = (float*)(ws.base + ws.off_c2d);
   float* c3d = (float*)(ws.base + ws.off_c3d);
   rc = head_decode_impl(h, features, batch, c2d, c3d, ws, st);
@@ -1063,6 +1263,7 @@ int mtb_profile_begin(mtb_handle* h, unsigned class_mask) {
   h->prof_mask = class_mask;
   h->prof_used = 0;
   h->prof_cls.clear();
+  h->prof_op.clear();
   h->prof_flops.clear();
   h->prof_bytes.clear();
   return MTB_OK;
@@ -1072,12 +1273,14 @@ int mtb_profile_end(mtb_handle* h, double* ms, double* flops, double* bytes, int
   if (!h || !ms || !flops || !bytes || !launches) return fail(h, MTB_ERR_INVALID_ARG, "null argument");
   DeviceGuard g(h->cfg.device);
   for (int i = 0; i < KC_COUNT; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
+  h->prof_op_ms.assign(h->ops.size(), 0.0);
   for (size_t i = 0; i < h->prof_cls.size(); ++i) {
     CUDA_TRY(h, cudaEventSynchronize(h->prof_events[2 * i + 1]));
     float t = 0.f;
     CUDA_TRY(h, cudaEventElapsedTime(&t, h->prof_events[2 * i], h->prof_events[2 * i + 1]));
     int cls = h->prof_cls[i];
     ms[cls] += t;
+    if (h->prof_op[i] >= 0 && h->prof_op[i] < (int)h->prof_op_ms.size()) h->prof_op_ms[h->prof_op[i]] += t;
     flops[cls] += h->prof_flops[i];
     bytes[cls] += h->prof_bytes[i];
     launches[cls] += (cls == KC_RECON) ? 2 : 1;
@@ -1085,8 +1288,22 @@ int mtb_profile_end(mtb_handle* h, double* ms, double* flops, double* bytes, int
   h->prof_mask = 0;
   h->prof_used = 0;
   h->prof_cls.clear();
+  h->prof_op.clear();
   h->prof_flops.clear();
   h->prof_bytes.clear();
+  return MTB_OK;
+}
+
+/* per-op device time (ms) accumulated by the last mtb_profile_begin/end window, plus each op's algorithmic FLOPs and
+ * bytes PER CROP and its kernel class */
+int mtb_profile_op_times(const mtb_handle* h, double* ms, double* flops_per_crop, double* bytes_per_crop, int* cls, int n) {
+  if (!h || !ms || n < (int)h->ops.size()) return fail(h, MTB_ERR_INVALID_ARG, "invalid arguments");
+  for (size_t i = 0; i < h->ops.size(); ++i) {
+    ms[i] = i < h->prof_op_ms.size() ? h->prof_op_ms[i] : 0.0;
+    if (flops_per_crop) flops_per_crop[i] = h->ops[i].flops;
+    if (bytes_per_crop) bytes_per_crop[i] = op_bytes(h, h->ops[i], 1);
+    if (cls) cls[i] = op_class(h->ops[i]);
+  }
   return MTB_OK;
 }
 

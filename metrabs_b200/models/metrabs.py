@@ -12,16 +12,13 @@ import torch
 from torch import nn
 
 from metrabs_b200 import _lib
-from metrabs_b200.backbones.efficientnet import Features
 from metrabs_b200.engine import Engine, make_config
 from metrabs_b200.util import get_config
 
 
 def _find_features(backbone):
-    if isinstance(backbone, Features):
-        return backbone
     for m in backbone.modules():
-        if isinstance(m, Features):
+        if hasattr(m, 'arch') and hasattr(m, 'last_channel') and hasattr(m, 'stages'):
             return m
     raise TypeError('backbone must contain a metrabs_b200.backbones.*.Features module '
                     '(e.g. Sequential(PreprocLayer(), efficientnet_v2_s().features))')
@@ -79,7 +76,7 @@ class Metrabs(nn.Module):
         if self._engine is None or self._engine.cfg.device != index:
             feats = self._features[0]
             self._engine = Engine(make_config(self._cfg, self.joint_info.n_joints, stages=feats.stages,
-                                              last_channel=feats.last_channel, device=index))
+                                              last_channel=feats.last_channel, arch=feats.arch, device=index))
             self._dirty = True
         if self._dirty:
             self._engine.load_state_dict(self.state_dict())

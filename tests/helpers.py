@@ -28,3 +28,14 @@ def device_model(name, pcfg: port.PathConfig, n_joints, sd, precision='fp32'):
 
 def rel_err(a, b):
     return port.relative_error(a.detach().float().cpu(), torch.as_tensor(b).float().cpu())
+
+
+def device_model_tf(kind, pcfg: port.PathConfig, n_joints, sd, precision='fp32'):
+    """kind: 'resnet50' | 'mobilenetv3-small' (TF-only backbones; key schema defined by this build)."""
+    from metrabs_b200.backbones import mobilenet_v3, resnet
+    cfg = metrabs_b200.Config(**{k: v for k, v in dataclasses.asdict(pcfg).items()}, precision=precision)
+    metrabs_b200.set_config(cfg)
+    feats = resnet.resnet50() if kind == 'resnet50' else mobilenet_v3.mobilenet_v3_small()
+    m = Metrabs(feats, joint_info(n_joints)).eval()
+    m.load_state_dict(sd, strict=True)
+    return m.cuda()

@@ -50,6 +50,24 @@ def test_tc_ops_match_cuda_core_ops(H, name, side, batch):
     print(f'{name}@{side}: {len(seen)} distinct op shapes, worst rel err {worst[0]:.2e} at {worst[1]}')
 
 
+def test_fused_depthwise_pooling_matches_separate_pool(H):
+    """BF16_TC fuses the SE squeeze into the depthwise kernel (block reduction + atomics); BF16_SIMT runs the plain
+    depthwise kernel and a separate pooling pass.  Compared through the op chain up to each avgpool of the first
+    MBConv stage (short prefix, so upstream bf16 drift stays small)."""
+    name, side, batch = 'efficientnetv2-s', 256, 3
+    pcfg = port.PathConfig(proc_side=side)
+    sd = port.make_effnet_state_dict(port.effnet_spec(name), pcfg, 8, seed=0, calib_batch=2)
+    e_tc = H.device_model(name, pcfg, 8, sd, precision='bf16').engine()
+    e_ref = H.device_model(name, pcfg, 8, sd, precision='bf16_simt').engine()
+    crops, _ = port.synthetic_inputs(batch, side, seed=0)
+    pools = [i for i, n in enumerate(e_tc.op_names()) if n.endswith('.avgpool')][:3]
+    for i in pools:
+        a = e_tc.debug_run_ops(crops.cuda(), i + 1)
+        b = e_ref.debug_run_ops(crops.cuda(), i + 1)
+        err = port.relative_error(a.cpu(), b.cpu())
+        assert err < 3e-2, (i, err)
+
+
 @pytest.mark.parametrize('channels,hw,j,depth,batch', [
     (1280, 8, 24, 8, 9),      # EffNetV2 @256: P=64, 4 crops per MMA, ragged last group
     (1280, 8, 122, 8, 5),     # c4: N=1098 -> 9 channel tiles, last one ragged

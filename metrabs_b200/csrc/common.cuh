@@ -22,6 +22,33 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
+// compile-time activation (exact expf forms: used by the fp32 parity kernels).  A runtime switch inside per-element code
+// gets if-converted into every branch, so kernels dispatch ONCE per thread with act_dispatch and run a templated body.
+template <int ACT>
+__device__ __forceinline__ float act_t(float x) {
+  if constexpr (ACT == ACT_SILU) return x * sigmoidf_(x);
+  else if constexpr (ACT == ACT_RELU) return fmaxf(x, 0.0f);
+  else if constexpr (ACT == ACT_HSWISH) return x * fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f);
+  else if constexpr (ACT == ACT_SIGMOID) return sigmoidf_(x);
+  else if constexpr (ACT == ACT_HSIGMOID) return fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f);
+  else return x;
+}
+template <int V>
+struct IntTag {
+  static constexpr int value = V;
+};
+template <typename F>
+__device__ __forceinline__ void act_dispatch(int act, F&& f) {
+  switch (act) {
+    case ACT_SILU: f(IntTag<ACT_SILU>{}); break;
+    case ACT_RELU: f(IntTag<ACT_RELU>{}); break;
+    case ACT_HSWISH: f(IntTag<ACT_HSWISH>{}); break;
+    case ACT_SIGMOID: f(IntTag<ACT_SIGMOID>{}); break;
+    case ACT_HSIGMOID: f(IntTag<ACT_HSIGMOID>{}); break;
+    default: f(IntTag<ACT_NONE>{}); break;
+  }
+}
+
 // ---- 4-wide vector load/store for fp32 and bf16 activation storage -------------------------------------
 template <typename T>
 __device__ __forceinline__ float4 load4(const T* p);

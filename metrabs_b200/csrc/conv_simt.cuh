@@ -167,39 +167,54 @@ conv_igemm_kernel(ConvParams p) {
     }
   }
 
-  // epilogue: bias + activation (+ residual)
+  // epilogue: bias + activation (+ residual); the activation is dispatched once, outside the per-element code
   TOut* __restrict__ out = reinterpret_cast<TOut*>(p.out);
   const TOut* __restrict__ res = reinterpret_cast<const TOut*>(p.res);
+  if (p.ksplit > 1) {  // raw partial sums of this K slice; the consumer sums the slices and applies bias/activation
+    if constexpr (sizeof(TOut) == 4) {
 #pragma unroll
-  for (int gi = 0; gi < GM; ++gi)
+      for (int gi = 0; gi < GM; ++gi)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int m = m0 + ty * 4 + gi * GSM + i;
-      if (m >= M) continue;
+        for (int i = 0; i < 4; ++i) {
+          int m = m0 + ty * 4 + gi * GSM + i;
+          if (m >= M) continue;
 #pragma unroll
-      for (int gj = 0; gj < GN; ++gj) {
-        int n = n0 + tx * 4 + gj * GSN;
-        if (n >= p.Cout) continue;
-        if (p.ksplit > 1) {  // raw partial sums of this K slice; the consumer sums the slices and applies bias/activation
-          if constexpr (sizeof(TOut) == 4) {
+          for (int gj = 0; gj < GN; ++gj) {
+            int n = n0 + tx * 4 + gj * GSN;
+            if (n >= p.Cout) continue;
             float* o = reinterpret_cast<float*>(out) + ((size_t)blockIdx.z * M + m) * p.Cout + n;
             *reinterpret_cast<float4*>(o) = make_float4(acc[gi * 4 + i][gj * 4 + 0], acc[gi * 4 + i][gj * 4 + 1],
                                                         acc[gi * 4 + i][gj * 4 + 2], acc[gi * 4 + i][gj * 4 + 3]);
           }
-          continue;
         }
-        float4 bv = *reinterpret_cast<const float4*>(p.bias + n);
-        float4 v = make_float4(acc[gi * 4 + i][gj * 4 + 0] + bv.x, acc[gi * 4 + i][gj * 4 + 1] + bv.y,
-                               acc[gi * 4 + i][gj * 4 + 2] + bv.z, acc[gi * 4 + i][gj * 4 + 3] + bv.w);
-        size_t o = (size_t)m * p.Cout + n;
-        float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (res) rv = load4<TOut>(res + o);
-        if (p.res_first) { v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w; }
-        v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
-        if (!p.res_first) { v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w; }
-        store4<TOut>(out + o, v);
-      }
     }
+    return;
+  }
+  act_dispatch(p.act, [&](auto tag) {
+    constexpr int ACT = decltype(tag)::value;
+#pragma unroll
+    for (int gi = 0; gi < GM; ++gi)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int m = m0 + ty * 4 + gi * GSM + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int gj = 0; gj < GN; ++gj) {
+          int n = n0 + tx * 4 + gj * GSN;
+          if (n >= p.Cout) continue;
+          float4 bv = *reinterpret_cast<const float4*>(p.bias + n);
+          float4 v = make_float4(acc[gi * 4 + i][gj * 4 + 0] + bv.x, acc[gi * 4 + i][gj * 4 + 1] + bv.y,
+                                 acc[gi * 4 + i][gj * 4 + 2] + bv.z, acc[gi * 4 + i][gj * 4 + 3] + bv.w);
+          size_t o = (size_t)m * p.Cout + n;
+          float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (res) rv = load4<TOut>(res + o);
+          if (p.res_first) { v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w; }
+          v.x = act_t<ACT>(v.x); v.y = act_t<ACT>(v.y); v.z = act_t<ACT>(v.z); v.w = act_t<ACT>(v.w);
+          if (!p.res_first) { v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w; }
+          store4<TOut>(out + o, v);
+        }
+      }
+  });
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -233,10 +248,10 @@ __global__ void __launch_bounds__(256) dwconv_kernel(ConvParams p) {
         acc.w = fmaf(v.w, wv.w, acc.w);
       }
     }
-    acc.x = apply_act(acc.x, p.act);
-    acc.y = apply_act(acc.y, p.act);
-    acc.z = apply_act(acc.z, p.act);
-    acc.w = apply_act(acc.w, p.act);
+    act_dispatch(p.act, [&](auto tag) {
+      constexpr int ACT = decltype(tag)::value;
+      acc.x = act_t<ACT>(acc.x); acc.y = act_t<ACT>(acc.y); acc.z = act_t<ACT>(acc.z); acc.w = act_t<ACT>(acc.w);
+    });
     store4<T>(out + pix * p.Cout + c, acc);
   }
 }
@@ -248,7 +263,26 @@ __global__ void __launch_bounds__(256) dwconv_kernel(ConvParams p) {
 // block and added (already divided by Hout*Wout) to pooled[b][c] with one atomic per channel per block, so the
 // pooling pass never re-reads the tensor.  grid (ceil(C/256), ceil(strips/8), B), block (32, 8).
 // ----------------------------------------------------------------------------------------------------------
-template <int STRIDE>
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int ACT>
+__device__ __forceinline__ float fast_act(float x) {  // compile-time activation; SiLU with one MUFU op (bf16 outputs)
+  if constexpr (ACT == ACT_SILU) {
+    float h = 0.5f * x;
+    return fmaf(h, fast_tanh(h), h);
+  } else if constexpr (ACT == ACT_RELU) {
+    return fmaxf(x, 0.0f);
+  } else if constexpr (ACT == ACT_HSWISH) {
+    return x * __saturatef(fmaf(x, 1.0f / 6.0f, 0.5f));
+  } else {
+    return x;
+  }
+}
+
+template <int STRIDE, int ACT>
 __global__ void __launch_bounds__(256) dwconv3x3_pool_bf16_kernel(ConvParams p, float* __restrict__ pooled) {
   constexpr int OW = 4;                          // outputs per thread along W
   constexpr int NCOL = (OW - 1) * STRIDE + 3;    // input columns feeding them
@@ -323,7 +357,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_pool_bf16_kernel(ConvParams p, 
       __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float a0 = apply_act(acc[i][2 * k], p.act), a1 = apply_act(acc[i][2 * k + 1], p.act);
+        float a0 = fast_act<ACT>(acc[i][2 * k]), a1 = fast_act<ACT>(acc[i][2 * k + 1]);
         o2[k] = __floats2bfloat162_rn(a0, a1);
         float2 back = __bfloat1622float2(o2[k]);  // pool what the next layer will actually read
         psum[2 * k] += back.x;
@@ -398,10 +432,10 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(StemParams p) {
         }
       }
     }
-    acc.x = apply_act(acc.x, p.act);
-    acc.y = apply_act(acc.y, p.act);
-    acc.z = apply_act(acc.z, p.act);
-    acc.w = apply_act(acc.w, p.act);
+    act_dispatch(p.act, [&](auto tag) {
+      constexpr int ACT = decltype(tag)::value;
+      acc.x = act_t<ACT>(acc.x); acc.y = act_t<ACT>(acc.y); acc.z = act_t<ACT>(acc.z); acc.w = act_t<ACT>(acc.w);
+    });
     store4<TOut>(out + pix * p.Cout + c, acc);
   }
 }

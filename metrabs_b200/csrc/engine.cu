@@ -670,7 +670,7 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
       p.res_first = op.res_first ? 1 : 0;
       if (op.type == OP_DW) {
         if (h->cfg.precision == MTB_PRECISION_BF16_TC && op.R == 3 && op.S == 3 && op.dil == 1 && op.Cout % 8 == 0 &&
-            (op.stride == 1 || op.stride == 2)) {
+            (op.stride == 1 || op.stride == 2) && (op.act == ACT_SILU || op.act == ACT_RELU || op.act == ACT_HSWISH)) {
           float* pooled = nullptr;
           if (op.fused_pool) {
             pooled = (float*)buf_ptr(ws, BUF_SMALL0, features);
@@ -678,8 +678,16 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
           }
           const int strips = op.Hout * ((op.Wout + 3) / 4);
           dim3 grid((op.Cout / 8 + 31) / 32, (strips + 7) / 8, B), block(32, 8);
-          if (op.stride == 1) dwconv3x3_pool_bf16_kernel<1><<<grid, block, 0, st>>>(p, pooled);
-          else dwconv3x3_pool_bf16_kernel<2><<<grid, block, 0, st>>>(p, pooled);
+          if (op.act == ACT_SILU) {
+            if (op.stride == 1) dwconv3x3_pool_bf16_kernel<1, ACT_SILU><<<grid, block, 0, st>>>(p, pooled);
+            else dwconv3x3_pool_bf16_kernel<2, ACT_SILU><<<grid, block, 0, st>>>(p, pooled);
+          } else if (op.act == ACT_RELU) {
+            if (op.stride == 1) dwconv3x3_pool_bf16_kernel<1, ACT_RELU><<<grid, block, 0, st>>>(p, pooled);
+            else dwconv3x3_pool_bf16_kernel<2, ACT_RELU><<<grid, block, 0, st>>>(p, pooled);
+          } else {
+            if (op.stride == 1) dwconv3x3_pool_bf16_kernel<1, ACT_HSWISH><<<grid, block, 0, st>>>(p, pooled);
+            else dwconv3x3_pool_bf16_kernel<2, ACT_HSWISH><<<grid, block, 0, st>>>(p, pooled);
+          }
         } else {
           size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
           dwconv_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
@@ -905,8 +913,14 @@ int mtb_destroy(mtb_handle* h) {
     DeviceGuard g(h->cfg.device);
     for (void* p : h->dev_allocs) cudaFree(p);
     if (trace) fprintf(stderr, "mtb_destroy: weights freed\n");
-    if (h->stage) cudaFree(h->stage);
-    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    if (h->stage) {
+      cudaError_t e = cudaFree(h->stage);
+      if (trace) fprintf(stderr, "mtb_destroy: stage freed (%s)\n", cudaGetErrorString(e));
+    }
+    for (size_t i = 0; i < h->prof_events.size(); ++i) {
+      cudaError_t e = cudaEventDestroy(h->prof_events[i]);
+      if (trace && (i < 2 || e != cudaSuccess)) fprintf(stderr, "mtb_destroy: event %zu destroyed (%s)\n", i, cudaGetErrorString(e));
+    }
     if (trace) fprintf(stderr, "mtb_destroy: events destroyed\n");
     if (h->nccl_comm && h->nccl_lib) {
       typedef int (*destroy_t)(void*);

@@ -471,6 +471,17 @@ __global__ void __launch_bounds__(256) pool_mean_kernel(const T* __restrict__ in
   }
 }
 
+// sums the split-K partial slices of a squeeze-excitation fc1 ([ksplit][B][C] raw sums), adds the bias and applies the
+// activation: hidden[b][c] = act(sum_z partial[z][b][c] + bias[c]).  Fixed summation order (deterministic).
+__global__ void __launch_bounds__(256) se_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
+                                                        float* __restrict__ out, int n, int C, int ksplit, int act) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = 0.f;
+  for (int z = 0; z < ksplit; ++z) v += partial[(size_t)z * n + i];
+  out[i] = apply_act(v + bias[i % C], act);
+}
+
 // max pool (ResNet stem, metrabs_tf/backbones/resnet.py:187-193), NHWC.  The reference pads with ZeroPadding2D and
 // pools VALID, so an out-of-bounds tap contributes the value 0 to the max.
 template <typename T>

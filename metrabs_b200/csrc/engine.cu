@@ -173,7 +173,7 @@ struct Planner {
     f2.Cin = csq; f2.Cout = cexp; f2.act = act2; f2.small_io = true; f2.pad_ok = true;
     f2.in_buf = BUF_SMALL0 + 1; f2.out_buf = BUF_SMALL0 + 2;
     f2.flops = 2.0 * cexp * csq_real;
-    if (f1.ksplit > 1) { f2.a_bias_from = f1_index; f2.a_act = act1; }
+    (void)f1_index;
     h->ops.push_back(f2);
     max_small = std::max(max_small, cexp);
   }
@@ -701,15 +701,18 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
         size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
         maxpool_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
       } else if (op.small_io) {
-        if (op.ksplit > 1) p.ksplit = op.ksplit;
-        if (op.a_bias_from >= 0) {
-          const Op& prod = h->ops[op.a_bias_from];
-          p.a_bias = prod.d_bias;
-          p.a_act = op.a_act;
-          p.a_splits = prod.ksplit;
-          p.a_split_stride = (size_t)B * prod.Cout;
+        float* final_out = (float*)p.out;
+        if (op.ksplit > 1) {  // split-K partial slices go to the (still unused) scale buffer, then one tiny reduce kernel
+          p.ksplit = op.ksplit;
+          p.out = buf_ptr(ws, BUF_SMALL0 + 2, features);
         }
         cudaError_t e = launch_conv_igemm<float, float>(p, st);
+        if (e == cudaSuccess && op.ksplit > 1) {
+          const int n = B * op.Cout;
+          se_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>((const float*)p.out, op.d_bias, final_out, n, op.Cout, op.ksplit, op.act);
+          h->launches++;
+          e = cudaGetLastError();
+        }
         if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "launch %s: %s", op.name.c_str(), cudaGetErrorString(e));
       } else if (op.tc.ready) {
         if (op.scale_buf != BUF_NONE) {  // squeeze-excitation scale applied in place ahead of the tensor-core projection

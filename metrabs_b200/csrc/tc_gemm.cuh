@@ -129,6 +129,19 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                       // layout type: SWIZZLE_128B
   return d;
 }
+// same for rows of BK bf16: BK = 64 -> 128 B rows / SWIZZLE_128B (type 2), BK = 32 -> 64 B rows / SWIZZLE_64B (type 4);
+// 8-row groups are 8*row_bytes apart
+template <int BK>
+__device__ __forceinline__ uint64_t umma_smem_desc_k(uint32_t smem_addr) {
+  constexpr uint64_t sbo = (8 * BK * 2) >> 4;
+  constexpr uint64_t layout = BK == 64 ? 2 : 4;
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= sbo << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n.
 __host__ __device__ inline uint32_t umma_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -155,6 +168,7 @@ struct TcConvParams {
   int n_tiles, m_tiles, kchunks, taps;
   int act, res_first;   // res_first: add the residual BEFORE the activation (ResNet), else after (EfficientNet)
   int Hout, Wout, tiles_w, tiles_h, pad_t, pad_l, S, stride, dil;
+  int bk;       // K elements per pipeline stage: 64 (128B swizzle) or 32 (64B swizzle, for Cin whose last 64-chunk is mostly empty)
 };
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -199,7 +213,7 @@ __device__ __forceinline__ void tma_store_wait_read() {
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ACT: epilogue activation; RES: 0 no residual, 1 residual added AFTER the activation (EfficientNet), 2 BEFORE (ResNet)
-template <int ACT, int RES>
+template <int ACT, int RES, int BK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const TcConvParams p) {
@@ -238,7 +252,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int num_kb = p.taps * p.kchunks;
-  const uint32_t stage_tx = TC_A_BYTES + (uint32_t)p.bn * TC_BK * 2;
+  const uint32_t stage_tx = (uint32_t)(TC_BM + p.bn) * BK * 2;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -262,12 +276,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sb = sa + TC_A_BYTES;
           mbar_expect_tx(&full[stage], stage_tx);
           if (p.mode == 0) {
-            tma_load_2d(sa, &tmA, &full[stage], kc * TC_BK, m_blk * TC_BM);
+            tma_load_2d(sa, &tmA, &full[stage], kc * BK, m_blk * TC_BM);
           } else {
             const int r = tap / p.S, s = tap - r * p.S;
-            tma_load_4d(sa, &tmA, &full[stage], kc * TC_BK, iw0 + s * p.dil, ih0 + r * p.dil, b);
+            tma_load_4d(sa, &tmA, &full[stage], kc * BK, iw0 + s * p.dil, ih0 + r * p.dil, b);
           }
-          tma_load_2d(sb, &tmB, &full[stage], tap * p.Cin + kc * TC_BK, n_blk * p.bn);
+          tma_load_2d(sb, &tmB, &full[stage], tap * p.Cin + kc * BK, n_blk * p.bn);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -292,8 +306,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
           const uint32_t sb = sa + TC_A_BYTES;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            umma_bf16(d_tmem, umma_smem_desc(sa + k * 32), umma_smem_desc(sb + k * 32), idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16(d_tmem, umma_smem_desc_k<BK>(sa + k * 32), umma_smem_desc_k<BK>(sb + k * 32), idesc, (kb | k) != 0);
           }
           umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -449,29 +463,33 @@ inline tmap_encode_fn get_tmap_encode() {
 }
 
 // rank-2 bf16 tensor [rows][cols] (cols contiguous), box [box_rows][64], 128B swizzle, OOB -> 0
-inline const char* make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+inline const char* make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                                uint32_t box_cols = TC_BK) {
   tmap_encode_fn enc = get_tmap_encode();
   if (!enc) return "cuTensorMapEncodeTiled unavailable";
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {TC_BK, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(2d) failed";
 }
 // rank-4 bf16 NHWC tensor [B][H][W][C]; box = 64 channels x (TILE_W x TILE_H) pixels sampled every `stride` pixels
 // (element strides: to load N elements along a dimension with traversal stride s, boxDim = N*s)
-inline const char* make_tmap_nhwc(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t stride) {
+inline const char* make_tmap_nhwc(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t stride,
+                                  uint32_t box_c = TC_BK) {
   tmap_encode_fn enc = get_tmap_encode();
   if (!enc) return "cuTensorMapEncodeTiled unavailable";
   cuuint64_t dims[4] = {C, W, H, B};
   cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
-  cuuint32_t box[4] = {TC_BK, TC_TILE_W * stride, TC_TILE_H * stride, 1};
+  cuuint32_t box[4] = {box_c, TC_TILE_W * stride, TC_TILE_H * stride, 1};
   cuuint32_t estr[4] = {1, stride, stride, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(4d) failed";
 }
@@ -554,18 +572,23 @@ inline int tc_pick_bn(int cout, int m_tiles, int num_kb) {
   return best;
 }
 
-template <int ACT, int RES>
-inline const char* tc_conv_launch_t(int grid, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const TcConvParams& q,
+template <int ACT, int RES, int BK>
+inline const char* tc_conv_launch_k(int grid, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const TcConvParams& q,
                                     cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_conv_kernel<ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_conv_kernel<ACT, RES, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
       return "cannot raise dynamic shared memory for tc_conv_kernel";
     attr_set = true;
   }
-  tc_conv_kernel<ACT, RES><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, b, o, q);
+  tc_conv_kernel<ACT, RES, BK><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, b, o, q);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+template <int ACT, int RES>
+inline const char* tc_conv_launch_t(int grid, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const TcConvParams& q,
+                                    cudaStream_t st) {
+  return q.bk == 32 ? tc_conv_launch_k<ACT, RES, 32>(grid, a, b, o, q, st) : tc_conv_launch_k<ACT, RES, 64>(grid, a, b, o, q, st);
 }
 
 template <int ACT>
@@ -595,7 +618,9 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
   q.mode = (p.R == 1 && p.stride == 1) ? 0 : 1;
   q.Cout = p.Cout; q.Cin = p.Cin; q.act = p.act; q.res_first = res_first ? 1 : 0;
   q.taps = w.taps; q.S = w.S; q.stride = p.stride; q.dil = p.dil;
-  q.kchunks = (p.Cin + TC_BK - 1) / TC_BK;
+  const int rem = p.Cin % 64;
+  q.bk = (rem != 0 && rem <= 32) ? 32 : 64;  // e.g. Cin = 32, 96, 160, 224: no zero-padded half chunk
+  q.kchunks = (p.Cin + q.bk - 1) / q.bk;
   q.Hout = p.Hout; q.Wout = p.Wout; q.pad_t = p.pad_t; q.pad_l = p.pad_l;
   q.tiles_w = (p.Wout + TC_TILE_W - 1) / TC_TILE_W;
   q.tiles_h = (p.Hout + TC_TILE_H - 1) / TC_TILE_H;
@@ -605,10 +630,10 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
   q.bn = bn;
   q.n_tiles = (p.Cout + bn - 1) / bn;
   if (w.cached_in != p.in || w.cached_out != p.out || w.cached_B != p.B || w.cached_bn != bn) {
-    const char* e = q.mode == 0 ? make_tmap_2d(&w.mapA, p.in, (uint64_t)q.M, (uint64_t)p.Cin, TC_BM)
-                                : make_tmap_nhwc(&w.mapA, p.in, p.B, p.Hin, p.Win, p.Cin, (uint32_t)p.stride);
+    const char* e = q.mode == 0 ? make_tmap_2d(&w.mapA, p.in, (uint64_t)q.M, (uint64_t)p.Cin, TC_BM, (uint32_t)q.bk)
+                                : make_tmap_nhwc(&w.mapA, p.in, p.B, p.Hin, p.Win, p.Cin, (uint32_t)p.stride, (uint32_t)q.bk);
     if (e) return e;
-    e = make_tmap_2d(&w.mapB, w.d_w, (uint64_t)p.Cout, (uint64_t)w.taps * p.Cin, (uint32_t)bn);
+    e = make_tmap_2d(&w.mapB, w.d_w, (uint64_t)p.Cout, (uint64_t)w.taps * p.Cin, (uint32_t)bn, (uint32_t)q.bk);
     if (e) return e;
     e = q.mode == 0 ? make_tmap_2d(&w.mapO, p.out, (uint64_t)q.M, (uint64_t)p.Cout, TC_BM)
                     : make_tmap_nhwc(&w.mapO, p.out, p.B, p.Hout, p.Wout, p.Cout, 1);

@@ -441,6 +441,62 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(StemParams p) {
 }
 
 // ----------------------------------------------------------------------------------------------------------
+// stem, second form: one thread per (pixel, CPT output channels) - the R*S*Cin input taps are loaded ONCE per pixel
+// (the first form re-loads them in each of its Cout/4 threads) and every weight float4 is a shared-memory broadcast.
+// ----------------------------------------------------------------------------------------------------------
+template <typename TOut, int CPT>
+__global__ void __launch_bounds__(128) stem_conv_wide_kernel(StemParams p) {
+  extern __shared__ float sw[];  // weights [R*S*Cin][Cout] + bias [Cout]
+  const int K = p.R * p.S * p.Cin;
+  for (int i = threadIdx.x; i < K * p.Cout; i += blockDim.x) sw[i] = p.w[i];
+  float* sb = sw + K * p.Cout;
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sb[i] = p.bias[i];
+  __syncthreads();
+  TOut* __restrict__ out = reinterpret_cast<TOut*>(p.out);
+  const int groups = p.Cout / CPT;
+  const size_t total = (size_t)p.B * p.Hout * p.Wout * groups;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(idx % groups) * CPT;
+    size_t pix = idx / groups;
+    int ow = (int)(pix % p.Wout);
+    size_t t = pix / p.Wout;
+    int oh = (int)(t % p.Hout);
+    int b = (int)(t / p.Hout);
+    float acc[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[j] = sb[c0 + j];
+    for (int r = 0; r < p.R; ++r) {
+      int ih = oh * p.stride - p.pad_t + r;
+      if (ih < 0 || ih >= p.Hin) continue;
+      for (int s = 0; s < p.S; ++s) {
+        int iw = ow * p.stride - p.pad_l + s;
+        if (iw < 0 || iw >= p.Win) continue;
+        for (int ci = 0; ci < p.Cin; ++ci) {
+          float v = __ldg(p.in + ((size_t)(b * p.Cin + ci) * p.Hin + ih) * p.Win + iw) * p.pre_scale[ci] + p.pre_shift[ci];
+          const float* wrow = sw + (size_t)((r * p.S + s) * p.Cin + ci) * p.Cout + c0;
+#pragma unroll
+          for (int j = 0; j < CPT; j += 4) {
+            float4 wv = *reinterpret_cast<const float4*>(wrow + j);
+            acc[j + 0] = fmaf(v, wv.x, acc[j + 0]);
+            acc[j + 1] = fmaf(v, wv.y, acc[j + 1]);
+            acc[j + 2] = fmaf(v, wv.z, acc[j + 2]);
+            acc[j + 3] = fmaf(v, wv.w, acc[j + 3]);
+          }
+        }
+      }
+    }
+    act_dispatch(p.act, [&](auto tag) {
+      constexpr int ACT = decltype(tag)::value;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) acc[j] = act_t<ACT>(acc[j]);
+    });
+#pragma unroll
+    for (int j = 0; j < CPT; j += 4)
+      store4<TOut>(out + pix * p.Cout + c0 + j, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
 // global average pool over the spatial axes (squeeze of squeeze-excitation): in [B,P,C] -> mean [B,C] fp32.
 // grid (ceil(C/128), B), block (32, 8).
 // ----------------------------------------------------------------------------------------------------------

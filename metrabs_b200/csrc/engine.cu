@@ -650,9 +650,12 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
       p.pre_scale[3] = 1.f; p.pre_shift[3] = 0.f;
       p.B = B; p.Hin = op.Hin; p.Win = op.Win; p.Cin = op.Cin; p.Hout = op.Hout; p.Wout = op.Wout; p.Cout = op.Cout;
       p.R = op.R; p.S = op.S; p.stride = op.stride; p.pad_t = op.pad_t; p.pad_l = op.pad_l; p.act = op.act;
-      size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
       size_t smem = ((size_t)op.R * op.S * op.Cin + 1) * op.Cout * 4;
-      stem_conv_kernel<T><<<grid_for(total, 256), 256, smem, st>>>(p);
+      const size_t pixels = (size_t)B * op.Hout * op.Wout;
+      if (op.Cout % 32 == 0) stem_conv_wide_kernel<T, 32><<<grid_for(pixels * (op.Cout / 32), 128), 128, smem, st>>>(p);
+      else if (op.Cout % 24 == 0) stem_conv_wide_kernel<T, 24><<<grid_for(pixels * (op.Cout / 24), 128), 128, smem, st>>>(p);
+      else if (op.Cout % 16 == 0) stem_conv_wide_kernel<T, 16><<<grid_for(pixels * (op.Cout / 16), 128), 128, smem, st>>>(p);
+      else stem_conv_kernel<T><<<grid_for(pixels * (op.Cout / 4), 256), 256, smem, st>>>(p);
       h->launches++;
       break;
     }
@@ -923,6 +926,10 @@ int mtb_destroy(mtb_handle* h) {
     for (size_t i = 0; i < h->prof_events.size(); ++i) {
       cudaError_t e = cudaEventDestroy(h->prof_events[i]);
       if (trace && (i < 2 || e != cudaSuccess)) fprintf(stderr, "mtb_destroy: event %zu destroyed (%s)\n", i, cudaGetErrorString(e));
+      if (e != cudaSuccess) {  // e.g. cudaErrorContextIsDestroyed during process teardown: the driver owns them now
+        cudaGetLastError();
+        break;
+      }
     }
     if (trace) fprintf(stderr, "mtb_destroy: events destroyed\n");
     if (h->nccl_comm && h->nccl_lib) {

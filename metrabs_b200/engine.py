@@ -1,6 +1,5 @@
 """Thin object wrapper over the C handle (``mtb_handle``): owns the torch-allocated workspace and output tensors,
 passes raw device pointers and the current CUDA stream to libmetrabs_b200.so."""
-import atexit
 import ctypes as C
 import sys
 import weakref
@@ -52,13 +51,9 @@ def make_config(cfg, n_joints, stages=None, last_channel=0, arch=_lib.ARCH_EFFNE
 
 
 _live_engines = weakref.WeakSet()
-
-
-@atexit.register
-def _destroy_all():
-    # release handles while the CUDA runtime is still alive (destructors at interpreter teardown run too late)
-    for e in list(_live_engines):
-        e.close()
+# No atexit teardown: at interpreter exit the CUDA context may already be going away (cudaEventDestroy was observed to
+# return cudaErrorContextIsDestroyed and then crash inside the driver); the process exit reclaims device memory.
+# Engine.close() / __del__ release the handle during normal operation.
 
 
 class Engine:

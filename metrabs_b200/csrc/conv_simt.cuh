@@ -260,8 +260,9 @@ __global__ void __launch_bounds__(256) dwconv_kernel(ConvParams p) {
 // depthwise 3x3 (+ stride 2) + bias + activation + squeeze-excitation pooling, bf16 NHWC, 8 channels x 4 output
 // pixels per thread: every input column vector is loaded once per row and reused by the outputs it feeds
 // (18 / 27 16-byte loads per 4 outputs instead of 36), and the per-channel sums of the SE squeeze are reduced in the
-// block and added (already divided by Hout*Wout) to pooled[b][c] with one atomic per channel per block, so the
-// pooling pass never re-reads the tensor.  grid (ceil(C/256), ceil(strips/8), B), block (32, 8).
+// block and stored (already divided by Hout*Wout) as partial slice pooled[blockIdx.y][b][c]; the consumer (fc1) sums the
+// <= 8 slices in a fixed order (deterministic, no atomics), so the pooling pass never re-reads the tensor.
+// grid (ceil(C/256), min(ceil(strips/8), 8), B), block (32, 8).
 // ----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
@@ -292,14 +293,12 @@ __global__ void __launch_bounds__(256) dwconv3x3_pool_bf16_kernel(ConvParams p, 
   const int cv = blockIdx.x * 32 + threadIdx.x;  // channel vector (8 channels)
   const int c = cv * 8;
   const int strips_w = (p.Wout + OW - 1) / OW;
-  const int strip = blockIdx.y * 8 + threadIdx.y;
   const int b = blockIdx.z;
-  const bool active = c < C && strip < strips_w * p.Hout;
   float acc[OW][8];
   float psum[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) psum[k] = 0.f;
-  if (active) {
+  for (int strip = blockIdx.y * 8 + threadIdx.y; c < C && strip < strips_w * p.Hout; strip += gridDim.y * 8) {
     const int oh = strip / strips_w;
     const int ow0 = (strip - oh * strips_w) * OW;
     float bias[8];
@@ -377,7 +376,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_pool_bf16_kernel(ConvParams p, 
         float t = 0.f;
 #pragma unroll
         for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][k];
-        atomicAdd(pooled + (size_t)b * C + c + k, t * inv);
+        pooled[((size_t)blockIdx.y * gridDim.z + b) * C + c + k] = t * inv;
       }
     }
   }

@@ -34,6 +34,7 @@ const char* kKClassNames[KC_COUNT] = {"stem_conv_kernel", "conv_igemm_kernel", "
                                       "softargmax_bhwn_kernel", "recon_pass1+2_kernel", "other"};
 enum { BUF_FEATURES = -2, BUF_NONE = -1, BUF_SMALL0 = 4 };  // 0..3 big activation buffers, 4..6 small [B,C]
 constexpr int kNumBig = 4, kNumSmall = 3;
+constexpr int kPoolSlices = 8;  // the fused depthwise+pool kernel leaves up to 8 partial slices [slice][B][C]
 
 struct HostTensor {
   std::vector<float> data;
@@ -54,6 +55,7 @@ struct Op {
   float pre_scale[3] = {2.f, 2.f, 2.f}, pre_shift[3] = {-1.f, -1.f, -1.f};  // stem input affine (PreprocLayer: x*2-1)
   bool fused_pool = false;  // bf16 modes: this depthwise op also produces the SE pooled means (next op is skipped)
   bool res_first = false;  // residual added BEFORE the activation (ResNet); EfficientNet adds it after
+  int pool_src = -1;       // fc1: index of the OP_POOL op that produces its input (fused pooling leaves partial slices)
   int ksplit = 1;          // split-K (squeeze-excitation fc1): raw sums, bias/act deferred to the consumer
   int a_bias_from = -1;    // op index whose bias (+ a_act) is applied to THIS op's input on load
   int a_act = ACT_NONE;
@@ -158,10 +160,12 @@ struct Planner {
     op.Hin = H; op.Win = W; op.Cin = op.Cout = cexp;
     op.in_buf = buf; op.out_buf = BUF_SMALL0;
     h->ops.push_back(op);
+    const int pool_index = (int)h->ops.size() - 1;
     Op f1;
     f1.type = OP_CONV; f1.name = name + ".fc1"; f1.wkey = fc1 + ".weight"; f1.biaskey = fc1 + ".bias";
     f1.Cin = cexp; f1.Cout = csq; f1.act = act1; f1.small_io = true; f1.pad_ok = true;
     f1.in_buf = BUF_SMALL0; f1.out_buf = BUF_SMALL0 + 1;
+    f1.pool_src = pool_index;
     f1.flops = 2.0 * cexp * csq_real;
     // K = cexp is long and M = batch is short: split K over CTAs; the ksplit partial slices [ksplit][B][csq] must fit
     // the small buffer (capacity >= cexp floats per crop)
@@ -564,7 +568,7 @@ Workspace layout(const mtb_handle* h, int B, void* base) {
   w.base = (char*)base;
   const size_t es = elem_size(h);
   w.big_stride = align_up(h->big_elems_per_crop * (size_t)B * es, 1024);
-  w.small_stride = align_up((size_t)h->small_c * B * 4, 1024);
+  w.small_stride = align_up((size_t)h->small_c * B * 4 * kPoolSlices, 1024);
   size_t o = w.big_stride * kNumBig;
   w.off_small = o; o += w.small_stride * kNumSmall;
   const size_t P = (size_t)h->feat_side * h->feat_side;
@@ -613,6 +617,18 @@ struct ProfScope {
     h->prof_used += 2;
   }
 };
+
+// shapes covered by dwconv3x3_pool_bf16_kernel
+bool dw_strip_eligible(const Op& op) {
+  return op.type == OP_DW && op.R == 3 && op.S == 3 && op.dil == 1 && op.Cout % 8 == 0 && (op.stride == 1 || op.stride == 2) &&
+         (op.act == ACT_SILU || op.act == ACT_RELU || op.act == ACT_HSWISH);
+}
+
+// number of partial pooling slices the fused depthwise kernel writes (= its gridDim.y)
+int dw_pool_slices(const Op& dw) {
+  const int strips = dw.Hout * ((dw.Wout + 3) / 4);
+  return std::min((strips + 7) / 8, kPoolSlices);
+}
 
 int op_class(const Op& op) {
   switch (op.type) {
@@ -672,15 +688,9 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
       p.R = op.R; p.S = op.S; p.stride = op.stride; p.dil = op.dil; p.pad_t = op.pad_t; p.pad_l = op.pad_l; p.act = op.act;
       p.res_first = op.res_first ? 1 : 0;
       if (op.type == OP_DW) {
-        if (h->cfg.precision == MTB_PRECISION_BF16_TC && op.R == 3 && op.S == 3 && op.dil == 1 && op.Cout % 8 == 0 &&
-            (op.stride == 1 || op.stride == 2) && (op.act == ACT_SILU || op.act == ACT_RELU || op.act == ACT_HSWISH)) {
-          float* pooled = nullptr;
-          if (op.fused_pool) {
-            pooled = (float*)buf_ptr(ws, BUF_SMALL0, features);
-            cudaMemsetAsync(pooled, 0, (size_t)B * op.Cout * 4, st);
-          }
-          const int strips = op.Hout * ((op.Wout + 3) / 4);
-          dim3 grid((op.Cout / 8 + 31) / 32, (strips + 7) / 8, B), block(32, 8);
+        if (h->cfg.precision == MTB_PRECISION_BF16_TC && dw_strip_eligible(op)) {
+          float* pooled = op.fused_pool ? (float*)buf_ptr(ws, BUF_SMALL0, features) : nullptr;
+          dim3 grid((op.Cout / 8 + 31) / 32, dw_pool_slices(op), B), block(32, 8);
           if (op.act == ACT_SILU) {
             if (op.stride == 1) dwconv3x3_pool_bf16_kernel<1, ACT_SILU><<<grid, block, 0, st>>>(p, pooled);
             else dwconv3x3_pool_bf16_kernel<2, ACT_SILU><<<grid, block, 0, st>>>(p, pooled);
@@ -694,17 +704,16 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
         } else {
           size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
           dwconv_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
-          if (op.fused_pool) {  // shapes the fused kernel does not cover: separate pooling pass
-            dim3 pg((op.Cout + 127) / 128, B), pb(32, 8);
-            pool_mean_kernel<T><<<pg, pb, 0, st>>>((const T*)p.out, (float*)buf_ptr(ws, BUF_SMALL0, features), op.Hout * op.Wout, op.Cout);
-            h->launches++;
-          }
         }
       } else if (op.type == OP_MAXPOOL) {
         size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
         maxpool_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
       } else if (op.small_io) {
         float* final_out = (float*)p.out;
+        if (op.pool_src > 0 && h->ops[op.pool_src].fused_pool) {  // input = partial pooling slices of the depthwise kernel
+          p.a_splits = dw_pool_slices(h->ops[op.pool_src - 1]);
+          p.a_split_stride = (size_t)B * op.Cin;
+        }
         if (op.ksplit > 1) {  // split-K partial slices go to the (still unused) scale buffer, then one tiny reduce kernel
           p.ksplit = op.ksplit;
           p.out = buf_ptr(ws, BUF_SMALL0 + 2, features);
@@ -986,7 +995,7 @@ int mtb_finalize_weights(mtb_handle* h) {
   h->dev_allocs.clear();
   for (auto& op : h->ops) op.fused_pool = false;
   for (size_t i = 0; i + 1 < h->ops.size(); ++i) {
-    const bool fuse = h->cfg.precision == MTB_PRECISION_BF16_TC && h->ops[i].type == OP_DW && h->ops[i + 1].type == OP_POOL;
+    const bool fuse = h->cfg.precision == MTB_PRECISION_BF16_TC && dw_strip_eligible(h->ops[i]) && h->ops[i + 1].type == OP_POOL;
     if (fuse) h->ops[i].fused_pool = h->ops[i + 1].fused_pool = true;
   }
   for (auto& op : h->ops) {

@@ -142,6 +142,17 @@ __device__ __forceinline__ uint64_t umma_smem_desc_k(uint32_t smem_addr) {
   d |= layout << 61;
   return d;
 }
+// K-major, NO swizzle ("interleave"): 8-row x 16-byte core matrices; LBO = byte distance between the two K core matrices
+// of one MMA (K = 16 bf16), SBO = byte distance between consecutive 8-row groups  (canonical layout ((8,n),2):((1,SBO),LBO)
+// in 16-byte units, cute/atom/mma_traits_sm100.hpp)
+__device__ __forceinline__ uint64_t umma_smem_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n.
 __host__ __device__ inline uint32_t umma_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -154,20 +165,34 @@ constexpr int TC_B_BYTES = TC_MAX_BN * TC_BK * 2;   // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_OUT_BOX_BYTES = TC_BM * 64 * 2;    // one [128 rows x 64 cols] bf16 output box (TMA store), 16 KB
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 2 * TC_OUT_BOX_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TC_TILE_W = 16, TC_TILE_H = 8;        // spatial M tile (16 x 8 = 128 output pixels)
+constexpr int TC_TILE_W = 16, TC_TILE_H = 8;        // spatial M tile of mode 1 (16 x 8 = 128 output pixels)
+// mode 2 (resident patch): 8 x 16 pixel tile, patch (8+2) x (16+2) pixels, planes of 16-byte channel chunks
+constexpr int TC_PT_W = 8, TC_PT_H = 16, TC_PATCH_W = TC_PT_W + 2, TC_PATCH_H = TC_PT_H + 2;
+constexpr int TC_PLANE_BYTES = TC_PATCH_W * TC_PATCH_H * 16;   // 2880
+constexpr int TC_PATCH_MAX_PLANES = 12;                          // Cin <= 96
+constexpr int TC_PATCH_BYTES = 35840;                            // >= 12 planes, 1024-aligned
+constexpr int TC_P_STAGES = 3;                                   // B-operand ring depth in mode 2
+constexpr int TC_P_PATCH_OFF = TC_P_STAGES * TC_B_BYTES;         // 96 KB: patches live behind the 3 B stages
 constexpr int TC_THREADS = 384;                      // warps 0-3: TMA / MMA / TMEM alloc / idle, warps 4-11: epilogue
 constexpr int TC_EPI_THREADS = 256;
 
 struct TcConvParams {
   const void* res;
+  const void* res_in;  // mode 2: the NHWC input tensor, read by the patch loader warps
   const float* bias;
-  int mode;     // 0: flat 1x1 stride 1 (rows = B*H*W, 2D maps), 1: spatial tiles (any RxS, stride 1/2, dilation; 4D maps)
+  int mode;     // 0: flat 1x1 stride 1 (rows = B*H*W, 2D maps); 1: spatial tiles, A tile per tap by 4D TMA (any RxS, stride
+                // 1/2, dilation); 2: 3x3 stride 1 with a RESIDENT input patch: the (tile+halo) x Cin patch is staged once per
+                // tile in a channel-chunk-planar layout and every tap's A operand is a no-swizzle UMMA descriptor into it
+  int tile_w, tile_h, tile_w_log2;  // spatial M tile: 16x8 (mode 1) or 8x16 (mode 2)
+  int Hin, Win;
   int M;        // mode 0: number of rows
   int Cout, Cin;
   int bn;       // N-tile stride, multiple of 64 (the MMA N of a tile is its valid width rounded up to 16)
   int n_tiles, m_tiles, kchunks, taps;
   int act, res_first;   // res_first: add the residual BEFORE the activation (ResNet), else after (EfficientNet)
   int Hout, Wout, tiles_w, tiles_h, pad_t, pad_l, S, stride, dil;
+  int debug;    // MTB_TC_DEBUG bits (perf experiments only): 1 = skip the TMA store, 2 = skip the epilogue math + staging,
+                // 4 = skip the residual load, 8 = skip the patch loads (mode 2)
   int bk;       // K elements per pipeline stage: 64 (128B swizzle) or 32 (64B swizzle, for Cin whose last 64-chunk is mostly empty)
 };
 
@@ -225,7 +250,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty = bars + TC_STAGES;        // [TC_STAGES]
   uint64_t* tmem_full = bars + 2 * TC_STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
-  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  uint64_t* patch_full = tmem_empty + 2;         // [2]  mode 2: input patch staged by the loader warps
+  uint64_t* patch_empty = patch_full + 2;        // [2]  mode 2: patch consumed by the MMAs of its tile
+  uint32_t* tmem_slot = (uint32_t*)(patch_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -241,6 +268,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], TC_EPI_THREADS / 32);
+      mbar_init(&patch_full[i], 2);   // one arrive per loader warp
+      mbar_init(&patch_empty[i], 1);  // tcgen05.commit
     }
     fence_barrier_init();
   }
@@ -252,7 +281,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int num_kb = p.taps * p.kchunks;
-  const uint32_t stage_tx = (uint32_t)(TC_BM + p.bn) * BK * 2;
+  const bool patch_mode = p.mode == 2;
+  const int nstages = patch_mode ? TC_P_STAGES : TC_STAGES;
+  const uint32_t stage_tx = patch_mode ? (uint32_t)p.bn * BK * 2 : (uint32_t)(TC_BM + p.bn) * BK * 2;
+  const int planes = p.kchunks * (BK / 8);  // 16-byte channel chunks per pixel in the patch (zero beyond Cin/8)
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -273,16 +305,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * TC_STAGE_BYTES;
-          uint8_t* sb = sa + TC_A_BYTES;
+          uint8_t* sb = patch_mode ? smem + stage * TC_B_BYTES : sa + TC_A_BYTES;
           mbar_expect_tx(&full[stage], stage_tx);
           if (p.mode == 0) {
             tma_load_2d(sa, &tmA, &full[stage], kc * BK, m_blk * TC_BM);
-          } else {
+          } else if (p.mode == 1) {
             const int r = tap / p.S, s = tap - r * p.S;
             tma_load_4d(sa, &tmA, &full[stage], kc * BK, iw0 + s * p.dil, ih0 + r * p.dil, b);
           }
           tma_load_2d(sb, &tmB, &full[stage], tap * p.Cin + kc * BK, n_blk * p.bn);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -293,6 +325,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int pb = 0;
+      uint32_t pb_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int n_blk = t % p.n_tiles;
         const int n_valid = min(p.bn, p.Cout - n_blk * p.bn);
@@ -300,23 +334,91 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_MAX_BN;
+        uint32_t patch_addr = 0;
+        if (patch_mode) {
+          mbar_wait(&patch_full[pb], pb_phase);
+          tc_fence_after();
+          patch_addr = smem_u32(smem + TC_P_PATCH_OFF + pb * TC_PATCH_BYTES);
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
-          const uint32_t sb = sa + TC_A_BYTES;
+          if (patch_mode) {
+            const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
+            const int r = tap / 3, s_ = tap - r * 3;
+            const uint32_t sb = smem_u32(smem + stage * TC_B_BYTES);
+            // tap (r,s): the same patch, start shifted by r rows and s pixels; 8-row groups = patch rows (SBO), the two
+            // 16-byte K chunks of one MMA are one plane apart (LBO)
+            const uint32_t a0 = patch_addr + (uint32_t)(kc * (BK / 8)) * TC_PLANE_BYTES + (uint32_t)(r * TC_PATCH_W + s_) * 16;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16(d_tmem, umma_smem_desc_k<BK>(sa + k * 32), umma_smem_desc_k<BK>(sb + k * 32), idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16(d_tmem, umma_smem_desc_nosw(a0 + (uint32_t)(2 * k) * TC_PLANE_BYTES, TC_PLANE_BYTES, TC_PATCH_W * 16),
+                        umma_smem_desc_k<BK>(sb + k * 32), idesc, (kb | k) != 0);
+            }
+          } else {
+            const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
+            const uint32_t sb = sa + TC_A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16(d_tmem, umma_smem_desc_k<BK>(sa + k * 32), umma_smem_desc_k<BK>(sb + k * 32), idesc, (kb | k) != 0);
+            }
           }
           umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+        if (patch_mode) {
+          umma_commit(&patch_empty[pb]);  // the patch may be overwritten once this tile's MMAs have read it
+          if (++pb == 2) { pb = 0; pb_phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    // ===== warps 2-3, mode 2 only: stage the (tile + halo) input patch, chunk-planar [plane][patch row][patch col][16 B] =====
+    if (patch_mode) {
+      const int lt = threadIdx.x - 64;  // 0..63
+      const __nv_bfloat16* __restrict__ in = (const __nv_bfloat16*)p.res_in;
+      const int real_planes = p.Cin >> 3;
+      int pb = 0;
+      uint32_t pb_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m_blk = t / p.n_tiles;
+        const int tw = m_blk % p.tiles_w;
+        const int th = (m_blk / p.tiles_w) % p.tiles_h;
+        const int b = m_blk / (p.tiles_w * p.tiles_h);
+        const int ih0 = th * TC_PT_H - p.pad_t, iw0 = tw * TC_PT_W - p.pad_l;
+        mbar_wait(&patch_empty[pb], pb_phase ^ 1);
+        uint8_t* patch = smem + TC_P_PATCH_OFF + pb * TC_PATCH_BYTES;
+        const int items = TC_PATCH_H * TC_PATCH_W * planes;
+        for (int i0 = lt; i0 < items; i0 += 64 * 4) {
+          uint4 v[4];
+          int dst[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 64;
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            dst[u] = -1;
+            if (i < items) {
+              const int j = i % planes, pix = i / planes;
+              const int ph = pix / TC_PATCH_W, pw = pix - ph * TC_PATCH_W;
+              const int ih = ih0 + ph, iw = iw0 + pw;
+              dst[u] = j * TC_PLANE_BYTES + pix * 16;
+              if (j < real_planes && ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win && !(p.debug & 8))
+                v[u] = *reinterpret_cast<const uint4*>(in + ((size_t)(b * p.Hin + ih) * p.Win + iw) * p.Cin + j * 8);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (dst[u] >= 0) *reinterpret_cast<uint4*>(patch + dst[u]) = v[u];
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&patch_full[pb]);
+        if (++pb == 2) { pb = 0; pb_phase ^= 1; }
+      }
+    }
+  } else {
     // ===== epilogue: 8 warps.  Warp w owns TMEM lanes [32(w%4), +32) = tile rows, and half (w-4)/4 of every 64-column
     // chunk.  TMEM -> registers -> bias/act/residual -> bf16 -> 128B-swizzled smem box -> TMA store (coalesced, and
     // tile tails are clipped by the tensor map). =====
@@ -343,7 +445,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tw = m_blk % p.tiles_w;
         th = (m_blk / p.tiles_w) % p.tiles_h;
         b = m_blk / (p.tiles_w * p.tiles_h);
-        int oh = th * TC_TILE_H + row / TC_TILE_W, ow = tw * TC_TILE_W + row % TC_TILE_W;
+        int oh = th * p.tile_h + (row >> p.tile_w_log2), ow = tw * p.tile_w + (row & (p.tile_w - 1));
         valid = oh < p.Hout && ow < p.Wout;
         off = ((size_t)(b * p.Hout + oh) * p.Wout + ow) * p.Cout;
       }
@@ -371,7 +473,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int g = 0; g < 4; ++g) {
           const int cg = c0 + g * 8;  // 8-column group (Cout % 8 == 0: all-or-nothing)
           uint4 ov = make_uint4(0u, 0u, 0u, 0u);
-          if (cg < n_valid) {
+          if (cg < n_valid && !(p.debug & 2)) {
             const int ng = n0 + cg;
             float4 b0 = *reinterpret_cast<const float4*>(p.bias + ng);
             float4 b1 = *reinterpret_cast<const float4*>(p.bias + ng + 4);
@@ -380,7 +482,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             o[4] = v[g * 8 + 4] + b1.x; o[5] = v[g * 8 + 5] + b1.y; o[6] = v[g * 8 + 6] + b1.z; o[7] = v[g * 8 + 7] + b1.w;
             if constexpr (RES != 0) {
               float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-              if (valid) {
+              if (valid && !(p.debug & 4)) {
                 uint4 rv = *reinterpret_cast<const uint4*>(res + off + ng);
                 const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
@@ -406,9 +508,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
         named_bar_sync(1, TC_EPI_THREADS);
-        if (leader) {
+        if (leader && !(p.debug & 1)) {
           if (p.mode == 0) tma_store_2d(&tmO, box, n0 + ch * 64, m_blk * TC_BM);
-          else tma_store_4d(&tmO, box, n0 + ch * 64, tw * TC_TILE_W, th * TC_TILE_H, b);
+          else tma_store_4d(&tmO, box, n0 + ch * 64, tw * p.tile_w, th * p.tile_h, b);
           tma_store_commit();
         }
         ++box_count;
@@ -480,12 +582,12 @@ inline const char* make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, 
 // rank-4 bf16 NHWC tensor [B][H][W][C]; box = 64 channels x (TILE_W x TILE_H) pixels sampled every `stride` pixels
 // (element strides: to load N elements along a dimension with traversal stride s, boxDim = N*s)
 inline const char* make_tmap_nhwc(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t stride,
-                                  uint32_t box_c = TC_BK) {
+                                  uint32_t box_c = TC_BK, uint32_t tile_w = TC_TILE_W, uint32_t tile_h = TC_TILE_H) {
   tmap_encode_fn enc = get_tmap_encode();
   if (!enc) return "cuTensorMapEncodeTiled unavailable";
   cuuint64_t dims[4] = {C, W, H, B};
   cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
-  cuuint32_t box[4] = {box_c, TC_TILE_W * stride, TC_TILE_H * stride, 1};
+  cuuint32_t box[4] = {box_c, tile_w * stride, tile_h * stride, 1};
   cuuint32_t estr[4] = {1, stride, stride, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -507,6 +609,15 @@ struct TcWeights {
   mutable const void* cached_out = nullptr;
   mutable int cached_B = -1, cached_bn = 0;
 };
+
+inline bool tc_patch_disabled() {  // MTB_DISABLE_PATCH=1: 3x3 convs fall back to the per-tap TMA mode (A/B testing)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTB_DISABLE_PATCH");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 
 inline bool tc_disabled() {
   static int v = -1;
@@ -615,15 +726,29 @@ inline const char* tc_conv_dispatch(int act, int res_mode, int grid, const CUten
 inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool res_first, cudaStream_t st) {
   TcConvParams q;
   q.res = p.res; q.bias = w.d_bias;
+  const int rem0 = p.Cin % 64;
+  const int bk0 = (rem0 != 0 && rem0 <= 32) ? 32 : 64;
+  const int planes0 = ((p.Cin + bk0 - 1) / bk0) * (bk0 / 8);
   q.mode = (p.R == 1 && p.stride == 1) ? 0 : 1;
+  if (p.R == 3 && p.S == 3 && p.stride == 1 && p.dil == 1 && planes0 <= TC_PATCH_MAX_PLANES && !tc_patch_disabled()) q.mode = 2;
+  q.tile_w = q.mode == 2 ? TC_PT_W : TC_TILE_W;
+  q.tile_h = q.mode == 2 ? TC_PT_H : TC_TILE_H;
+  q.tile_w_log2 = q.mode == 2 ? 3 : 4;
+  q.Hin = p.Hin; q.Win = p.Win;
+  q.res_in = p.in;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("MTB_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    q.debug = dbg;
+  }
   q.Cout = p.Cout; q.Cin = p.Cin; q.act = p.act; q.res_first = res_first ? 1 : 0;
   q.taps = w.taps; q.S = w.S; q.stride = p.stride; q.dil = p.dil;
   const int rem = p.Cin % 64;
   q.bk = (rem != 0 && rem <= 32) ? 32 : 64;  // e.g. Cin = 32, 96, 160, 224: no zero-padded half chunk
   q.kchunks = (p.Cin + q.bk - 1) / q.bk;
   q.Hout = p.Hout; q.Wout = p.Wout; q.pad_t = p.pad_t; q.pad_l = p.pad_l;
-  q.tiles_w = (p.Wout + TC_TILE_W - 1) / TC_TILE_W;
-  q.tiles_h = (p.Hout + TC_TILE_H - 1) / TC_TILE_H;
+  q.tiles_w = (p.Wout + q.tile_w - 1) / q.tile_w;
+  q.tiles_h = (p.Hout + q.tile_h - 1) / q.tile_h;
   q.M = p.B * p.Hout * p.Wout;
   q.m_tiles = q.mode == 0 ? (q.M + TC_BM - 1) / TC_BM : p.B * q.tiles_w * q.tiles_h;
   const int bn = tc_pick_bn(p.Cout, q.m_tiles, q.taps * q.kchunks);
@@ -636,7 +761,7 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
     e = make_tmap_2d(&w.mapB, w.d_w, (uint64_t)p.Cout, (uint64_t)w.taps * p.Cin, (uint32_t)bn, (uint32_t)q.bk);
     if (e) return e;
     e = q.mode == 0 ? make_tmap_2d(&w.mapO, p.out, (uint64_t)q.M, (uint64_t)p.Cout, TC_BM)
-                    : make_tmap_nhwc(&w.mapO, p.out, p.B, p.Hout, p.Wout, p.Cout, 1);
+                    : make_tmap_nhwc(&w.mapO, p.out, p.B, p.Hout, p.Wout, p.Cout, 1, TC_BK, (uint32_t)q.tile_w, (uint32_t)q.tile_h);
     if (e) return e;
     w.cached_in = p.in;
     w.cached_out = p.out;

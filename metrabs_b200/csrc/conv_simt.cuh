@@ -294,49 +294,55 @@ __global__ void __launch_bounds__(256) dwconv3x3_pool_bf16_kernel(ConvParams p, 
   const int c = cv * 8;
   const int strips_w = (p.Wout + OW - 1) / OW;
   const int b = blockIdx.z;
-  float acc[OW][8];
+  const int cstride = C >> 3;                    // uint4 per pixel
   float psum[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) psum[k] = 0.f;
+  float bias[8];
+  if (c < C) {
+    float4 b0 = *reinterpret_cast<const float4*>(p.bias + c), b1 = *reinterpret_cast<const float4*>(p.bias + c + 4);
+    bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+    bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+  }
   for (int strip = blockIdx.y * 8 + threadIdx.y; c < C && strip < strips_w * p.Hout; strip += gridDim.y * 8) {
     const int oh = strip / strips_w;
     const int ow0 = (strip - oh * strips_w) * OW;
-    float bias[8];
-    {
-      float4 b0 = *reinterpret_cast<const float4*>(p.bias + c), b1 = *reinterpret_cast<const float4*>(p.bias + c + 4);
-      bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
-      bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
-    }
+    const int iw0 = ow0 * STRIDE - p.pad_l;
+    unsigned colmask = 0;
+#pragma unroll
+    for (int x = 0; x < NCOL; ++x)
+      if (iw0 + x >= 0 && iw0 + x < p.Win) colmask |= 1u << x;
+    float acc[OW][8];
 #pragma unroll
     for (int i = 0; i < OW; ++i)
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[i][k] = bias[k];
-    const int iw0 = ow0 * STRIDE - p.pad_l;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int ih = oh * STRIDE - p.pad_t + r;
-      if (ih < 0 || ih >= p.Hin) continue;
+      if (ih < 0 || ih >= p.Hin) continue;  // warp-uniform (a warp shares its strip)
+      // 16-byte vectors of the NCOL input columns of this row (all loads issued before any use)
+      const uint4* rowp = reinterpret_cast<const uint4*>(in + ((size_t)(b * p.Hin + ih) * p.Win) * C + c) + (ptrdiff_t)iw0 * cstride;
+      uint4 raw[NCOL];
+#pragma unroll
+      for (int x = 0; x < NCOL; ++x) raw[x] = (colmask >> x) & 1u ? __ldg(rowp + (ptrdiff_t)x * cstride) : make_uint4(0u, 0u, 0u, 0u);
       float w[3][8];
 #pragma unroll
       for (int s_ = 0; s_ < 3; ++s_) {
         const float* wp = p.w + (size_t)(r * 3 + s_) * C + c;
-        float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+        float4 w0 = __ldg(reinterpret_cast<const float4*>(wp)), w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
         w[s_][0] = w0.x; w[s_][1] = w0.y; w[s_][2] = w0.z; w[s_][3] = w0.w;
         w[s_][4] = w1.x; w[s_][5] = w1.y; w[s_][6] = w1.z; w[s_][7] = w1.w;
       }
-      const __nv_bfloat16* rowp = in + ((size_t)(b * p.Hin + ih) * p.Win) * p.Cin + c;
 #pragma unroll
       for (int x = 0; x < NCOL; ++x) {
-        const int iw = iw0 + x;
-        if (iw < 0 || iw >= p.Win) continue;
-        uint4 raw = *reinterpret_cast<const uint4*>(rowp + (size_t)iw * p.Cin);
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        // bf16 -> fp32 is a 16-bit shift / mask of the packed words: one ALU op per element
+        const unsigned wd[4] = {raw[x].x, raw[x].y, raw[x].z, raw[x].w};
         float v[8];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          float2 f = __bfloat1622float2(h2[k]);
-          v[2 * k] = f.x;
-          v[2 * k + 1] = f.y;
+          v[2 * k] = __uint_as_float(wd[k] << 16);
+          v[2 * k + 1] = __uint_as_float(wd[k] & 0xffff0000u);
         }
 #pragma unroll
         for (int i = 0; i < OW; ++i) {
@@ -348,36 +354,40 @@ __global__ void __launch_bounds__(256) dwconv3x3_pool_bf16_kernel(ConvParams p, 
         }
       }
     }
+    __nv_bfloat16* orow = out + ((size_t)(b * p.Hout + oh) * p.Wout + ow0) * C + c;
 #pragma unroll
     for (int i = 0; i < OW; ++i) {
-      const int ow = ow0 + i;
-      if (ow >= p.Wout) continue;
+      if (ow0 + i >= p.Wout) continue;
       uint4 ov;
       __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         float a0 = fast_act<ACT>(acc[i][2 * k]), a1 = fast_act<ACT>(acc[i][2 * k + 1]);
         o2[k] = __floats2bfloat162_rn(a0, a1);
-        float2 back = __bfloat1622float2(o2[k]);  // pool what the next layer will actually read
-        psum[2 * k] += back.x;
-        psum[2 * k + 1] += back.y;
+        psum[2 * k] += a0;
+        psum[2 * k + 1] += a1;
       }
-      *reinterpret_cast<uint4*>(out + ((size_t)(b * p.Hout + oh) * p.Wout + ow) * C + c) = ov;
+      *reinterpret_cast<uint4*>(orow + (size_t)i * C) = ov;
     }
   }
   if (pooled) {
     __shared__ float red[8][32][9];
+#pragma unroll
     for (int k = 0; k < 8; ++k) red[threadIdx.y][threadIdx.x][k] = psum[k];
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
       const float inv = 1.0f / (float)(p.Hout * p.Wout);
+      float t[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        float t = 0.f;
+        t[k] = 0.f;
 #pragma unroll
-        for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][k];
-        pooled[((size_t)blockIdx.y * gridDim.z + b) * C + c + k] = t * inv;
+        for (int y = 0; y < 8; ++y) t[k] += red[y][threadIdx.x][k];
+        t[k] *= inv;
       }
+      float* dst = pooled + ((size_t)blockIdx.y * gridDim.z + b) * C + c;
+      *reinterpret_cast<float4*>(dst) = make_float4(t[0], t[1], t[2], t[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(t[4], t[5], t[6], t[7]);
     }
   }
 }

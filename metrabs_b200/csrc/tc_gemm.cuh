@@ -191,6 +191,7 @@ struct TcConvParams {
   int n_tiles, m_tiles, kchunks, taps;
   int act, res_first;   // res_first: add the residual BEFORE the activation (ResNet), else after (EfficientNet)
   int Hout, Wout, tiles_w, tiles_h, pad_t, pad_l, S, stride, dil;
+  long long* trace;  // MTB_TC_TRACE: CTA 0 writes clock64 timestamps [role][event] (role 0 producer, 1 MMA, 2 epilogue), 256 each
   int debug;    // MTB_TC_DEBUG bits (perf experiments only): 1 = skip the TMA store, 2 = skip the epilogue math + staging,
                 // 4 = skip the residual load, 8 = skip the patch loads (mode 2)
   int bk;       // K elements per pipeline stage: 64 (128B swizzle) or 32 (64B swizzle, for Cin whose last 64-chunk is mostly empty)
@@ -291,6 +292,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int tr = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int m_blk = t / p.n_tiles, n_blk = t - m_blk * p.n_tiles;
         int b = 0, ih0 = 0, iw0 = 0;
@@ -314,6 +316,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_4d(sa, &tmA, &full[stage], kc * BK, iw0 + s * p.dil, ih0 + r * p.dil, b);
           }
           tma_load_2d(sb, &tmB, &full[stage], tap * p.Cin + kc * BK, n_blk * p.bn);
+          if (p.trace && blockIdx.x == 0 && tr < 256) p.trace[tr++] = clock64();
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
@@ -327,6 +330,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t acc_phase = 0;
       int pb = 0;
       uint32_t pb_phase = 0;
+      int tr = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int n_blk = t % p.n_tiles;
         const int n_valid = min(p.bn, p.Cout - n_blk * p.bn);
@@ -343,6 +347,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
+          if (p.trace && blockIdx.x == 0 && tr < 256) p.trace[256 + tr++] = clock64();
           if (patch_mode) {
             const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
             const int r = tap / 3, s_ = tap - r * 3;
@@ -429,6 +434,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t box_count = 0;
+    int etr = 0;
     const __nv_bfloat16* __restrict__ res = (const __nv_bfloat16*)p.res;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int m_blk = t / p.n_tiles, n_blk = t - m_blk * p.n_tiles;
@@ -451,6 +457,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (p.trace && blockIdx.x == 0 && leader && etr < 256) p.trace[512 + etr++] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_MAX_BN;
       const int nchunks = (n_valid + 63) >> 6;
       for (int ch = 0; ch < nchunks; ++ch) {
@@ -515,6 +522,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         ++box_count;
       }
+      if (p.trace && blockIdx.x == 0 && leader && etr < 256) p.trace[512 + etr++] = clock64();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (leader) tma_store_wait_all();  // global writes complete before the CTA exits
@@ -771,7 +779,36 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
   const int total = q.m_tiles * q.n_tiles;
   const int grid = total < 148 ? total : 148;
   const int res_mode = p.res ? (res_first ? 2 : 1) : 0;
-  return tc_conv_dispatch(p.act, res_mode, grid, w.mapA, w.mapB, w.mapO, q, st);
+  q.trace = nullptr;
+  static const char* trace_env = getenv("MTB_TC_TRACE");  // "<Cin>x<Cout>": trace the first launch of that shape
+  static long long* trace_buf = nullptr;
+  static bool traced = false;
+  bool dump = false;
+  if (trace_env && !traced) {
+    int ci = 0, co = 0;
+    if (sscanf(trace_env, "%dx%d", &ci, &co) == 2 && ci == p.Cin && co == p.Cout) {
+      if (!trace_buf) cudaMalloc(&trace_buf, 768 * sizeof(long long));
+      cudaMemsetAsync(trace_buf, 0, 768 * sizeof(long long), st);
+      q.trace = trace_buf;
+      dump = traced = true;
+    }
+  }
+  const char* err = tc_conv_dispatch(p.act, res_mode, grid, w.mapA, w.mapB, w.mapO, q, st);
+  if (dump && !err) {
+    std::vector<long long> hbuf(768);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hbuf.data(), trace_buf, 768 * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long t0 = hbuf[0];
+    fprintf(stderr, "MTB_TC_TRACE Cin=%d Cout=%d mode=%d bk=%d bn=%d kb/tile=%d tiles=%d grid=%d\n", p.Cin, p.Cout, q.mode, q.bk, q.bn,
+            q.taps * q.kchunks, total, grid);
+    const char* names[3] = {"producer(TMA issued)", "mma(full wait done)", "epilogue(tmem_full done / tile end)"};
+    for (int r = 0; r < 3; ++r) {
+      fprintf(stderr, "  %s:", names[r]);
+      for (int i = 0; i < 60 && hbuf[r * 256 + i]; ++i) fprintf(stderr, " %lld", hbuf[r * 256 + i] - t0);
+      fprintf(stderr, "\n");
+    }
+  }
+  return err;
 }
 
 inline const char* tc_se_scale_launch(void* x, const float* s, int B, int P, int C, cudaStream_t st) {

@@ -159,22 +159,32 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int n) {
 }
 
 // ------------------------------------------------------------------------------------------- conv/GEMM kernel
+// constants shared with the fused head kernel (fixed 4-stage ring of [A 16 KB | B 32 KB] stages)
 constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4, TC_MAX_BN = 256;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;       // 16 KB
 constexpr int TC_B_BYTES = TC_MAX_BN * TC_BK * 2;   // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_OUT_BOX_BYTES = TC_BM * 64 * 2;    // one [128 rows x 64 cols] bf16 output box (TMA store), 16 KB
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 2 * TC_OUT_BOX_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 32768 + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// conv kernel: shared-memory plan (bytes from the 1024-aligned base)
+//   [0, RING)            operand ring: `nstages` stages of (A tile | B tile); in mode 2 the ring holds B tiles only and
+//                        the two resident input patches live at its tail
+//   [RING, RING+64K)     epilogue staging: 8 warps x 2 slabs of [32 rows x 128 B] (one TMA-store box each)
+//   then                 per-warp bias staging (8 x 256 B), mbarriers, TMEM slot
+constexpr int TCV_RING_BYTES = 144 * 1024;
+constexpr int TCV_MAX_STAGES = 8;
+constexpr int TCV_SLAB_BYTES = 32 * 128;
+constexpr int TCV_EPI_OFF = TCV_RING_BYTES;
+constexpr int TCV_BIAS_OFF = TCV_EPI_OFF + 8 * 2 * TCV_SLAB_BYTES;
+constexpr int TCV_BAR_OFF = TCV_BIAS_OFF + 8 * 256;
+constexpr int TCV_SMEM_BYTES = TCV_BAR_OFF + 512 + 1024 /*align slack*/;
 constexpr int TC_TILE_W = 16, TC_TILE_H = 8;        // spatial M tile of mode 1 (16 x 8 = 128 output pixels)
 // mode 2 (resident patch): 8 x 16 pixel tile, patch (8+2) x (16+2) pixels, planes of 16-byte channel chunks
 constexpr int TC_PT_W = 8, TC_PT_H = 16, TC_PATCH_W = TC_PT_W + 2, TC_PATCH_H = TC_PT_H + 2;
 constexpr int TC_PLANE_BYTES = TC_PATCH_W * TC_PATCH_H * 16;   // 2880
 constexpr int TC_PATCH_MAX_PLANES = 12;                          // Cin <= 96
-constexpr int TC_PATCH_BYTES = 35840;                            // >= 12 planes, 1024-aligned
-constexpr int TC_P_STAGES = 3;                                   // B-operand ring depth in mode 2
-constexpr int TC_P_PATCH_OFF = TC_P_STAGES * TC_B_BYTES;         // 96 KB: patches live behind the 3 B stages
-constexpr int TC_THREADS = 384;                      // warps 0-3: TMA / MMA / TMEM alloc / idle, warps 4-11: epilogue
-constexpr int TC_EPI_THREADS = 256;
+constexpr int TC_THREADS = 384;  // warps 0-7 epilogue; 8 A producer / patch loader; 9 B producer; 10 MMA + TMEM; 11 patch loader
+constexpr int TCV_EPI_WARPS = 8;
 
 struct TcConvParams {
   const void* res;
@@ -189,12 +199,13 @@ struct TcConvParams {
   int Cout, Cin;
   int bn;       // N-tile stride, multiple of 64 (the MMA N of a tile is its valid width rounded up to 16)
   int n_tiles, m_tiles, kchunks, taps;
-  int act, res_first;   // res_first: add the residual BEFORE the activation (ResNet), else after (EfficientNet)
-  int Hout, Wout, tiles_w, tiles_h, pad_t, pad_l, S, stride, dil;
-  long long* trace;  // MTB_TC_TRACE: CTA 0 writes clock64 timestamps [role][event] (role 0 producer, 1 MMA, 2 epilogue), 256 each
+  int nstages, stage_stride;  // operand ring depth and stage size in bytes (A at +0, B at +a_bytes)
+  int patch_off, patch_bytes; // mode 2: the two resident patches sit at the tail of the ring region
+  int Hout, Wout, tiles_w, tiles_h, pad_t, pad_l, R, S, stride, dil;
+  long long* trace;  // MTB_TC_TRACE: CTA 0 writes clock64 timestamps [role][event] (0 A/B producer, 1 MMA, 2 epilogue warp 0)
   int debug;    // MTB_TC_DEBUG bits (perf experiments only): 1 = skip the TMA store, 2 = skip the epilogue math + staging,
                 // 4 = skip the residual load, 8 = skip the patch loads (mode 2)
-  int bk;       // K elements per pipeline stage: 64 (128B swizzle) or 32 (64B swizzle, for Cin whose last 64-chunk is mostly empty)
+  int bk;       // K elements per ring stage (host-side copy of the BK template argument)
 };
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -218,9 +229,6 @@ __device__ __forceinline__ float tc_act(float x) {
     return x;
   }
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)),
                "r"(c0), "r"(c1)
@@ -237,100 +245,152 @@ __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// 16-byte async copy global -> shared; src_bytes = 0 zero-fills (out-of-image halo)
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// four TMEM loads in flight, one wait
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
 
-// ACT: epilogue activation; RES: 0 no residual, 1 residual added AFTER the activation (EfficientNet), 2 BEFORE (ResNet)
+// ACT: epilogue activation; RES: 0 no residual, 1 residual added AFTER the activation (EfficientNet), 2 BEFORE (ResNet);
+// BK: K elements per ring stage: 64 (128B-swizzled rows) or 32 (64B-swizzled rows).
+//
+// Warp roles (higher warp ids win issue arbitration on Blackwell, so the single-thread issuers sit on top):
+//   warps 0-7  epilogue: warp w owns TMEM lanes / tile rows [32(w&3), +32) and the 64-column chunks ch = (w>>2) mod 2;
+//              TMEM -> registers -> +bias -> act -> (+residual) -> bf16 -> private 128B-swizzled [32 x 64] slab -> its own
+//              TMA store.  No cross-warp synchronisation in the epilogue.
+//   warp 8     A-operand TMA producer (modes 0/1) / patch loader (mode 2)
+//   warp 9     B-operand (weights) TMA producer
+//   warp 10    TMEM allocator + single-thread tcgen05.mma issuer
+//   warp 11    second patch loader (mode 2)
 template <int ACT, int RES, int BK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const TcConvParams p) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B needs 1024 B alignment
-  uint8_t* out_stage = smem + TC_STAGES * TC_STAGE_BYTES;                          // 2 x 16 KB output boxes
-  uint64_t* bars = (uint64_t*)(out_stage + 2 * TC_OUT_BOX_BYTES);
-  uint64_t* full = bars;                     // [TC_STAGES]
-  uint64_t* empty = bars + TC_STAGES;        // [TC_STAGES]
-  uint64_t* tmem_full = bars + 2 * TC_STAGES;   // [2]
-  uint64_t* tmem_empty = tmem_full + 2;          // [2]
-  uint64_t* patch_full = tmem_empty + 2;         // [2]  mode 2: input patch staged by the loader warps
-  uint64_t* patch_empty = patch_full + 2;        // [2]  mode 2: patch consumed by the MMAs of its tile
+  uint64_t* bars = (uint64_t*)(smem + TCV_BAR_OFF);
+  uint64_t* full = bars;                              // [8]
+  uint64_t* empty = bars + TCV_MAX_STAGES;            // [8]
+  uint64_t* tmem_full = bars + 2 * TCV_MAX_STAGES;    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;               // [2]
+  uint64_t* patch_full = tmem_empty + 2;              // [2]
+  uint64_t* patch_empty = patch_full + 2;             // [2]
   uint32_t* tmem_slot = (uint32_t*)(patch_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
+  const bool patch_mode = p.mode == 2;
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
   }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < TC_STAGES; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+  if (warp == 9 && lane == 0) {
+    for (int i = 0; i < TCV_MAX_STAGES; ++i) {
+      mbar_init(&full[i], patch_mode ? 1 : 2);  // one arrive.expect_tx per TMA producer
+      mbar_init(&empty[i], 1);                  // tcgen05.commit
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], TC_EPI_THREADS / 32);
+      mbar_init(&tmem_empty[i], TCV_EPI_WARPS);
       mbar_init(&patch_full[i], 2);   // one arrive per loader warp
       mbar_init(&patch_empty[i], 1);  // tcgen05.commit
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 10) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_tiles = p.m_tiles * p.n_tiles;
-  const int num_kb = p.taps * p.kchunks;
-  const bool patch_mode = p.mode == 2;
-  const int nstages = patch_mode ? TC_P_STAGES : TC_STAGES;
-  const uint32_t stage_tx = patch_mode ? (uint32_t)p.bn * BK * 2 : (uint32_t)(TC_BM + p.bn) * BK * 2;
+  const uint32_t a_bytes = patch_mode ? 0u : (uint32_t)TC_BM * BK * 2;
+  const uint32_t b_bytes = (uint32_t)p.bn * BK * 2;
+  const int nstages = p.nstages;
   const int planes = p.kchunks * (BK / 8);  // 16-byte channel chunks per pixel in the patch (zero beyond Cin/8)
 
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int tr = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m_blk = t / p.n_tiles, n_blk = t - m_blk * p.n_tiles;
-        int b = 0, ih0 = 0, iw0 = 0;
-        if (p.mode == 1) {
-          int tw = m_blk % p.tiles_w;
-          int th = (m_blk / p.tiles_w) % p.tiles_h;
-          b = m_blk / (p.tiles_w * p.tiles_h);
-          ih0 = th * TC_TILE_H * p.stride - p.pad_t;
-          iw0 = tw * TC_TILE_W * p.stride - p.pad_l;
-        }
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
-          mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * TC_STAGE_BYTES;
-          uint8_t* sb = patch_mode ? smem + stage * TC_B_BYTES : sa + TC_A_BYTES;
-          mbar_expect_tx(&full[stage], stage_tx);
-          if (p.mode == 0) {
-            tma_load_2d(sa, &tmA, &full[stage], kc * BK, m_blk * TC_BM);
-          } else if (p.mode == 1) {
-            const int r = tap / p.S, s = tap - r * p.S;
-            tma_load_4d(sa, &tmA, &full[stage], kc * BK, iw0 + s * p.dil, ih0 + r * p.dil, b);
+  if (warp == 8) {
+    if (!patch_mode) {
+      // ===== A-operand TMA producer =====
+      if (lane == 0) {
+        int stage = 0, tr = 0;
+        uint32_t phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+          const int m_blk = t / p.n_tiles;
+          int b = 0, ih0 = 0, iw0 = 0;
+          if (p.mode == 1) {
+            int tw = m_blk % p.tiles_w;
+            int th = (m_blk / p.tiles_w) % p.tiles_h;
+            b = m_blk / (p.tiles_w * p.tiles_h);
+            ih0 = th * TC_TILE_H * p.stride - p.pad_t;
+            iw0 = tw * TC_TILE_W * p.stride - p.pad_l;
           }
-          tma_load_2d(sb, &tmB, &full[stage], tap * p.Cin + kc * BK, n_blk * p.bn);
-          if (p.trace && blockIdx.x == 0 && tr < 256) p.trace[tr++] = clock64();
-          if (++stage == nstages) { stage = 0; phase ^= 1; }
+          const int row0 = m_blk * TC_BM;
+          for (int r = 0; r < p.R; ++r)
+            for (int s_ = 0; s_ < p.S; ++s_)
+              for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * p.stage_stride;
+                mbar_expect_tx(&full[stage], a_bytes);
+                if (p.mode == 0) tma_load_2d(sa, &tmA, &full[stage], kc * BK, row0);
+                else tma_load_4d(sa, &tmA, &full[stage], kc * BK, iw0 + s_ * p.dil, ih0 + r * p.dil, b);
+                if (p.trace && blockIdx.x == 0 && tr < 256) p.trace[tr++] = clock64();
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
+              }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
+    // ===== B-operand (weights) TMA producer =====
+    if (lane == 0) {
+      int stage = 0, tr = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n_blk = t % p.n_tiles;
+        const int nrow = n_blk * p.bn;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          int col = tap * p.Cin;
+          for (int kc = 0; kc < p.kchunks; ++kc, col += BK) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sb = smem + stage * p.stage_stride + a_bytes;
+            mbar_expect_tx(&full[stage], b_bytes);
+            tma_load_2d(sb, &tmB, &full[stage], col, nrow);
+            if (patch_mode && p.trace && blockIdx.x == 0 && tr < 256) p.trace[tr++] = clock64();
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 10) {
     // ===== MMA issuer (one elected thread) =====
     if (lane == 0) {
-      int stage = 0;
+      int stage = 0, tr = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       int pb = 0;
       uint32_t pb_phase = 0;
-      int tr = 0;
+      const uint32_t smem_a0 = smem_u32(smem);
+      // constant high words of the operand descriptors: SBO | version 1 | layout type
+      const uint32_t hi_sw = (uint32_t)((8 * BK * 2) >> 4) | (1u << 14) | ((BK == 64 ? 2u : 4u) << 29);
+      const uint32_t hi_patch = (uint32_t)((TC_PATCH_W * 16) >> 4) | (1u << 14);
+      const uint32_t lbo_patch = (uint32_t)(TC_PLANE_BYTES >> 4) << 16;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int n_blk = t % p.n_tiles;
         const int n_valid = min(p.bn, p.Cout - n_blk * p.bn);
@@ -342,34 +402,38 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (patch_mode) {
           mbar_wait(&patch_full[pb], pb_phase);
           tc_fence_after();
-          patch_addr = smem_u32(smem + TC_P_PATCH_OFF + pb * TC_PATCH_BYTES);
+          patch_addr = smem_a0 + p.patch_off + pb * p.patch_bytes;
         }
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          if (p.trace && blockIdx.x == 0 && tr < 256) p.trace[256 + tr++] = clock64();
-          if (patch_mode) {
-            const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
-            const int r = tap / 3, s_ = tap - r * 3;
-            const uint32_t sb = smem_u32(smem + stage * TC_B_BYTES);
-            // tap (r,s): the same patch, start shifted by r rows and s pixels; 8-row groups = patch rows (SBO), the two
-            // 16-byte K chunks of one MMA are one plane apart (LBO)
-            const uint32_t a0 = patch_addr + (uint32_t)(kc * (BK / 8)) * TC_PLANE_BYTES + (uint32_t)(r * TC_PATCH_W + s_) * 16;
+        uint32_t first = 0;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          // mode 2, tap (r,s): the same patch, start shifted by r rows and s pixels; 8-row groups = patch rows (SBO), the
+          // two 16-byte K chunks of one MMA are one plane apart (LBO)
+          const uint32_t tap_off = patch_mode ? (uint32_t)((tap / 3) * TC_PATCH_W + (tap % 3)) * 16 : 0u;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            if (p.trace && blockIdx.x == 0 && tr < 256) p.trace[256 + tr++] = clock64();
+            const uint32_t sa = smem_a0 + stage * p.stage_stride;
+            const uint32_t sb_lo = (sa + a_bytes) >> 4;
+            if (patch_mode) {
+              const uint32_t a_lo = (patch_addr + (uint32_t)(kc * (BK / 8)) * TC_PLANE_BYTES + tap_off) >> 4;
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              umma_bf16(d_tmem, umma_smem_desc_nosw(a0 + (uint32_t)(2 * k) * TC_PLANE_BYTES, TC_PLANE_BYTES, TC_PATCH_W * 16),
-                        umma_smem_desc_k<BK>(sb + k * 32), idesc, (kb | k) != 0);
-            }
-          } else {
-            const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
-            const uint32_t sb = sa + TC_A_BYTES;
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_bf16(d_tmem, make_desc(((a_lo + (uint32_t)(2 * k) * (TC_PLANE_BYTES >> 4)) & 0x3FFF) | lbo_patch, hi_patch),
+                          make_desc((sb_lo + 2 * k) & 0x3FFF, hi_sw), idesc, first | (uint32_t)k);
+              }
+            } else {
+              const uint32_t sa_lo = sa >> 4;
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              umma_bf16(d_tmem, umma_smem_desc_k<BK>(sa + k * 32), umma_smem_desc_k<BK>(sb + k * 32), idesc, (kb | k) != 0);
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_bf16(d_tmem, make_desc((sa_lo + 2 * k) & 0x3FFF, hi_sw), make_desc((sb_lo + 2 * k) & 0x3FFF, hi_sw), idesc,
+                          first | (uint32_t)k);
+              }
             }
+            first = 1;
+            umma_commit(&empty[stage]);  // frees the ring slot once these MMAs have read it
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         if (patch_mode) {
           umma_commit(&patch_empty[pb]);  // the patch may be overwritten once this tile's MMAs have read it
@@ -379,63 +443,49 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp < 4) {
-    // ===== warps 2-3, mode 2 only: stage the (tile + halo) input patch, chunk-planar [plane][patch row][patch col][16 B] =====
-    if (patch_mode) {
-      const int lt = threadIdx.x - 64;  // 0..63
-      const __nv_bfloat16* __restrict__ in = (const __nv_bfloat16*)p.res_in;
-      const int real_planes = p.Cin >> 3;
-      int pb = 0;
-      uint32_t pb_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m_blk = t / p.n_tiles;
-        const int tw = m_blk % p.tiles_w;
-        const int th = (m_blk / p.tiles_w) % p.tiles_h;
-        const int b = m_blk / (p.tiles_w * p.tiles_h);
-        const int ih0 = th * TC_PT_H - p.pad_t, iw0 = tw * TC_PT_W - p.pad_l;
-        mbar_wait(&patch_empty[pb], pb_phase ^ 1);
-        uint8_t* patch = smem + TC_P_PATCH_OFF + pb * TC_PATCH_BYTES;
-        const int items = TC_PATCH_H * TC_PATCH_W * planes;
-        for (int i0 = lt; i0 < items; i0 += 64 * 4) {
-          uint4 v[4];
-          int dst[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * 64;
-            v[u] = make_uint4(0u, 0u, 0u, 0u);
-            dst[u] = -1;
-            if (i < items) {
-              const int j = i % planes, pix = i / planes;
-              const int ph = pix / TC_PATCH_W, pw = pix - ph * TC_PATCH_W;
-              const int ih = ih0 + ph, iw = iw0 + pw;
-              dst[u] = j * TC_PLANE_BYTES + pix * 16;
-              if (j < real_planes && ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win && !(p.debug & 8))
-                v[u] = *reinterpret_cast<const uint4*>(in + ((size_t)(b * p.Hin + ih) * p.Win + iw) * p.Cin + j * 8);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (dst[u] >= 0) *reinterpret_cast<uint4*>(patch + dst[u]) = v[u];
-        }
-        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&patch_full[pb]);
-        if (++pb == 2) { pb = 0; pb_phase ^= 1; }
+  }
+  if ((warp == 8 || warp == 11) && patch_mode) {
+    // ===== mode 2: stage the (tile + halo) input patch, chunk-planar [plane][patch row][patch col][16 B], with cp.async
+    // (all of a thread's 16-byte copies in flight at once; out-of-image halo pixels and channels >= Cin zero-filled) =====
+    const int lt = (warp == 8 ? 0 : 32) + lane;  // 0..63
+    const __nv_bfloat16* __restrict__ in = (const __nv_bfloat16*)p.res_in;
+    const int real_planes = p.Cin >> 3;
+    const int items = TC_PATCH_H * TC_PATCH_W * planes;
+    int pb = 0;
+    uint32_t pb_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m_blk = t / p.n_tiles;
+      const int tw = m_blk % p.tiles_w;
+      const int th = (m_blk / p.tiles_w) % p.tiles_h;
+      const int b = m_blk / (p.tiles_w * p.tiles_h);
+      const int ih0 = th * TC_PT_H - p.pad_t, iw0 = tw * TC_PT_W - p.pad_l;
+      mbar_wait(&patch_empty[pb], pb_phase ^ 1);
+      uint8_t* patch = smem + p.patch_off + pb * p.patch_bytes;
+      for (int i = lt; i < items; i += 64) {
+        const int j = i % planes, pix = i / planes;
+        const int ph = pix / TC_PATCH_W, pw = pix - ph * TC_PATCH_W;
+        const int ih = ih0 + ph, iw = iw0 + pw;
+        const bool ok = j < real_planes && ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win && !(p.debug & 8);
+        const __nv_bfloat16* src = ok ? in + ((size_t)(b * p.Hin + ih) * p.Win + iw) * p.Cin + j * 8 : in;
+        cp_async_16(patch + j * TC_PLANE_BYTES + pix * 16, src, ok ? 16u : 0u);
       }
+      cp_async_wait_all();
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&patch_full[pb]);
+      if (++pb == 2) { pb = 0; pb_phase ^= 1; }
     }
-  } else {
-    // ===== epilogue: 8 warps.  Warp w owns TMEM lanes [32(w%4), +32) = tile rows, and half (w-4)/4 of every 64-column
-    // chunk.  TMEM -> registers -> bias/act/residual -> bf16 -> 128B-swizzled smem box -> TMA store (coalesced, and
-    // tile tails are clipped by the tensor map). =====
-    const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
+  }
+  if (warp < TCV_EPI_WARPS) {
+    // ===== epilogue =====
+    const int q = warp & 3, par = warp >> 2;
     const int row = q * 32 + lane;
-    const bool leader = threadIdx.x == 4 * 32;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    uint32_t box_count = 0;
-    int etr = 0;
+    uint8_t* slabs = smem + TCV_EPI_OFF + warp * 2 * TCV_SLAB_BYTES;
+    float* bias_s = (float*)(smem + TCV_BIAS_OFF + warp * 256);
+    int acc = 0, etr = 0;
+    uint32_t acc_phase = 0, slab_count = 0;
     const __nv_bfloat16* __restrict__ res = (const __nv_bfloat16*)p.res;
+    const int rows_per_q = 32 >> p.tile_w_log2;  // tile rows covered by one warp's 32 lanes (spatial modes)
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int m_blk = t / p.n_tiles, n_blk = t - m_blk * p.n_tiles;
       const int n0 = n_blk * p.bn;
@@ -457,50 +507,62 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      if (p.trace && blockIdx.x == 0 && leader && etr < 256) p.trace[512 + etr++] = clock64();
+      if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && etr < 256) p.trace[512 + etr++] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_MAX_BN;
       const int nchunks = (n_valid + 63) >> 6;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int c0 = ch * 64 + half * 32;  // this warp's 32 columns of the chunk
-        float v[32];
-        if (c0 < n_valid) {
-          tmem_ld16(taddr + c0, v);
-          if (c0 + 16 < n_valid) tmem_ld16(taddr + c0 + 16, v + 16);
+      bool released = false;
+      for (int ch = par; ch < nchunks; ch += 2) {
+        const int c0 = ch * 64;
+        const int ncols = min(64, n_valid - c0);  // multiple of 8
+        // residual for this thread's row: issue the loads before waiting on TMEM
+        uint4 rv[8];
+        if constexpr (RES != 0) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            rv[g] = make_uint4(0u, 0u, 0u, 0u);
+            if (valid && g * 8 < ncols && !(p.debug & 4)) rv[g] = *reinterpret_cast<const uint4*>(res + off + n0 + c0 + g * 8);
+          }
         }
-        if (ch == nchunks - 1) {  // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+        // bias of the chunk -> this warp's staging (64 floats), broadcast-read below
+        __syncwarp();
+        if (lane < 16) {
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (lane * 4 < ncols) bv = *reinterpret_cast<const float4*>(p.bias + n0 + c0 + lane * 4);
+          *reinterpret_cast<float4*>(bias_s + lane * 4) = bv;
+        }
+        uint32_t v[64];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (g * 16 < ncols) tmem_ld16_issue(taddr + c0 + g * 16, v + g * 16);
+        tmem_ld_wait();
+        if (ch + 2 >= nchunks) {  // last chunk of this warp: its TMEM reads of the tile are done
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          released = true;
         }
-        uint8_t* box = out_stage + (box_count & 1) * TC_OUT_BOX_BYTES;
-        // the TMA store that last read this box (2 boxes ago) must have finished reading shared memory
-        if (leader) tma_store_wait_read<1>();
-        named_bar_sync(1, TC_EPI_THREADS);
+        uint8_t* slab = slabs + (slab_count & 1) * TCV_SLAB_BYTES;
+        if (lane == 0) tma_store_wait_read<1>();  // the store that last read this slab (2 chunks ago) is done with it
+        __syncwarp();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int cg = c0 + g * 8;  // 8-column group (Cout % 8 == 0: all-or-nothing)
+        for (int g = 0; g < 8; ++g) {
           uint4 ov = make_uint4(0u, 0u, 0u, 0u);
-          if (cg < n_valid && !(p.debug & 2)) {
-            const int ng = n0 + cg;
-            float4 b0 = *reinterpret_cast<const float4*>(p.bias + ng);
-            float4 b1 = *reinterpret_cast<const float4*>(p.bias + ng + 4);
+          if (g * 8 < ncols && !(p.debug & 2)) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + g * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + g * 8 + 4);
             float o[8];
-            o[0] = v[g * 8 + 0] + b0.x; o[1] = v[g * 8 + 1] + b0.y; o[2] = v[g * 8 + 2] + b0.z; o[3] = v[g * 8 + 3] + b0.w;
-            o[4] = v[g * 8 + 4] + b1.x; o[5] = v[g * 8 + 5] + b1.y; o[6] = v[g * 8 + 6] + b1.z; o[7] = v[g * 8 + 7] + b1.w;
+            o[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; o[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+            o[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; o[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+            o[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; o[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+            o[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; o[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
             if constexpr (RES != 0) {
-              float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-              if (valid && !(p.debug & 4)) {
-                uint4 rv = *reinterpret_cast<const uint4*>(res + off + ng);
-                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+              const unsigned wd[4] = {rv[g].x, rv[g].y, rv[g].z, rv[g].w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  float2 f = __bfloat1622float2(r2[i]);
-                  r[2 * i] = f.x;
-                  r[2 * i + 1] = f.y;
-                }
+              for (int i = 0; i < 4; ++i) {
+                const float r0 = __uint_as_float(wd[i] << 16), r1 = __uint_as_float(wd[i] & 0xffff0000u);
+                o[2 * i] = RES == 2 ? tc_act<ACT>(o[2 * i] + r0) : tc_act<ACT>(o[2 * i]) + r0;
+                o[2 * i + 1] = RES == 2 ? tc_act<ACT>(o[2 * i + 1] + r1) : tc_act<ACT>(o[2 * i + 1]) + r1;
               }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = RES == 2 ? tc_act<ACT>(o[i] + r[i]) : tc_act<ACT>(o[i]) + r[i];
             } else {
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] = tc_act<ACT>(o[i]);
@@ -509,27 +571,31 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
           }
-          // 128B swizzle: 16-byte chunk j of row r lives at chunk position j ^ (r & 7)
-          const int j = half * 4 + g;
-          *reinterpret_cast<uint4*>(box + row * 128 + ((j ^ (row & 7)) << 4)) = ov;
+          // 128B swizzle: 16-byte chunk g of slab row r lives at chunk position g ^ (r & 7)
+          *reinterpret_cast<uint4*>(slab + lane * 128 + ((g ^ (lane & 7)) << 4)) = ov;
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-        named_bar_sync(1, TC_EPI_THREADS);
-        if (leader && !(p.debug & 1)) {
-          if (p.mode == 0) tma_store_2d(&tmO, box, n0 + ch * 64, m_blk * TC_BM);
-          else tma_store_4d(&tmO, box, n0 + ch * 64, tw * p.tile_w, th * p.tile_h, b);
+        __syncwarp();
+        if (lane == 0 && !(p.debug & 1)) {
+          if (p.mode == 0) tma_store_2d(&tmO, slab, n0 + c0, m_blk * TC_BM + q * 32);
+          else tma_store_4d(&tmO, slab, n0 + c0, tw * p.tile_w, th * p.tile_h + q * rows_per_q, b);
           tma_store_commit();
         }
-        ++box_count;
+        ++slab_count;
       }
-      if (p.trace && blockIdx.x == 0 && leader && etr < 256) p.trace[512 + etr++] = clock64();
+      if (!released) {  // this warp had no chunk in the tile (narrow last tile): still hand the accumulator back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
+      if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && etr < 256) p.trace[512 + etr++] = clock64();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (leader) tma_store_wait_all();  // global writes complete before the CTA exits
+    if (lane == 0) tma_store_wait_all();  // global writes complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 10) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -672,8 +738,11 @@ inline const char* tc_prepare_weights(TcWeights& w, const float* wk, const float
   return nullptr;
 }
 
-// N-tile stride (multiple of 64): fewest waves first, then least padded MMA work
-inline int tc_pick_bn(int cout, int m_tiles, int num_kb) {
+// N-tile stride (multiple of 64).  Per-tile time model (cycles): the single-thread TMA / MMA issuers cost ~kb_floor per
+// k-block whatever its size (measured with the in-kernel clock64 trace), an MMA k-block takes (BK/16) * N/2, and the
+// epilogue (overlapped with the next tile's main loop) ~epi_chunk per pair of 64-column chunks.
+inline int tc_pick_bn(int cout, int m_tiles, int num_kb, int bk) {
+  const double kb_floor = 300.0, epi_chunk = 900.0;
   int best = 64;
   double best_cost = 1e30;
   for (int bn = 256; bn >= 64; bn -= 64) {
@@ -682,7 +751,10 @@ inline int tc_pick_bn(int cout, int m_tiles, int num_kb) {
     long waves = (tiles + 147) / 148;
     int last = cout - (nt - 1) * bn;                          // width of the ragged last tile
     double avg_n = ((double)(nt - 1) * bn + ((last + 15) & ~15)) / nt;
-    double cost = (double)waves * (avg_n * (num_kb + 2) + 96.0);
+    double mma_kb = (bk / 16) * avg_n / 2.0;
+    double mainloop = num_kb * (mma_kb > kb_floor ? mma_kb : kb_floor);
+    double epi = ((bn / 64 + 1) / 2) * epi_chunk;
+    double cost = (double)waves * ((mainloop > epi ? mainloop : epi) + 400.0);
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best = bn;
@@ -696,11 +768,11 @@ inline const char* tc_conv_launch_k(int grid, const CUtensorMap& a, const CUtens
                                     cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_conv_kernel<ACT, RES, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_conv_kernel<ACT, RES, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCV_SMEM_BYTES) != cudaSuccess)
       return "cannot raise dynamic shared memory for tc_conv_kernel";
     attr_set = true;
   }
-  tc_conv_kernel<ACT, RES, BK><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, b, o, q);
+  tc_conv_kernel<ACT, RES, BK><<<grid, TC_THREADS, TCV_SMEM_BYTES, st>>>(a, b, o, q);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -749,8 +821,8 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
     if (dbg < 0) { const char* e = getenv("MTB_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
     q.debug = dbg;
   }
-  q.Cout = p.Cout; q.Cin = p.Cin; q.act = p.act; q.res_first = res_first ? 1 : 0;
-  q.taps = w.taps; q.S = w.S; q.stride = p.stride; q.dil = p.dil;
+  q.Cout = p.Cout; q.Cin = p.Cin;
+  q.taps = w.taps; q.R = p.R; q.S = w.S; q.stride = p.stride; q.dil = p.dil;
   const int rem = p.Cin % 64;
   q.bk = (rem != 0 && rem <= 32) ? 32 : 64;  // e.g. Cin = 32, 96, 160, 224: no zero-padded half chunk
   q.kchunks = (p.Cin + q.bk - 1) / q.bk;
@@ -759,8 +831,18 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
   q.tiles_h = (p.Hout + q.tile_h - 1) / q.tile_h;
   q.M = p.B * p.Hout * p.Wout;
   q.m_tiles = q.mode == 0 ? (q.M + TC_BM - 1) / TC_BM : p.B * q.tiles_w * q.tiles_h;
-  const int bn = tc_pick_bn(p.Cout, q.m_tiles, q.taps * q.kchunks);
+  const int bn = tc_pick_bn(p.Cout, q.m_tiles, q.taps * q.kchunks, q.bk);
   q.bn = bn;
+  {
+    const int a_bytes = q.mode == 2 ? 0 : TC_BM * q.bk * 2;
+    q.stage_stride = (a_bytes + bn * q.bk * 2 + 1023) / 1024 * 1024;
+    q.patch_bytes = q.mode == 2 ? (planes0 * TC_PLANE_BYTES + 1023) / 1024 * 1024 : 0;
+    q.patch_off = TCV_RING_BYTES - 2 * q.patch_bytes;
+    const int ring = q.mode == 2 ? q.patch_off : TCV_RING_BYTES;
+    q.nstages = ring / q.stage_stride;
+    if (q.nstages > TCV_MAX_STAGES) q.nstages = TCV_MAX_STAGES;
+    if (q.nstages < 2) return "operand ring too small for this tile";
+  }
   q.n_tiles = (p.Cout + bn - 1) / bn;
   if (w.cached_in != p.in || w.cached_out != p.out || w.cached_B != p.B || w.cached_bn != bn) {
     const char* e = q.mode == 0 ? make_tmap_2d(&w.mapA, p.in, (uint64_t)q.M, (uint64_t)p.Cin, TC_BM, (uint32_t)q.bk)
@@ -768,8 +850,9 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
     if (e) return e;
     e = make_tmap_2d(&w.mapB, w.d_w, (uint64_t)p.Cout, (uint64_t)w.taps * p.Cin, (uint32_t)bn, (uint32_t)q.bk);
     if (e) return e;
-    e = q.mode == 0 ? make_tmap_2d(&w.mapO, p.out, (uint64_t)q.M, (uint64_t)p.Cout, TC_BM)
-                    : make_tmap_nhwc(&w.mapO, p.out, p.B, p.Hout, p.Wout, p.Cout, 1, TC_BK, (uint32_t)q.tile_w, (uint32_t)q.tile_h);
+    // output boxes are per epilogue warp: 32 tile rows x 64 channels
+    e = q.mode == 0 ? make_tmap_2d(&w.mapO, p.out, (uint64_t)q.M, (uint64_t)p.Cout, 32)
+                    : make_tmap_nhwc(&w.mapO, p.out, p.B, p.Hout, p.Wout, p.Cout, 1, TC_BK, (uint32_t)q.tile_w, (uint32_t)(32 / q.tile_w));
     if (e) return e;
     w.cached_in = p.in;
     w.cached_out = p.out;

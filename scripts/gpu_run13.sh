@@ -1,0 +1,8 @@
+for k in "tc_ops and tiny" "tc_ops and v2-s" "tc_ops and v2-l" "fused_depthwise"; do
+  echo "=== $k"; timeout 600 python -m pytest tests/test_gpu_tc.py -q -s -k "$k" 2>&1 | grep -v "^$" | tail -8
+done
+timeout 300 python scripts/op_profile.py --batch 128 --top 16 2>&1 | tail -20
+for sh in 32x32 64x256 224x1344 1344x224; do
+  echo "=== trace $sh"; MTB_TC_TRACE=$sh timeout 300 python scripts/op_profile.py --batch 128 --top 3 2>&1 | grep -A4 "MTB_TC_TRACE" | cut -c1-420
+done
+echo "=== bench bf16 B=256"; timeout 900 python bench.py --precision bf16 --steps 10 --warmup 3 --batch 256 --no-cpu-baseline 2>&1 | cut -c1-300 | tail -4

@@ -29,6 +29,8 @@ struct ConvParams {
 template <int BM, int BN, int TM, int TN, typename TIn, typename TOut>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 conv_igemm_kernel(ConvParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int BK = 16;
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int A_LD = (BM * BK / 4) / NT;  // float4 loads of A per thread per tile
@@ -222,6 +224,8 @@ conv_igemm_kernel(ConvParams p) {
 // ----------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv_kernel(ConvParams p) {
+  pdl_trigger();
+  pdl_wait();
   const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
   T* __restrict__ out = reinterpret_cast<T*>(p.out);
   const int C4 = p.Cout >> 2;
@@ -285,6 +289,8 @@ __device__ __forceinline__ float fast_act(float x) {  // compile-time activation
 
 template <int STRIDE, int ACT>
 __global__ void __launch_bounds__(256) dwconv3x3_pool_bf16_kernel(ConvParams p, float* __restrict__ pooled) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int OW = 4;                          // outputs per thread along W
   constexpr int NCOL = (OW - 1) * STRIDE + 3;    // input columns feeding them
   const __nv_bfloat16* __restrict__ in = reinterpret_cast<const __nv_bfloat16*>(p.in);
@@ -408,6 +414,8 @@ struct StemParams {
 
 template <typename TOut>
 __global__ void __launch_bounds__(256) stem_conv_kernel(StemParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sw[];  // weights [R*S*Cin][Cout] + bias [Cout]
   const int K = p.R * p.S * p.Cin;
   for (int i = threadIdx.x; i < K * p.Cout; i += blockDim.x) sw[i] = p.w[i];
@@ -455,6 +463,8 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(StemParams p) {
 // ----------------------------------------------------------------------------------------------------------
 template <typename TOut, int CPT>
 __global__ void __launch_bounds__(128) stem_conv_wide_kernel(StemParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sw[];  // weights [R*S*Cin][Cout] + bias [Cout]
   const int K = p.R * p.S * p.Cin;
   for (int i = threadIdx.x; i < K * p.Cout; i += blockDim.x) sw[i] = p.w[i];
@@ -511,6 +521,8 @@ __global__ void __launch_bounds__(128) stem_conv_wide_kernel(StemParams p) {
 // ----------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) pool_mean_kernel(const T* __restrict__ in, float* __restrict__ out, int P, int C) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float4 red[8][32];
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int b = blockIdx.y;
@@ -540,6 +552,8 @@ __global__ void __launch_bounds__(256) pool_mean_kernel(const T* __restrict__ in
 // activation: hidden[b][c] = act(sum_z partial[z][b][c] + bias[c]).  Fixed summation order (deterministic).
 __global__ void __launch_bounds__(256) se_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
                                                         float* __restrict__ out, int n, int C, int ksplit, int act) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = 0.f;
@@ -551,6 +565,8 @@ __global__ void __launch_bounds__(256) se_reduce_kernel(const float* __restrict_
 // pools VALID, so an out-of-bounds tap contributes the value 0 to the max.
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_kernel(ConvParams p) {
+  pdl_trigger();
+  pdl_wait();
   const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
   T* __restrict__ out = reinterpret_cast<T*>(p.out);
   const int C4 = p.Cout >> 2;
@@ -583,13 +599,13 @@ inline cudaError_t launch_conv_igemm(const ConvParams& p, cudaStream_t st) {
   const int M = p.B * p.Hout * p.Wout;
   if (p.Cout > 64 && M >= 128 * 148) {
     dim3 grid((M + 127) / 128, (p.Cout + 127) / 128);
-    conv_igemm_kernel<128, 128, 8, 8, TIn, TOut><<<grid, 256, 0, st>>>(p);
+    launch_k(conv_igemm_kernel<128, 128, 8, 8, TIn, TOut>, dim3(grid), dim3(256), 0, st, p);
   } else if (M >= 128 * 148) {
     dim3 grid((M + 127) / 128, (p.Cout + 63) / 64);
-    conv_igemm_kernel<128, 64, 8, 4, TIn, TOut><<<grid, 256, 0, st>>>(p);
+    launch_k(conv_igemm_kernel<128, 64, 8, 4, TIn, TOut>, dim3(grid), dim3(256), 0, st, p);
   } else {
     dim3 grid((M + 63) / 64, (p.Cout + 63) / 64, p.ksplit);
-    conv_igemm_kernel<64, 64, 4, 4, TIn, TOut><<<grid, 256, 0, st>>>(p);
+    launch_k(conv_igemm_kernel<64, 64, 4, 4, TIn, TOut>, dim3(grid), dim3(256), 0, st, p);
   }
   return cudaGetLastError();
 }

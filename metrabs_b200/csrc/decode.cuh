@@ -47,6 +47,8 @@ __device__ __forceinline__ float soft_coord(float weighted_index_sum, float s, i
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) softargmax_bdjhw_kernel(const T* __restrict__ logits, float* __restrict__ out,
                                                                int J, int D, int H, int W, int two_d) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x;  // b*J + j
   const int b = row / J, j = row - b * J;
   const int HW = H * W;
@@ -127,6 +129,8 @@ template <typename T>
 __global__ void __launch_bounds__(512) softargmax_bhwn_kernel(const T* __restrict__ logits, float* __restrict__ out2d,
                                                               float* __restrict__ out3d, int J, int D, int H, int W,
                                                               int ld, DecodeScale sc) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];  // [N][4] per-channel (m, s, sx, sy) + [PY][128][4] merge scratch
   const int N = J * (1 + D);
   const int P = H * W;
@@ -234,6 +238,8 @@ __device__ __forceinline__ void inv3x3(const float* k, float* inv) {
 }
 
 __global__ void __launch_bounds__(128) recon_pass1_kernel(ReconParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   __shared__ float kinv[9];
   __shared__ double red[4][2];
@@ -269,6 +275,8 @@ __global__ void __launch_bounds__(128) recon_pass1_kernel(ReconParams p) {
 }
 
 __global__ void __launch_bounds__(128) recon_pass2_kernel(ReconParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   __shared__ double red[4][9 + 3];
   __shared__ double tot[2];

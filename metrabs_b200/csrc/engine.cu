@@ -27,11 +27,11 @@ std::string g_error;
 enum OpType { OP_STEM = 0, OP_CONV = 1, OP_DW = 2, OP_POOL = 3, OP_MAXPOOL = 4 };
 // kernel classes for the CUDA-event profiler (mtb_profile_begin / mtb_profile_end)
 enum KClass { KC_STEM = 0, KC_IGEMM_SIMT = 1, KC_DWCONV = 2, KC_POOL = 3, KC_SE_FC = 4, KC_TC_GEMM = 5, KC_TC_CONV3 = 6,
-              KC_HEAD_FUSED = 7, KC_HEAD_CONV_SIMT = 8, KC_SOFTARGMAX = 9, KC_RECON = 10, KC_OTHER = 11, KC_COUNT = 12 };
+              KC_HEAD_FUSED = 7, KC_HEAD_CONV_SIMT = 8, KC_SOFTARGMAX = 9, KC_RECON = 10, KC_OTHER = 11, KC_SE_SCALE = 12, KC_COUNT = 13 };
 const char* kKClassNames[KC_COUNT] = {"stem_conv_kernel", "conv_igemm_kernel", "dwconv_kernel", "pool_mean_kernel",
                                       "se_fc(conv_igemm_kernel)", "tc_gemm_kernel", "tc_conv3x3_kernel",
                                       "tc_head_softargmax_kernel", "head_conv(conv_igemm_kernel)",
-                                      "softargmax_bhwn_kernel", "recon_pass1+2_kernel", "other"};
+                                      "softargmax_bhwn_kernel", "recon_pass1+2_kernel", "other", "se_scale_kernel"};
 enum { BUF_FEATURES = -2, BUF_NONE = -1, BUF_SMALL0 = 4 };  // 0..3 big activation buffers, 4..6 small [B,C]
 constexpr int kNumBig = 4, kNumSmall = 3;
 constexpr int kPoolSlices = 8;  // the fused depthwise+pool kernel leaves up to 8 partial slices [slice][B][C]
@@ -657,6 +657,15 @@ double op_bytes(const mtb_handle* h, const Op& op, int B) {
 template <typename T>
 int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Workspace& ws, void* features,
              cudaStream_t st) {
+  if (op.type == OP_CONV && op.tc.ready && op.scale_buf != BUF_NONE) {
+    // squeeze-excitation scale applied in place ahead of the tensor-core projection (own profiler class)
+    void* x = buf_ptr(ws, op.in_buf, features);
+    const double bytes = 2.0 * B * op.Hin * op.Win * op.Cin * elem_size(h);
+    ProfScope ps(h, KC_SE_SCALE, 0.0, bytes, st);
+    const char* e = tc_se_scale_launch(x, (const float*)buf_ptr(ws, op.scale_buf, features), B, op.Hin * op.Win, op.Cin, st);
+    if (e) return fail(h, MTB_ERR_CUDA, "se scale %s: %s", op.name.c_str(), e);
+    h->launches++;
+  }
   ProfScope prof(h, op_class(op), op.flops * B, op_bytes(h, op, B), st);
   switch (op.type) {
     case OP_STEM: {
@@ -668,10 +677,10 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
       p.R = op.R; p.S = op.S; p.stride = op.stride; p.pad_t = op.pad_t; p.pad_l = op.pad_l; p.act = op.act;
       size_t smem = ((size_t)op.R * op.S * op.Cin + 1) * op.Cout * 4;
       const size_t pixels = (size_t)B * op.Hout * op.Wout;
-      if (op.Cout % 32 == 0) stem_conv_wide_kernel<T, 32><<<grid_for(pixels * (op.Cout / 32), 128), 128, smem, st>>>(p);
-      else if (op.Cout % 24 == 0) stem_conv_wide_kernel<T, 24><<<grid_for(pixels * (op.Cout / 24), 128), 128, smem, st>>>(p);
-      else if (op.Cout % 16 == 0) stem_conv_wide_kernel<T, 16><<<grid_for(pixels * (op.Cout / 16), 128), 128, smem, st>>>(p);
-      else stem_conv_kernel<T><<<grid_for(pixels * (op.Cout / 4), 256), 256, smem, st>>>(p);
+      if (op.Cout % 32 == 0) launch_k(stem_conv_wide_kernel<T, 32>, dim3(grid_for(pixels * (op.Cout / 32), 128)), dim3(128), smem, st, p);
+      else if (op.Cout % 24 == 0) launch_k(stem_conv_wide_kernel<T, 24>, dim3(grid_for(pixels * (op.Cout / 24), 128)), dim3(128), smem, st, p);
+      else if (op.Cout % 16 == 0) launch_k(stem_conv_wide_kernel<T, 16>, dim3(grid_for(pixels * (op.Cout / 16), 128)), dim3(128), smem, st, p);
+      else launch_k(stem_conv_kernel<T>, dim3(grid_for(pixels * (op.Cout / 4), 256)), dim3(256), smem, st, p);
       h->launches++;
       break;
     }
@@ -692,22 +701,22 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
           float* pooled = op.fused_pool ? (float*)buf_ptr(ws, BUF_SMALL0, features) : nullptr;
           dim3 grid((op.Cout / 8 + 31) / 32, dw_pool_slices(op), B), block(32, 8);
           if (op.act == ACT_SILU) {
-            if (op.stride == 1) dwconv3x3_pool_bf16_kernel<1, ACT_SILU><<<grid, block, 0, st>>>(p, pooled);
-            else dwconv3x3_pool_bf16_kernel<2, ACT_SILU><<<grid, block, 0, st>>>(p, pooled);
+            if (op.stride == 1) launch_k(dwconv3x3_pool_bf16_kernel<1, ACT_SILU>, dim3(grid), dim3(block), 0, st, p, pooled);
+            else launch_k(dwconv3x3_pool_bf16_kernel<2, ACT_SILU>, dim3(grid), dim3(block), 0, st, p, pooled);
           } else if (op.act == ACT_RELU) {
-            if (op.stride == 1) dwconv3x3_pool_bf16_kernel<1, ACT_RELU><<<grid, block, 0, st>>>(p, pooled);
-            else dwconv3x3_pool_bf16_kernel<2, ACT_RELU><<<grid, block, 0, st>>>(p, pooled);
+            if (op.stride == 1) launch_k(dwconv3x3_pool_bf16_kernel<1, ACT_RELU>, dim3(grid), dim3(block), 0, st, p, pooled);
+            else launch_k(dwconv3x3_pool_bf16_kernel<2, ACT_RELU>, dim3(grid), dim3(block), 0, st, p, pooled);
           } else {
-            if (op.stride == 1) dwconv3x3_pool_bf16_kernel<1, ACT_HSWISH><<<grid, block, 0, st>>>(p, pooled);
-            else dwconv3x3_pool_bf16_kernel<2, ACT_HSWISH><<<grid, block, 0, st>>>(p, pooled);
+            if (op.stride == 1) launch_k(dwconv3x3_pool_bf16_kernel<1, ACT_HSWISH>, dim3(grid), dim3(block), 0, st, p, pooled);
+            else launch_k(dwconv3x3_pool_bf16_kernel<2, ACT_HSWISH>, dim3(grid), dim3(block), 0, st, p, pooled);
           }
         } else {
           size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
-          dwconv_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
+          launch_k(dwconv_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, st, p);
         }
       } else if (op.type == OP_MAXPOOL) {
         size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
-        maxpool_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
+        launch_k(maxpool_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, st, p);
       } else if (op.small_io) {
         float* final_out = (float*)p.out;
         if (op.pool_src > 0 && h->ops[op.pool_src].fused_pool) {  // input = partial pooling slices of the depthwise kernel
@@ -721,17 +730,12 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
         cudaError_t e = launch_conv_igemm<float, float>(p, st);
         if (e == cudaSuccess && op.ksplit > 1) {
           const int n = B * op.Cout;
-          se_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>((const float*)p.out, op.d_bias, final_out, n, op.Cout, op.ksplit, op.act);
+          launch_k(se_reduce_kernel, dim3((n + 255) / 256), dim3(256), 0, st, (const float*)p.out, op.d_bias, final_out, n, op.Cout, op.ksplit, op.act);
           h->launches++;
           e = cudaGetLastError();
         }
         if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "launch %s: %s", op.name.c_str(), cudaGetErrorString(e));
       } else if (op.tc.ready) {
-        if (op.scale_buf != BUF_NONE) {  // squeeze-excitation scale applied in place ahead of the tensor-core projection
-          const char* e = tc_se_scale_launch(const_cast<void*>(p.in), p.a_scale, B, op.Hin * op.Win, op.Cin, st);
-          if (e) return fail(h, MTB_ERR_CUDA, "se scale %s: %s", op.name.c_str(), e);
-          h->launches++;
-        }
         const char* e = tc_conv_launch(op.tc, p, op.res_first, st);
         if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 launch %s: %s", op.name.c_str(), e);
       } else {
@@ -743,7 +747,7 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
     }
     case OP_POOL: {
       dim3 grid((op.Cin + 127) / 128, B), block(32, 8);
-      pool_mean_kernel<T><<<grid, block, 0, st>>>((const T*)buf_ptr(ws, op.in_buf, features),
+      launch_k(pool_mean_kernel<T>, dim3(grid), dim3(block), 0, st, (const T*)buf_ptr(ws, op.in_buf, features),
                                                    (float*)buf_ptr(ws, op.out_buf, features), op.Hin * op.Win, op.Cin);
       h->launches++;
       break;
@@ -796,7 +800,7 @@ int launch_softargmax_bhwn(const void* logits, float* out2d, float* out3d, int B
     cudaError_t e = cudaFuncSetAttribute(softargmax_bhwn_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  softargmax_bhwn_kernel<T><<<B, 512, smem, st>>>((const T*)logits, out2d, out3d, J, D, H, W, ld, sc);
+  launch_k(softargmax_bhwn_kernel<T>, dim3(B), dim3(512), smem, st, (const T*)logits, out2d, out3d, J, D, H, W, ld, sc);
   return (int)cudaGetLastError();
 }
 
@@ -848,8 +852,8 @@ int recon_impl(mtb_handle* h, const float* c2d, const float* c3d, const float* K
   p.use_mix = c.mix_3d_inside_fov >= 0.f;
   p.mix = c.mix_3d_inside_fov;
   ProfScope prof(h, KC_RECON, 0.0, (double)B * c.n_joints * 8 * 4 + (double)B * 36, st);
-  recon_pass1_kernel<<<B, 128, 0, st>>>(p);
-  recon_pass2_kernel<<<B, 128, 0, st>>>(p);
+  launch_k(recon_pass1_kernel, dim3(B), dim3(128), 0, st, p);
+  launch_k(recon_pass2_kernel, dim3(B), dim3(128), 0, st, p);
   h->launches += 2;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "reconstruct: %s", cudaGetErrorString(e));
@@ -857,11 +861,15 @@ int recon_impl(mtb_handle* h, const float* c2d, const float* c3d, const float* K
 }
 
 __global__ void to_float_kernel(const __nv_bfloat16* in, float* out, size_t n) {
+  pdl_trigger();
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = __bfloat162float(in[i]);
 }
 
 __global__ void from_float_kernel(const float* in, __nv_bfloat16* out, size_t n) {
+  pdl_trigger();
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(in[i]);
 }
@@ -1097,11 +1105,11 @@ int mtb_softargmax(const void* logits, int dtype, int layout_, int batch, int n_
     const bool vec = (width % 4 == 0) && (((uintptr_t)logits) % 16 == 0);
     const int rows = batch * n_joints;
     if (dtype == MTB_DTYPE_F32) {
-      if (vec) softargmax_bdjhw_kernel<float, 4><<<rows, 256, 0, st>>>((const float*)logits, out, n_joints, D, height, width, two_d);
-      else softargmax_bdjhw_kernel<float, 1><<<rows, 256, 0, st>>>((const float*)logits, out, n_joints, D, height, width, two_d);
+      if (vec) launch_k(softargmax_bdjhw_kernel<float, 4>, dim3(rows), dim3(256), 0, st, (const float*)logits, out, n_joints, D, height, width, two_d);
+      else launch_k(softargmax_bdjhw_kernel<float, 1>, dim3(rows), dim3(256), 0, st, (const float*)logits, out, n_joints, D, height, width, two_d);
     } else {
-      if (vec) softargmax_bdjhw_kernel<__nv_bfloat16, 4><<<rows, 256, 0, st>>>((const __nv_bfloat16*)logits, out, n_joints, D, height, width, two_d);
-      else softargmax_bdjhw_kernel<__nv_bfloat16, 1><<<rows, 256, 0, st>>>((const __nv_bfloat16*)logits, out, n_joints, D, height, width, two_d);
+      if (vec) launch_k(softargmax_bdjhw_kernel<__nv_bfloat16, 4>, dim3(rows), dim3(256), 0, st, (const __nv_bfloat16*)logits, out, n_joints, D, height, width, two_d);
+      else launch_k(softargmax_bdjhw_kernel<__nv_bfloat16, 1>, dim3(rows), dim3(256), 0, st, (const __nv_bfloat16*)logits, out, n_joints, D, height, width, two_d);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(nullptr, MTB_ERR_CUDA, "softargmax launch: %s", cudaGetErrorString(e));
@@ -1286,7 +1294,7 @@ int mtb_debug_run_ops(mtb_handle* h, const float* crops, int batch, int n_ops, f
   if (small || !is_bf16(h)) {
     CUDA_TRY(h, cudaMemcpyAsync(out, src, n * 4, cudaMemcpyDeviceToDevice, st));
   } else {
-    to_float_kernel<<<grid_for(n, 256), 256, 0, st>>>((const __nv_bfloat16*)src, out, n);
+    launch_k(to_float_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, (const __nv_bfloat16*)src, out, n);
   }
   return MTB_OK;
 }
@@ -1372,7 +1380,7 @@ int mtb_debug_run_op(mtb_handle* h, int op_index, const float* in, const float* 
   auto put = [&](const float* src, int buf, size_t n, bool as_f32) {
     void* dst = buf_ptr(ws, buf, nullptr);
     if (as_f32 || !is_bf16(h)) cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, st);
-    else from_float_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, (__nv_bfloat16*)dst, n);
+    else launch_k(from_float_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, src, (__nv_bfloat16*)dst, n);
   };
   const float* crops = nullptr;
   if (o.type == OP_STEM) {
@@ -1393,7 +1401,7 @@ int mtb_debug_run_op(mtb_handle* h, int op_index, const float* in, const float* 
   if (rc) return rc;
   void* src = buf_ptr(ws, o.out_buf, nullptr);
   if (small || !is_bf16(h)) CUDA_TRY(h, cudaMemcpyAsync(out, src, n_out * 4, cudaMemcpyDeviceToDevice, st));
-  else to_float_kernel<<<grid_for(n_out, 256), 256, 0, st>>>((const __nv_bfloat16*)src, out, n_out);
+  else launch_k(to_float_kernel, dim3(grid_for(n_out, 256)), dim3(256), 0, st, (const __nv_bfloat16*)src, out, n_out);
   return MTB_OK;
 }
 

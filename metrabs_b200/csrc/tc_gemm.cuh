@@ -172,7 +172,7 @@ constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 32768 + 1024 /*align 
 //   [RING, RING+64K)     epilogue staging: 8 warps x 2 slabs of [32 rows x 128 B] (one TMA-store box each)
 //   then                 per-warp bias staging (8 x 256 B), mbarriers, TMEM slot
 constexpr int TCV_RING_BYTES = 144 * 1024;
-constexpr int TCV_MAX_STAGES = 8;
+constexpr int TCV_MAX_STAGES = 12;
 constexpr int TCV_SLAB_BYTES = 32 * 128;
 constexpr int TCV_EPI_OFF = TCV_RING_BYTES;
 constexpr int TCV_BIAS_OFF = TCV_EPI_OFF + 8 * 2 * TCV_SLAB_BYTES;
@@ -201,6 +201,7 @@ struct TcConvParams {
   int n_tiles, m_tiles, kchunks, taps;
   int nstages, stage_stride;  // operand ring depth and stage size in bytes (A at +0, B at +a_bytes)
   int patch_off, patch_bytes; // mode 2: the two resident patches sit at the tail of the ring region
+  int b_resident;             // mode 2, one N tile, all k-blocks of the weights fit the ring: loaded once per CTA
   int Hout, Wout, tiles_w, tiles_h, pad_t, pad_l, R, S, stride, dil;
   long long* trace;  // MTB_TC_TRACE: CTA 0 writes clock64 timestamps [role][event] (0 A/B producer, 1 MMA, 2 epilogue warp 0)
   int debug;    // MTB_TC_DEBUG bits (perf experiments only): 1 = skip the TMA store, 2 = skip the epilogue math + staging,
@@ -308,7 +309,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], TCV_EPI_WARPS);
-      mbar_init(&patch_full[i], 2);   // one arrive per loader warp
+      mbar_init(&patch_full[i], p.b_resident ? 3 : 2);   // one arrive per loader warp
       mbar_init(&patch_empty[i], 1);  // tcgen05.commit
     }
     fence_barrier_init();
@@ -318,6 +319,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();  // the next kernel may start its own prologue on SMs this grid has left
+  pdl_wait();     // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   const int total_tiles = p.m_tiles * p.n_tiles;
   const uint32_t a_bytes = patch_mode ? 0u : (uint32_t)TC_BM * BK * 2;
@@ -358,7 +361,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 9) {
     // ===== B-operand (weights) TMA producer =====
-    if (lane == 0) {
+    if (lane == 0 && p.b_resident) {
+      // the whole weight panel stays in the ring: slot kb <- k-block kb, loaded once
+      int kb = 0;
+      for (int tap = 0; tap < p.taps; ++tap)
+        for (int kc = 0; kc < p.kchunks; ++kc, ++kb) {
+          mbar_expect_tx(&full[kb], b_bytes);
+          tma_load_2d(smem + kb * p.stage_stride, &tmB, &full[kb], tap * p.Cin + kc * BK, 0);
+        }
+    } else if (lane == 0) {
       int stage = 0, tr = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -371,7 +382,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint8_t* sb = smem + stage * p.stage_stride + a_bytes;
             mbar_expect_tx(&full[stage], b_bytes);
             tma_load_2d(sb, &tmB, &full[stage], col, nrow);
-            if (patch_mode && p.trace && blockIdx.x == 0 && tr < 256) p.trace[tr++] = clock64();
             if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
         }
@@ -410,8 +420,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // two 16-byte K chunks of one MMA are one plane apart (LBO)
           const uint32_t tap_off = patch_mode ? (uint32_t)((tap / 3) * TC_PATCH_W + (tap % 3)) * 16 : 0u;
           for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(&full[stage], phase);
-            tc_fence_after();
+            if (!p.b_resident || t == (int)blockIdx.x) {
+              mbar_wait(&full[stage], phase);
+              tc_fence_after();
+            }
             if (p.trace && blockIdx.x == 0 && tr < 256) p.trace[256 + tr++] = clock64();
             const uint32_t sa = smem_a0 + stage * p.stage_stride;
             const uint32_t sb_lo = (sa + a_bytes) >> 4;
@@ -431,10 +443,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             first = 1;
-            umma_commit(&empty[stage]);  // frees the ring slot once these MMAs have read it
+            if (!p.b_resident) umma_commit(&empty[stage]);  // frees the ring slot once these MMAs have read it
             if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
         }
+        if (p.b_resident) { stage = 0; phase = 0; }  // resident weights: slot kb <-> k-block kb for every tile
+        if (p.trace && blockIdx.x == 0 && tr < 256) p.trace[256 + tr++] = -clock64();  // (negative) all MMAs of the tile issued
         if (patch_mode) {
           umma_commit(&patch_empty[pb]);  // the patch may be overwritten once this tile's MMAs have read it
           if (++pb == 2) { pb = 0; pb_phase ^= 1; }
@@ -444,14 +458,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   }
-  if ((warp == 8 || warp == 11) && patch_mode) {
+  if ((warp == 8 || warp == 11 || (warp == 9 && p.b_resident)) && patch_mode) {
     // ===== mode 2: stage the (tile + halo) input patch, chunk-planar [plane][patch row][patch col][16 B], with cp.async
     // (all of a thread's 16-byte copies in flight at once; out-of-image halo pixels and channels >= Cin zero-filled) =====
-    const int lt = (warp == 8 ? 0 : 32) + lane;  // 0..63
+    const int nload = p.b_resident ? 96 : 64;
+    const int lt = (warp == 8 ? 0 : warp == 11 ? 32 : 64) + lane;
     const __nv_bfloat16* __restrict__ in = (const __nv_bfloat16*)p.res_in;
     const int real_planes = p.Cin >> 3;
     const int items = TC_PATCH_H * TC_PATCH_W * planes;
-    int pb = 0;
+    int pb = 0, ltr = 0;
     uint32_t pb_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int m_blk = t / p.n_tiles;
@@ -460,8 +475,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int b = m_blk / (p.tiles_w * p.tiles_h);
       const int ih0 = th * TC_PT_H - p.pad_t, iw0 = tw * TC_PT_W - p.pad_l;
       mbar_wait(&patch_empty[pb], pb_phase ^ 1);
+      if (p.trace && blockIdx.x == 0 && warp == 8 && lane == 0 && ltr < 256) p.trace[ltr++] = clock64();  // patch slot free
       uint8_t* patch = smem + p.patch_off + pb * p.patch_bytes;
-      for (int i = lt; i < items; i += 64) {
+      for (int i = lt; i < items; i += nload) {
         const int j = i % planes, pix = i / planes;
         const int ph = pix / TC_PATCH_W, pw = pix - ph * TC_PATCH_W;
         const int ih = ih0 + ph, iw = iw0 + pw;
@@ -473,6 +489,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&patch_full[pb]);
+      if (p.trace && blockIdx.x == 0 && warp == 8 && lane == 0 && ltr < 256) p.trace[ltr++] = clock64();  // patch staged
       if (++pb == 2) { pb = 0; pb_phase ^= 1; }
     }
   }
@@ -482,7 +499,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = q * 32 + lane;
     uint8_t* slabs = smem + TCV_EPI_OFF + warp * 2 * TCV_SLAB_BYTES;
     float* bias_s = (float*)(smem + TCV_BIAS_OFF + warp * 256);
-    int acc = 0, etr = 0;
+    int acc = 0, etr = 0, tile_i = 0;
     uint32_t acc_phase = 0, slab_count = 0;
     const __nv_bfloat16* __restrict__ res = (const __nv_bfloat16*)p.res;
     const int rows_per_q = 32 >> p.tile_w_log2;  // tile rows covered by one warp's 32 lanes (spatial modes)
@@ -511,7 +528,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_MAX_BN;
       const int nchunks = (n_valid + 63) >> 6;
       bool released = false;
-      for (int ch = par; ch < nchunks; ch += 2) {
+      // two warp groups (par 0 / 1) alternate the 64-column chunks; one-chunk tiles alternate between the groups tile by tile
+      for (int ch = par ^ (nchunks == 1 ? (tile_i & 1) : 0); ch < nchunks; ch += 2) {
         const int c0 = ch * 64;
         const int ncols = min(64, n_valid - c0);  // multiple of 8
         // residual for this thread's row: issue the loads before waiting on TMEM
@@ -589,6 +607,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       }
       if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && etr < 256) p.trace[512 + etr++] = clock64();
+      ++tile_i;
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait_all();  // global writes complete before the CTA exits
@@ -604,6 +623,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // in-place squeeze-excitation scaling  x[b,p,c] *= s[b,c]  ahead of a tcgen05 projection GEMM
 __global__ void __launch_bounds__(256) se_scale_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ s, int P, int C,
                                                        size_t total8) {
+  pdl_trigger();
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (size_t)gridDim.x * blockDim.x) {
     size_t e = i * 8;
     int c = (int)(e % C);
@@ -772,7 +793,7 @@ inline const char* tc_conv_launch_k(int grid, const CUtensorMap& a, const CUtens
       return "cannot raise dynamic shared memory for tc_conv_kernel";
     attr_set = true;
   }
-  tc_conv_kernel<ACT, RES, BK><<<grid, TC_THREADS, TCV_SMEM_BYTES, st>>>(a, b, o, q);
+  launch_k(tc_conv_kernel<ACT, RES, BK>, dim3(grid), dim3(TC_THREADS), TCV_SMEM_BYTES, st, a, b, o, q);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -806,8 +827,7 @@ inline const char* tc_conv_dispatch(int act, int res_mode, int grid, const CUten
 inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool res_first, cudaStream_t st) {
   TcConvParams q;
   q.res = p.res; q.bias = w.d_bias;
-  const int rem0 = p.Cin % 64;
-  const int bk0 = (rem0 != 0 && rem0 <= 32) ? 32 : 64;
+  const int bk0 = p.Cin <= 32 ? 32 : 64;  // 64B-swizzled half-width stages only when they do not add k-blocks
   const int planes0 = ((p.Cin + bk0 - 1) / bk0) * (bk0 / 8);
   q.mode = (p.R == 1 && p.stride == 1) ? 0 : 1;
   if (p.R == 3 && p.S == 3 && p.stride == 1 && p.dil == 1 && planes0 <= TC_PATCH_MAX_PLANES && !tc_patch_disabled()) q.mode = 2;
@@ -823,8 +843,7 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
   }
   q.Cout = p.Cout; q.Cin = p.Cin;
   q.taps = w.taps; q.R = p.R; q.S = w.S; q.stride = p.stride; q.dil = p.dil;
-  const int rem = p.Cin % 64;
-  q.bk = (rem != 0 && rem <= 32) ? 32 : 64;  // e.g. Cin = 32, 96, 160, 224: no zero-padded half chunk
+  q.bk = bk0;  // every k-block costs ~0.3-0.5k cycles of single-thread TMA/MMA issue: never trade padding for more k-blocks
   q.kchunks = (p.Cin + q.bk - 1) / q.bk;
   q.Hout = p.Hout; q.Wout = p.Wout; q.pad_t = p.pad_t; q.pad_l = p.pad_l;
   q.tiles_w = (p.Wout + q.tile_w - 1) / q.tile_w;
@@ -842,6 +861,9 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
     q.nstages = ring / q.stage_stride;
     if (q.nstages > TCV_MAX_STAGES) q.nstages = TCV_MAX_STAGES;
     if (q.nstages < 2) return "operand ring too small for this tile";
+    const int num_kb = q.taps * q.kchunks;
+    q.b_resident = (q.mode == 2 && (p.Cout + bn - 1) / bn == 1 && num_kb <= q.nstages) ? 1 : 0;
+    if (q.b_resident) q.nstages = num_kb;
   }
   q.n_tiles = (p.Cout + bn - 1) / bn;
   if (w.cached_in != p.in || w.cached_out != p.out || w.cached_B != p.B || w.cached_bn != bn) {
@@ -881,13 +903,18 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
     std::vector<long long> hbuf(768);
     cudaStreamSynchronize(st);
     cudaMemcpy(hbuf.data(), trace_buf, 768 * sizeof(long long), cudaMemcpyDeviceToHost);
-    long long t0 = hbuf[0];
+    long long t0 = hbuf[0] ? hbuf[0] : hbuf[256];
+    if (t0 < 0) t0 = -t0;
     fprintf(stderr, "MTB_TC_TRACE Cin=%d Cout=%d mode=%d bk=%d bn=%d kb/tile=%d tiles=%d grid=%d\n", p.Cin, p.Cout, q.mode, q.bk, q.bn,
             q.taps * q.kchunks, total, grid);
     const char* names[3] = {"producer(TMA issued)", "mma(full wait done)", "epilogue(tmem_full done / tile end)"};
     for (int r = 0; r < 3; ++r) {
       fprintf(stderr, "  %s:", names[r]);
-      for (int i = 0; i < 60 && hbuf[r * 256 + i]; ++i) fprintf(stderr, " %lld", hbuf[r * 256 + i] - t0);
+      for (int i = 0; i < 70 && hbuf[r * 256 + i]; ++i) {
+        long long v = hbuf[r * 256 + i];
+        if (v < 0) fprintf(stderr, " [%lld]", -v - t0);
+        else fprintf(stderr, " %lld", v - t0);
+      }
       fprintf(stderr, "\n");
     }
   }
@@ -896,7 +923,7 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
 
 inline const char* tc_se_scale_launch(void* x, const float* s, int B, int P, int C, cudaStream_t st) {
   size_t total8 = (size_t)B * P * C / 8;
-  se_scale_kernel<<<grid_for(total8, 256), 256, 0, st>>>((__nv_bfloat16*)x, s, P, C, total8);
+  launch_k(se_scale_kernel, dim3(grid_for(total8, 256)), dim3(256), 0, st, (__nv_bfloat16*)x, s, P, C, total8);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -954,6 +981,8 @@ tc_head_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   const int items = p.n_groups * p.m_tiles;
   const uint32_t stage_tx = TC_A_BYTES + (uint32_t)p.bnp * TC_BK * 2;
@@ -1092,6 +1121,8 @@ tc_head_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 __global__ void __launch_bounds__(128) head_finalize_kernel(const float4* __restrict__ states, float* __restrict__ out2d,
                                                             float* __restrict__ out3d, int J, int D, int H, int W,
                                                             DecodeScale sc) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   const int n_out = J * (1 + D);
   for (int j = threadIdx.x; j < J; j += blockDim.x) {
@@ -1181,8 +1212,8 @@ inline const char* tc_head_launch(const TcWeights& w, const void* features, int 
     w.cached_B = B;
   }
   const int items = q.n_groups * q.m_tiles;
-  tc_head_kernel<<<items < 148 ? items : 148, 256, TC_SMEM_BYTES, st>>>(w.mapA, w.mapB, q);
-  head_finalize_kernel<<<B, 128, 0, st>>>(q.states, c2d, c3d, J, D, H, W, sc);
+  launch_k(tc_head_kernel, dim3(items < 148 ? items : 148), dim3(256), TC_SMEM_BYTES, st, w.mapA, w.mapB, q);
+  launch_k(head_finalize_kernel, dim3(B), dim3(128), 0, st, q.states, c2d, c3d, J, D, H, W, sc);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

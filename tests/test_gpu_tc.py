@@ -50,6 +50,41 @@ def test_tc_ops_match_cuda_core_ops(H, name, side, batch):
     print(f'{name}@{side}: {len(seen)} distinct op shapes, worst rel err {worst[0]:.2e} at {worst[1]}')
 
 
+@pytest.mark.parametrize('kind,cfgkw,batch', [
+    ('resnet50', dict(proc_side=256, stride_test=8, depth=8), 2),     # dilated 3x3, strided 1x1, residual BEFORE ReLU
+    ('resnet50', dict(proc_side=128, stride_test=32, depth=8), 3),
+    ('mobilenetv3-small', dict(proc_side=256, stride_test=32, depth=8), 3),  # hard-swish epilogues, 5x5 depthwise (CUDA cores)
+])
+def test_tc_ops_match_cuda_core_ops_tf_backbones(H, kind, cfgkw, batch):
+    from oracle import port_tf_backbones as tfb
+    pcfg = port.PathConfig(**cfgkw)
+    spec = tfb.ResNet50Spec(pcfg) if kind == 'resnet50' else tfb.MobileNetV3SmallSpec(pcfg)
+    sd = tfb.make_state_dict(spec, pcfg, 8, seed=0, calib_batch=2)
+    e_tc = H.device_model_tf(kind, pcfg, 8, sd, precision='bf16').engine()
+    e_ref = H.device_model_tf(kind, pcfg, 8, sd, precision='bf16_simt').engine()
+    g = torch.Generator().manual_seed(4)
+    seen, worst = set(), (0.0, None)
+    for i, nm in enumerate(e_tc.op_names()):
+        if nm.endswith(('.avgpool', '.fc1', '.fc2')) or i == 0:
+            continue
+        io = e_tc.op_io(i)
+        sig = (io['in_shape'], io['out_shape'], io['residual'], io['scale'], nm.rsplit('_', 2)[-2:] if kind == 'resnet50' else nm.rsplit('.', 1)[-1])
+        sig = str(sig)
+        if sig in seen:
+            continue
+        seen.add(sig)
+        x = torch.randn((batch,) + io['in_shape'], generator=g).bfloat16().float().cuda()
+        res = torch.randn((batch,) + io['out_shape'], generator=g).bfloat16().float().cuda() if io['residual'] else None
+        sc = torch.rand(batch, io['in_shape'][2], generator=g).cuda() if io['scale'] else None
+        a = e_tc.debug_run_op(i, x, res, sc)
+        b = e_ref.debug_run_op(i, x, res, sc)
+        err = port.relative_error(a.cpu(), b.cpu())
+        if err > worst[0]:
+            worst = (err, (nm, io))
+        assert err < 1e-2, f'op {i} {nm} {io}: tensor-core vs CUDA-core rel err {err:.3e}'
+    print(f'{kind} {cfgkw}: {len(seen)} distinct op shapes, worst rel err {worst[0]:.2e} at {worst[1]}')
+
+
 def test_fused_depthwise_pooling_matches_separate_pool(H):
     """BF16_TC fuses the SE squeeze into the depthwise kernel (block reduction -> partial slices summed by fc1 in a
     fixed order); BF16_SIMT runs the plain depthwise kernel and a separate pooling pass.  Compared at the output of the

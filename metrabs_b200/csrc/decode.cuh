@@ -44,51 +44,119 @@ __device__ __forceinline__ float soft_coord(float weighted_index_sum, float s, i
 // with two_d != 0, logits [B,J,H,W] -> out [B,J,2].  One CTA per (b,j) row: D segments of H*W contiguous
 // elements.  Single pass over HBM (algorithmic bytes = the logits once), 128-bit loads when W % 4 == 0.
 // ----------------------------------------------------------------------------------------------------------
-template <typename T, int VEC>
+// 16-byte vector of logits -> floats (4 fp32 or 8 bf16)
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float* v) {
+    float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+};
+template <>
+struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
+    uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+    const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+
+__device__ __forceinline__ float ex2_fast(float x) {  // one MUFU op; inputs here are <= 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// VEC = elements per load: 16 bytes' worth (4 fp32 / 8 bf16) when W % VEC == 0 and the base is 16-byte aligned, else 1.
+// UNROLL independent 16-byte loads are in flight per thread before any is consumed.  The first version of this kernel
+// spent ~32 lane-instructions per element (ncu: issue slots 73 % busy at 51 % of HBM peak: integer divisions per vector,
+// int->float converts and the slow-path exp2f per element); this one spends ~9: power-of-two index math when H*W and W
+// are powers of two (POW2), exp2 as one FFMA + one MUFU (the shared factor 2^(-m*log2e) cancels in sum(e*x)/sum(e), so
+// its rounding is irrelevant), and the x-weights as compile-time constants plus one FMA per vector.
+template <typename T, int VEC, bool POW2>
 __global__ void __launch_bounds__(256) softargmax_bdjhw_kernel(const T* __restrict__ logits, float* __restrict__ out,
-                                                               int J, int D, int H, int W, int two_d) {
+                                                               int J, int D, int H, int W, int two_d, int hw_shift,
+                                                               int w_shift) {
   pdl_trigger();
   pdl_wait();
+  constexpr int UNROLL = 4;
   const int row = blockIdx.x;  // b*J + j
   const int b = row / J, j = row - b * J;
   const int HW = H * W;
   const int n = D * HW;
   constexpr float L2E = 1.4426950408889634f;
-  SoftState st;
-  soft_init(st);
-  // VEC consecutive elements share y (W % VEC == 0) and d.
-  for (int e = threadIdx.x * VEC; e < n; e += blockDim.x * VEC) {
-    int d = e / HW;
-    int rem = e - d * HW;
-    int y = rem / W, x = rem - y * W;
-    const T* ptr = logits + ((size_t)(b * D + d) * J + j) * HW + rem;
-    float v[VEC];
-    if (VEC == 4) {
-      float4 q = load4<T>(ptr);
-      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
-      v[0] = load1<T>(ptr);
-    }
-    float vm = v[0];
+  float m = -INFINITY, mL = -INFINITY, s_ = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+  const int step = blockDim.x * VEC;
+  const T* base = logits + ((size_t)b * D * J + j) * HW;
+  const size_t dstride = (size_t)J * HW;
+  for (int e0 = threadIdx.x * VEC; e0 < n; e0 += step * UNROLL) {
+    float v[UNROLL][VEC];
+    int dd[UNROLL], yy[UNROLL], xx[UNROLL];
+    bool ok[UNROLL];
 #pragma unroll
-    for (int i = 1; i < VEC; ++i) vm = fmaxf(vm, v[i]);
-    if (vm > st.m) {
-      float f = exp2f((st.m - vm) * L2E);  // first time: exp2(-inf) = 0
-      st.s *= f; st.sx *= f; st.sy *= f; st.sz *= f;
-      st.m = vm;
-    }
-    float es = 0.f, ex = 0.f;
+    for (int u = 0; u < UNROLL; ++u) {
+      const int e = e0 + u * step;
+      ok[u] = e < n;
+      const int ee = ok[u] ? e : 0;
+      int d, rem, y;
+      if (POW2) {
+        d = ee >> hw_shift;
+        rem = ee & (HW - 1);
+        y = rem >> w_shift;
+        xx[u] = rem & (W - 1);
+      } else {
+        d = ee / HW;
+        rem = ee - d * HW;
+        y = rem / W;
+        xx[u] = rem - y * W;
+      }
+      dd[u] = d; yy[u] = y;
+      const T* ptr = base + (size_t)d * dstride + rem;
+      if (ok[u]) {
+        if constexpr (VEC == 1) v[u][0] = load1<T>(ptr);
+        else Vec16<T>::load(ptr, v[u]);
+      } else {
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      float ee = exp2f((v[i] - st.m) * L2E);
-      es += ee;
-      ex = fmaf(ee, (float)(x + i), ex);
+        for (int i = 0; i < VEC; ++i) v[u][i] = -INFINITY;  // exp2(-inf) = 0: contributes nothing
+      }
     }
-    st.s += es;
-    st.sx += ex;
-    st.sy = fmaf(es, (float)y, st.sy);
-    st.sz = fmaf(es, (float)d, st.sz);
+    float vm = v[0][0];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) vm = fmaxf(vm, v[u][i]);
+    if (vm > m) {
+      const float mL_new = vm * L2E;
+      const float f = ex2_fast(mL - mL_new);  // same rounded offsets as the elements use; first time exp2(-inf) = 0
+      s_ *= f; sx *= f; sy *= f; sz *= f;
+      m = vm;
+      mL = mL_new;
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      float es = 0.f, ex = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float ee = ex2_fast(fmaf(v[u][i], L2E, -mL));
+        es += ee;
+        if (i > 0) ex = fmaf(ee, (float)i, ex);
+      }
+      s_ += es;
+      sx += fmaf(es, (float)xx[u], ex);
+      sy = fmaf(es, (float)yy[u], sy);
+      sz = fmaf(es, (float)dd[u], sz);
+    }
   }
+  SoftState st;
+  st.m = m; st.s = s_; st.sx = sx; st.sy = sy; st.sz = sz;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     SoftState other = soft_shfl_xor(st, o);

@@ -169,7 +169,7 @@ struct Planner {
     f1.flops = 2.0 * cexp * csq_real;
     // K = cexp is long and M = batch is short: split K over CTAs; the ksplit partial slices [ksplit][B][csq] must fit
     // the small buffer (capacity >= cexp floats per crop)
-    f1.ksplit = std::max(1, std::min({32, cexp / 64, cexp / csq}));
+    f1.ksplit = std::max(1, std::min({8, cexp / 64, cexp / csq}));  // <= 8 slices: fc2 sums them on its A load
     h->ops.push_back(f1);
     const int f1_index = (int)h->ops.size() - 1;
     Op f2;
@@ -177,7 +177,7 @@ struct Planner {
     f2.Cin = csq; f2.Cout = cexp; f2.act = act2; f2.small_io = true; f2.pad_ok = true;
     f2.in_buf = BUF_SMALL0 + 1; f2.out_buf = BUF_SMALL0 + 2;
     f2.flops = 2.0 * cexp * csq_real;
-    (void)f1_index;
+    if (f1.ksplit > 1) { f2.a_bias_from = f1_index; f2.a_act = act1; }
     h->ops.push_back(f2);
     max_small = std::max(max_small, cexp);
   }
@@ -657,8 +657,9 @@ double op_bytes(const mtb_handle* h, const Op& op, int B) {
 template <typename T>
 int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Workspace& ws, void* features,
              cudaStream_t st) {
-  if (op.type == OP_CONV && op.tc.ready && op.scale_buf != BUF_NONE) {
-    // squeeze-excitation scale applied in place ahead of the tensor-core projection (own profiler class)
+  if (op.type == OP_CONV && op.tc.ready && op.scale_buf != BUF_NONE && !(op.R == 1 && op.stride == 1) ) {
+    // squeeze-excitation scale applied in place ahead of a tensor-core conv that cannot fuse it (1x1 stride-1 projections
+    // apply it to the A tiles in shared memory inside tc_conv_kernel)
     void* x = buf_ptr(ws, op.in_buf, features);
     const double bytes = 2.0 * B * op.Hin * op.Win * op.Cin * elem_size(h);
     ProfScope ps(h, KC_SE_SCALE, 0.0, bytes, st);
@@ -718,22 +719,19 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
         size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
         launch_k(maxpool_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, st, p);
       } else if (op.small_io) {
-        float* final_out = (float*)p.out;
         if (op.pool_src > 0 && h->ops[op.pool_src].fused_pool) {  // input = partial pooling slices of the depthwise kernel
           p.a_splits = dw_pool_slices(h->ops[op.pool_src - 1]);
           p.a_split_stride = (size_t)B * op.Cin;
         }
-        if (op.ksplit > 1) {  // split-K partial slices go to the (still unused) scale buffer, then one tiny reduce kernel
-          p.ksplit = op.ksplit;
-          p.out = buf_ptr(ws, BUF_SMALL0 + 2, features);
+        if (op.ksplit > 1) p.ksplit = op.ksplit;  // split-K: raw partial slices [ksplit][B][Cout]; the consumer (fc2) sums them
+        if (op.a_bias_from >= 0) {               // fc2: input = fc1's slices; + fc1 bias, activation, all on the A load
+          const Op& prod = h->ops[op.a_bias_from];
+          p.a_bias = prod.d_bias;
+          p.a_act = op.a_act;
+          p.a_splits = prod.ksplit;
+          p.a_split_stride = (size_t)B * prod.Cout;
         }
         cudaError_t e = launch_conv_igemm<float, float>(p, st);
-        if (e == cudaSuccess && op.ksplit > 1) {
-          const int n = B * op.Cout;
-          launch_k(se_reduce_kernel, dim3((n + 255) / 256), dim3(256), 0, st, (const float*)p.out, op.d_bias, final_out, n, op.Cout, op.ksplit, op.act);
-          h->launches++;
-          e = cudaGetLastError();
-        }
         if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "launch %s: %s", op.name.c_str(), cudaGetErrorString(e));
       } else if (op.tc.ready) {
         const char* e = tc_conv_launch(op.tc, p, op.res_first, st);
@@ -1102,15 +1100,27 @@ int mtb_softargmax(const void* logits, int dtype, int layout_, int batch, int n_
     float* out = two_d ? out2d : out3d;
     if (!out) return fail(nullptr, MTB_ERR_INVALID_ARG, "null output");
     const int D = two_d ? 1 : depth;
-    const bool vec = (width % 4 == 0) && (((uintptr_t)logits) % 16 == 0);
+    const int vw = dtype == MTB_DTYPE_F32 ? 4 : 8;  // elements per 16-byte vector
+    const bool vec = (width % vw == 0) && (((uintptr_t)logits) % 16 == 0);
     const int rows = batch * n_joints;
+    const int hw = height * width;
+    const bool pow2 = (hw & (hw - 1)) == 0 && (width & (width - 1)) == 0;
+    int hw_shift = 0, w_shift = 0;
+    while ((1 << hw_shift) < hw) ++hw_shift;
+    while ((1 << w_shift) < width) ++w_shift;
+#define MTB_SA_LAUNCH(TT, VV, PP)                                                                                        \
+  launch_k(softargmax_bdjhw_kernel<TT, VV, PP>, dim3(rows), dim3(256), 0, st, (const TT*)logits, out, n_joints, D, height, \
+           width, (int)two_d, hw_shift, w_shift)
     if (dtype == MTB_DTYPE_F32) {
-      if (vec) launch_k(softargmax_bdjhw_kernel<float, 4>, dim3(rows), dim3(256), 0, st, (const float*)logits, out, n_joints, D, height, width, two_d);
-      else launch_k(softargmax_bdjhw_kernel<float, 1>, dim3(rows), dim3(256), 0, st, (const float*)logits, out, n_joints, D, height, width, two_d);
+      if (vec && pow2) MTB_SA_LAUNCH(float, 4, true);
+      else if (vec) MTB_SA_LAUNCH(float, 4, false);
+      else MTB_SA_LAUNCH(float, 1, false);
     } else {
-      if (vec) launch_k(softargmax_bdjhw_kernel<__nv_bfloat16, 4>, dim3(rows), dim3(256), 0, st, (const __nv_bfloat16*)logits, out, n_joints, D, height, width, two_d);
-      else launch_k(softargmax_bdjhw_kernel<__nv_bfloat16, 1>, dim3(rows), dim3(256), 0, st, (const __nv_bfloat16*)logits, out, n_joints, D, height, width, two_d);
+      if (vec && pow2) MTB_SA_LAUNCH(__nv_bfloat16, 8, true);
+      else if (vec) MTB_SA_LAUNCH(__nv_bfloat16, 8, false);
+      else MTB_SA_LAUNCH(__nv_bfloat16, 1, false);
     }
+#undef MTB_SA_LAUNCH
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(nullptr, MTB_ERR_CUDA, "softargmax launch: %s", cudaGetErrorString(e));
     return MTB_OK;

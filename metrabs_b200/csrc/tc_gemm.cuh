@@ -183,13 +183,16 @@ constexpr int TC_TILE_W = 16, TC_TILE_H = 8;        // spatial M tile of mode 1 
 constexpr int TC_PT_W = 8, TC_PT_H = 16, TC_PATCH_W = TC_PT_W + 2, TC_PATCH_H = TC_PT_H + 2;
 constexpr int TC_PLANE_BYTES = TC_PATCH_W * TC_PATCH_H * 16;   // 2880
 constexpr int TC_PATCH_MAX_PLANES = 12;                          // Cin <= 96
-constexpr int TC_THREADS = 384;  // warps 0-7 epilogue; 8 A producer / patch loader; 9 B producer; 10 MMA + TMEM; 11 patch loader
+constexpr int TC_THREADS = 416;  // warps 0-7 epilogue; 8 A producer / patch loader; 9 B producer; 10 MMA + TMEM; 11 patch loader /
+                                 // SE scaler; 12 SE scaler
 constexpr int TCV_EPI_WARPS = 8;
 
 struct TcConvParams {
   const void* res;
   const void* res_in;  // mode 2: the NHWC input tensor, read by the patch loader warps
   const float* bias;
+  const float* a_scale;  // mode 0 only: squeeze-excitation scale [B][Cin] (fp32) applied to the A tiles in shared memory
+  int a_scale_P;         // pixels per crop (row / P = crop index)
   int mode;     // 0: flat 1x1 stride 1 (rows = B*H*W, 2D maps); 1: spatial tiles, A tile per tap by 4D TMA (any RxS, stride
                 // 1/2, dilation); 2: 3x3 stride 1 with a RESIDENT input patch: the (tile+halo) x Cin patch is staged once per
                 // tile in a channel-chunk-planar layout and every tap's A operand is a no-swizzle UMMA descriptor into it
@@ -292,7 +295,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_empty = tmem_full + 2;               // [2]
   uint64_t* patch_full = tmem_empty + 2;              // [2]
   uint64_t* patch_empty = patch_full + 2;             // [2]
-  uint32_t* tmem_slot = (uint32_t*)(patch_empty + 2);
+  uint64_t* scaled = patch_empty + 2;                 // [12] mode 0 + SE: A tile of the stage multiplied by the SE scale
+  uint32_t* tmem_slot = (uint32_t*)(scaled + TCV_MAX_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool patch_mode = p.mode == 2;
@@ -305,6 +309,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < TCV_MAX_STAGES; ++i) {
       mbar_init(&full[i], patch_mode ? 1 : 2);  // one arrive.expect_tx per TMA producer
       mbar_init(&empty[i], 1);                  // tcgen05.commit
+      mbar_init(&scaled[i], 2);                 // one arrive per scaler warp
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -421,7 +426,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t tap_off = patch_mode ? (uint32_t)((tap / 3) * TC_PATCH_W + (tap % 3)) * 16 : 0u;
           for (int kc = 0; kc < p.kchunks; ++kc) {
             if (!p.b_resident || t == (int)blockIdx.x) {
-              mbar_wait(&full[stage], phase);
+              mbar_wait(p.a_scale ? &scaled[stage] : &full[stage], phase);
               tc_fence_after();
             }
             if (p.trace && blockIdx.x == 0 && tr < 256) p.trace[256 + tr++] = clock64();
@@ -455,6 +460,58 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+  if ((warp == 11 || warp == 12) && p.a_scale != nullptr) {
+    // ===== squeeze-excitation scalers (mode 0): once the TMA has landed a stage, multiply its A tile IN SHARED MEMORY by
+    // s[crop(row)][k] (models the reference's `scale * x` ahead of the projection conv, backbones/efficientnet.py:110-173),
+    // then hand the stage to the MMA warp.  Thread t owns tile rows t and t+64. =====
+    const int lt = (warp - 11) * 32 + lane;  // 0..63
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m_blk = t / p.n_tiles;
+      const float* srow[2];
+      bool rok[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int m = m_blk * TC_BM + lt + h * 64;
+        rok[h] = m < p.M;
+        srow[h] = p.a_scale + (size_t)(rok[h] ? m / p.a_scale_P : 0) * p.Cin;
+      }
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&full[stage], phase);
+        uint8_t* sa = smem + stage * p.stage_stride;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = lt + h * 64;
+          if (!rok[h]) continue;
+          uint8_t* rowp = sa + r * (BK * 2);
+#pragma unroll
+          for (int pos = 0; pos < BK / 8; ++pos) {
+            const int chunk = pos ^ (r & (BK / 8 - 1));          // swizzle: 16-byte chunk `chunk` sits at position `pos`
+            const int k = kc * BK + chunk * 8;
+            if (k >= p.Cin) continue;                            // K tail: the tile holds TMA zero fill there
+            uint4 v = *reinterpret_cast<uint4*>(rowp + pos * 16);
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(srow[h] + k));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(srow[h] + k + 4));
+            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            unsigned wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float lo = __uint_as_float(wd[i] << 16) * sc[2 * i];
+              const float hi = __uint_as_float(wd[i] & 0xffff0000u) * sc[2 * i + 1];
+              __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+              wd[i] = *reinterpret_cast<unsigned*>(&pk);
+            }
+            *reinterpret_cast<uint4*>(rowp + pos * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&scaled[stage]);
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
     }
   }
@@ -532,15 +589,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int ch = par ^ (nchunks == 1 ? (tile_i & 1) : 0); ch < nchunks; ch += 2) {
         const int c0 = ch * 64;
         const int ncols = min(64, n_valid - c0);  // multiple of 8
-        // residual for this thread's row: issue the loads before waiting on TMEM
-        uint4 rv[8];
-        if constexpr (RES != 0) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            rv[g] = make_uint4(0u, 0u, 0u, 0u);
-            if (valid && g * 8 < ncols && !(p.debug & 4)) rv[g] = *reinterpret_cast<const uint4*>(res + off + n0 + c0 + g * 8);
-          }
-        }
         // bias of the chunk -> this warp's staging (64 floats), broadcast-read below
         __syncwarp();
         if (lane < 16) {
@@ -548,49 +596,63 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane * 4 < ncols) bv = *reinterpret_cast<const float4*>(p.bias + n0 + c0 + lane * 4);
           *reinterpret_cast<float4*>(bias_s + lane * 4) = bv;
         }
-        uint32_t v[64];
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          if (g * 16 < ncols) tmem_ld16_issue(taddr + c0 + g * 16, v + g * 16);
-        tmem_ld_wait();
-        if (ch + 2 >= nchunks) {  // last chunk of this warp: its TMEM reads of the tile are done
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-          released = true;
-        }
         uint8_t* slab = slabs + (slab_count & 1) * TCV_SLAB_BYTES;
         if (lane == 0) tma_store_wait_read<1>();  // the store that last read this slab (2 chunks ago) is done with it
         __syncwarp();
+        // two halves of 32 columns (keeps the live register set under the 128-register budget of a 416-thread CTA)
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          uint4 ov = make_uint4(0u, 0u, 0u, 0u);
-          if (g * 8 < ncols && !(p.debug & 2)) {
-            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + g * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + g * 8 + 4);
-            float o[8];
-            o[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; o[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
-            o[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; o[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
-            o[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; o[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
-            o[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; o[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
-            if constexpr (RES != 0) {
-              const unsigned wd[4] = {rv[g].x, rv[g].y, rv[g].z, rv[g].w};
+        for (int hf = 0; hf < 2; ++hf) {
+          const int cb = hf * 32;
+          // residual for this thread's row: issue the loads before waiting on TMEM
+          uint4 rv[4];
+          if constexpr (RES != 0) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float r0 = __uint_as_float(wd[i] << 16), r1 = __uint_as_float(wd[i] & 0xffff0000u);
-                o[2 * i] = RES == 2 ? tc_act<ACT>(o[2 * i] + r0) : tc_act<ACT>(o[2 * i]) + r0;
-                o[2 * i + 1] = RES == 2 ? tc_act<ACT>(o[2 * i + 1] + r1) : tc_act<ACT>(o[2 * i + 1]) + r1;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = tc_act<ACT>(o[i]);
+            for (int g = 0; g < 4; ++g) {
+              rv[g] = make_uint4(0u, 0u, 0u, 0u);
+              if (valid && cb + g * 8 < ncols && !(p.debug & 4)) rv[g] = *reinterpret_cast<const uint4*>(res + off + n0 + c0 + cb + g * 8);
             }
-            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
           }
-          // 128B swizzle: 16-byte chunk g of slab row r lives at chunk position g ^ (r & 7)
-          *reinterpret_cast<uint4*>(slab + lane * 128 + ((g ^ (lane & 7)) << 4)) = ov;
+          uint32_t v[32];
+          if (cb < ncols) tmem_ld16_issue(taddr + c0 + cb, v);
+          if (cb + 16 < ncols) tmem_ld16_issue(taddr + c0 + cb + 16, v + 16);
+          tmem_ld_wait();
+          if (hf == 1 && ch + 2 >= nchunks) {  // last TMEM read of this warp in the tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            released = true;
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 ov = make_uint4(0u, 0u, 0u, 0u);
+            if (cb + g * 8 < ncols && !(p.debug & 2)) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cb + g * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + cb + g * 8 + 4);
+              float o[8];
+              o[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; o[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+              o[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; o[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+              o[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; o[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+              o[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; o[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+              if constexpr (RES != 0) {
+                const unsigned wd[4] = {rv[g].x, rv[g].y, rv[g].z, rv[g].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float r0 = __uint_as_float(wd[i] << 16), r1 = __uint_as_float(wd[i] & 0xffff0000u);
+                  o[2 * i] = RES == 2 ? tc_act<ACT>(o[2 * i] + r0) : tc_act<ACT>(o[2 * i]) + r0;
+                  o[2 * i + 1] = RES == 2 ? tc_act<ACT>(o[2 * i + 1] + r1) : tc_act<ACT>(o[2 * i + 1]) + r1;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = tc_act<ACT>(o[i]);
+              }
+              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+            }
+            // 128B swizzle: 16-byte chunk j of slab row r lives at chunk position j ^ (r & 7)
+            const int j = hf * 4 + g;
+            *reinterpret_cast<uint4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = ov;
+          }
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
@@ -826,6 +888,8 @@ inline const char* tc_conv_dispatch(int act, int res_mode, int grid, const CUten
 
 inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool res_first, cudaStream_t st) {
   TcConvParams q;
+  q.a_scale = (p.R == 1 && p.stride == 1) ? p.a_scale : nullptr;  // fused in shared memory (mode 0); else pre-scaled
+  q.a_scale_P = p.Hin * p.Win;
   q.res = p.res; q.bias = w.d_bias;
   const int bk0 = p.Cin <= 32 ? 32 : 64;  // 64B-swizzled half-width stages only when they do not add k-blocks
   const int planes0 = ((p.Cin + bk0 - 1) / bk0) * (bk0 / 8);
@@ -1046,7 +1110,7 @@ tc_head_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       const float bias_n = nvalid ? p.bias[n] : 0.f;
       int crop = p.cpt > 0 ? g * p.cpt : g;
       int pix = 0, x = 0, y = 0;
-      float m = -INFINITY, s = 0.f, sx = 0.f, sy = 0.f;
+      float m = -INFINITY, mL = -INFINITY, s = 0.f, sx = 0.f, sy = 0.f;
       for (int pt = 0; pt < p.npt; ++pt) {
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -1061,13 +1125,16 @@ tc_head_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             for (int i = 1; i < 16; ++i) vm = fmaxf(vm, v[i]);
             vm += bias_n;
             if (vm > m) {
-              float f = exp2f((m - vm) * L2E);
+              const float mL_new = vm * L2E;
+              float f = ex2_fast(mL - mL_new);  // same rounded offsets as the elements use
               s *= f; sx *= f; sy *= f;
               m = vm;
+              mL = mL_new;
             }
+            const float cL = fmaf(bias_n, L2E, -mL);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              float e = exp2f((v[i] + bias_n - m) * L2E);
+              float e = ex2_fast(fmaf(v[i], L2E, cL));
               s += e;
               sx = fmaf(e, (float)x, sx);
               sy = fmaf(e, (float)y, sy);
@@ -1077,7 +1144,7 @@ tc_head_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             if (pix == p.P) {
               if (nvalid && crop < p.B) p.states[(size_t)crop * p.n_out + n] = make_float4(m, s, sx, sy);
               ++crop; pix = 0; x = 0; y = 0;
-              m = -INFINITY; s = 0.f; sx = 0.f; sy = 0.f;
+              m = -INFINITY; mL = -INFINITY; s = 0.f; sx = 0.f; sy = 0.f;
             }
           } else {
             // chunk straddles a crop boundary (P % 16 != 0): element-wise
@@ -1085,11 +1152,13 @@ tc_head_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             for (int i = 0; i < 16; ++i) {
               float vv = v[i] + bias_n;
               if (vv > m) {
-                float f = exp2f((m - vv) * L2E);
+                const float mL_new = vv * L2E;
+                float f = ex2_fast(mL - mL_new);
                 s *= f; sx *= f; sy *= f;
                 m = vv;
+                mL = mL_new;
               }
-              float e = exp2f((vv - m) * L2E);
+              float e = ex2_fast(fmaf(vv, L2E, -mL));
               s += e;
               sx = fmaf(e, (float)x, sx);
               sy = fmaf(e, (float)y, sy);
@@ -1097,7 +1166,7 @@ tc_head_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
               if (++pix == p.P) {
                 if (nvalid && crop < p.B) p.states[(size_t)crop * p.n_out + n] = make_float4(m, s, sx, sy);
                 ++crop; pix = 0; x = 0; y = 0;
-                m = -INFINITY; s = 0.f; sx = 0.f; sy = 0.f;
+                m = -INFINITY; mL = -INFINITY; s = 0.f; sx = 0.f; sy = 0.f;
               }
             }
           }

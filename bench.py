@@ -22,7 +22,8 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 METRIC = 'crops/sec'
-NAMES = {'s': 'efficientnetv2-s', 'm': 'efficientnetv2-m', 'l': 'efficientnetv2-l', 'tiny': 'efficientnetv2-tiny'}
+NAMES = {'s': 'efficientnetv2-s', 'm': 'efficientnetv2-m', 'l': 'efficientnetv2-l', 'tiny': 'efficientnetv2-tiny',
+         'resnet50': 'resnet50', 'mobilenetv3-small': 'mobilenetv3-small'}
 
 
 def parse():
@@ -33,11 +34,15 @@ def parse():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--size', default='l', choices=list(NAMES))
     ap.add_argument('--side', type=int, default=256)
+    ap.add_argument('--stride', type=int, default=32, help='stride_test (ResNet-50 config c2: 8)')
+    ap.add_argument('--depth', type=int, default=8, help='heatmap depth D (config c2: 32)')
     ap.add_argument('--joints', type=int, default=24)
     ap.add_argument('--batch', type=int, default=256, help='crops per GPU per step (weak scaling)')
     ap.add_argument('--precision', default=os.environ.get('MTB_BENCH_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
     ap.add_argument('--cpu-sample', type=int, default=8, help='crops per CPU-baseline forward')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--graph', type=int, default=int(os.environ.get('MTB_BENCH_GRAPH', '0')),
+                    help='1: replay the forward from a CUDA graph in the `value` region (mtb_forward never syncs or allocates)')
     return ap.parse_args()
 
 
@@ -113,10 +118,19 @@ def build_model(args, device):
     from metrabs_b200.init import conditioned_random_init_
     from metrabs_b200.models.metrabs import Metrabs
     import types
-    metrabs_b200.set_config(metrabs_b200.Config(proc_side=args.side, precision=args.precision))
+    metrabs_b200.set_config(metrabs_b200.Config(proc_side=args.side, precision=args.precision,
+                                                stride_test=getattr(args, 'stride', 32), depth=getattr(args, 'depth', 8)))
     ji = types.SimpleNamespace(names=[f'j{i}' for i in range(args.joints)], stick_figure_edges=[(0, 1)],
                                n_joints=args.joints)
-    model = Metrabs(torch.nn.Sequential(E.PreprocLayer(), E.EfficientNet(args.size).features), ji).eval()
+    if args.size == 'resnet50':
+        from metrabs_b200.backbones import resnet
+        backbone = resnet.resnet50()
+    elif args.size == 'mobilenetv3-small':
+        from metrabs_b200.backbones import mobilenet_v3
+        backbone = mobilenet_v3.mobilenet_v3_small()
+    else:
+        backbone = torch.nn.Sequential(E.PreprocLayer(), E.EfficientNet(args.size).features)
+    model = Metrabs(backbone, ji).eval()
     conditioned_random_init_(model, seed=0)
     return model.to(device) if device is not None else model
 
@@ -188,8 +202,12 @@ def cpu_reference_forward(args, n_crops, iters, warmup):
     torch.set_num_threads(best_thread_count())
     model = build_model(args, None)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    pcfg = port.PathConfig(proc_side=args.side)
-    spec = port.effnet_spec(NAMES[args.size])
+    pcfg = port.PathConfig(proc_side=args.side, stride_test=getattr(args, 'stride', 32), depth=getattr(args, 'depth', 8))
+    if args.size in ('resnet50', 'mobilenetv3-small'):
+        from oracle import port_tf_backbones as tfb
+        spec = tfb.ResNet50Spec(pcfg) if args.size == 'resnet50' else tfb.MobileNetV3SmallSpec(pcfg)
+    else:
+        spec = port.effnet_spec(NAMES[args.size])
     crops, k = synthetic(n_crops, args.side, 0)
     times = []
     with torch.inference_mode():
@@ -203,7 +221,7 @@ def cpu_reference_forward(args, n_crops, iters, warmup):
 
 
 def workload_name(args):
-    return (f'{NAMES[args.size]} {args.side}x{args.side} J={args.joints} D=8, {args.batch} crops/GPU/step '
+    return (f'{NAMES[args.size]} {args.side}x{args.side} J={args.joints} D={args.depth} stride={args.stride}, {args.batch} crops/GPU/step '
             f'(BASELINE.json metric: crops/sec, 256x256, EffNetV2-L, 24 joints)')
 
 
@@ -265,6 +283,14 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    graph = None
+    if args.graph and world == 1:
+        step()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            eng.forward(crops_d, k_d, out=out_d)
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -280,6 +306,18 @@ def run_b200(args):
     total_ms_all = sum(v['ms'] for v in prof_all.values())
 
     barrier()
+    graph_ms = None
+    if graph is not None:  # CUDA-graph replay of the same K steps (no per-kernel events inside): reported beside `value`
+        for _ in range(2):
+            graph.replay()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        g0.record()
+        for _ in range(args.steps):
+            graph.replay()
+        g1.record()
+        torch.cuda.synchronize()
+        graph_ms = g0.elapsed_time(g1)
     eng.profile_begin([dom_cls])
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -340,7 +378,8 @@ def run_b200(args):
                    'l2_policy': f'inputs larger than L2: {B * 3 * S * S * 4 / 1e6:.0f} MB of crops per step',
                    'backbone_gflop_per_crop': flops_crop / 1e9,
                    'tensor_util_of_peak': value / world * flops_crop / 1e12 / pk['tflops'],
-                   'peaks': pk['source']},
+                   'peaks': pk['source'],
+                   'cuda_graph_replay_crops_per_s': (world * B * args.steps / (graph_ms / 1e3)) if graph_ms else None},
         'e2e': {'value': e2e, 'unit': 'crops/s', 'h2d_bytes_per_step': B * 3 * S * S * 4 + B * 36,
                 'd2h_bytes_per_step': B * J * 3 * 4},
         'gpu_launches': launches,

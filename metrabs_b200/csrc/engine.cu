@@ -29,7 +29,7 @@ enum OpType { OP_STEM = 0, OP_CONV = 1, OP_DW = 2, OP_POOL = 3, OP_MAXPOOL = 4 }
 enum KClass { KC_STEM = 0, KC_IGEMM_SIMT = 1, KC_DWCONV = 2, KC_POOL = 3, KC_SE_FC = 4, KC_TC_GEMM = 5, KC_TC_CONV3 = 6,
               KC_HEAD_FUSED = 7, KC_HEAD_CONV_SIMT = 8, KC_SOFTARGMAX = 9, KC_RECON = 10, KC_OTHER = 11, KC_SE_SCALE = 12, KC_COUNT = 13 };
 const char* kKClassNames[KC_COUNT] = {"stem_conv_kernel", "conv_igemm_kernel", "dwconv_kernel", "pool_mean_kernel",
-                                      "se_fc(conv_igemm_kernel)", "tc_gemm_kernel", "tc_conv3x3_kernel",
+                                      "se_fc(conv_igemm_kernel)", "tc_conv_kernel", "tc_conv_kernel(unused)",
                                       "tc_head_softargmax_kernel", "head_conv(conv_igemm_kernel)",
                                       "softargmax_bhwn_kernel", "recon_pass1+2_kernel", "other", "se_scale_kernel"};
 enum { BUF_FEATURES = -2, BUF_NONE = -1, BUF_SMALL0 = 4 };  // 0..3 big activation buffers, 4..6 small [B,C]
@@ -169,7 +169,7 @@ struct Planner {
     f1.flops = 2.0 * cexp * csq_real;
     // K = cexp is long and M = batch is short: split K over CTAs; the ksplit partial slices [ksplit][B][csq] must fit
     // the small buffer (capacity >= cexp floats per crop)
-    f1.ksplit = std::max(1, std::min({8, cexp / 64, cexp / csq}));  // <= 8 slices: fc2 sums them on its A load
+    f1.ksplit = std::max(1, std::min({32, cexp / 64, cexp / csq}));
     h->ops.push_back(f1);
     const int f1_index = (int)h->ops.size() - 1;
     Op f2;
@@ -177,7 +177,7 @@ struct Planner {
     f2.Cin = csq; f2.Cout = cexp; f2.act = act2; f2.small_io = true; f2.pad_ok = true;
     f2.in_buf = BUF_SMALL0 + 1; f2.out_buf = BUF_SMALL0 + 2;
     f2.flops = 2.0 * cexp * csq_real;
-    if (f1.ksplit > 1) { f2.a_bias_from = f1_index; f2.a_act = act1; }
+    (void)f1_index;  // (fc2 summing the slices on its A load was measured slower than the tiny reduce kernel)
     h->ops.push_back(f2);
     max_small = std::max(max_small, cexp);
   }
@@ -639,7 +639,7 @@ int op_class(const Op& op) {
     default: break;
   }
   if (op.small_io) return KC_SE_FC;
-  if (op.tc.ready) return (op.R == 1 && op.stride == 1) ? KC_TC_GEMM : KC_TC_CONV3;
+  if (op.tc.ready) return KC_TC_GEMM;  // one class per kernel: every tensor-core conv/GEMM launch is tc_conv_kernel
   return KC_IGEMM_SIMT;
 }
 
@@ -657,7 +657,7 @@ double op_bytes(const mtb_handle* h, const Op& op, int B) {
 template <typename T>
 int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Workspace& ws, void* features,
              cudaStream_t st) {
-  if (op.type == OP_CONV && op.tc.ready && op.scale_buf != BUF_NONE && !(op.R == 1 && op.stride == 1) ) {
+  if (op.type == OP_CONV && op.tc.ready && op.scale_buf != BUF_NONE && !(tc_fuse_se() && op.R == 1 && op.stride == 1)) {
     // squeeze-excitation scale applied in place ahead of a tensor-core conv that cannot fuse it (1x1 stride-1 projections
     // apply it to the A tiles in shared memory inside tc_conv_kernel)
     void* x = buf_ptr(ws, op.in_buf, features);
@@ -723,15 +723,19 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
           p.a_splits = dw_pool_slices(h->ops[op.pool_src - 1]);
           p.a_split_stride = (size_t)B * op.Cin;
         }
-        if (op.ksplit > 1) p.ksplit = op.ksplit;  // split-K: raw partial slices [ksplit][B][Cout]; the consumer (fc2) sums them
-        if (op.a_bias_from >= 0) {               // fc2: input = fc1's slices; + fc1 bias, activation, all on the A load
-          const Op& prod = h->ops[op.a_bias_from];
-          p.a_bias = prod.d_bias;
-          p.a_act = op.a_act;
-          p.a_splits = prod.ksplit;
-          p.a_split_stride = (size_t)B * prod.Cout;
+        float* final_out = (float*)p.out;
+        if (op.ksplit > 1) {  // split-K partial slices go to the (still unused) scale buffer, then one tiny reduce kernel
+          p.ksplit = op.ksplit;
+          p.out = buf_ptr(ws, BUF_SMALL0 + 2, features);
         }
         cudaError_t e = launch_conv_igemm<float, float>(p, st);
+        if (e == cudaSuccess && op.ksplit > 1) {
+          const int n = B * op.Cout;
+          launch_k(se_reduce_kernel, dim3((n + 255) / 256), dim3(256), 0, st, (const float*)p.out, (const float*)op.d_bias, final_out, n,
+                   op.Cout, op.ksplit, op.act);
+          h->launches++;
+          e = cudaGetLastError();
+        }
         if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "launch %s: %s", op.name.c_str(), cudaGetErrorString(e));
       } else if (op.tc.ready) {
         const char* e = tc_conv_launch(op.tc, p, op.res_first, st);

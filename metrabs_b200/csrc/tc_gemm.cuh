@@ -767,6 +767,15 @@ struct TcWeights {
   mutable int cached_B = -1, cached_bn = 0;
 };
 
+inline bool tc_fuse_se() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTB_FUSE_SE");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 inline bool tc_patch_disabled() {  // MTB_DISABLE_PATCH=1: 3x3 convs fall back to the per-tap TMA mode (A/B testing)
   static int v = -1;
   if (v < 0) {
@@ -888,7 +897,11 @@ inline const char* tc_conv_dispatch(int act, int res_mode, int grid, const CUten
 
 inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool res_first, cudaStream_t st) {
   TcConvParams q;
-  q.a_scale = (p.R == 1 && p.stride == 1) ? p.a_scale : nullptr;  // fused in shared memory (mode 0); else pre-scaled
+  // Squeeze-excitation scale fused into the A tiles in shared memory (scaler warps 11-12): implemented and correct, but
+  // MEASURED SLOWER than the separate in-place pass (projection GEMMs 1.05 -> 2.5 ms per 24 launches at 128 crops: two
+  // warps cannot rescale a 16 KB tile within a k-block period, and the extra hand-off sits on the pipeline's critical
+  // path), so it is opt-in (MTB_FUSE_SE=1) and the default keeps se_scale_kernel.
+  q.a_scale = (tc_fuse_se() && p.R == 1 && p.stride == 1) ? p.a_scale : nullptr;
   q.a_scale_P = p.Hin * p.Win;
   q.res = p.res; q.bias = w.d_bias;
   const int bk0 = p.Cin <= 32 ? 32 : 64;  // 64B-swizzled half-width stages only when they do not add k-blocks

@@ -72,6 +72,18 @@ def launch_list(src, out_csv, out_md):
         f.write(f"\ntotal {tot / 1e3:.2f} ms over {int(sum(a['n'] for a in per.values()))} launches "
                 f"(ncu serialises launches and runs them cold-cache: compare SHARES, not absolutes)\n")
     print('wrote', out_csv, out_md)
+    # DRAM traffic per launch of each kernel FAMILY (template arguments stripped), read by bench.py for roofline.traffic
+    fam = collections.defaultdict(lambda: [0, 0.0])
+    for k, a in per.items():
+        f_ = k.split('<')[0]
+        fam[f_][0] += a['n']
+        fam[f_][1] += a.get('dram', 0.0)
+    traffic = {k: v[1] / v[0] for k, v in fam.items() if v[1] > 0}
+    if traffic:
+        with open(os.path.join(P, 'traffic.json'), 'w') as f:
+            json.dump(dict(source=f'{out_csv}: mean dram__bytes_read.sum + dram__bytes_write.sum per launch over the bench step '
+                                  f'(EfficientNetV2-L@256, 256 crops)', **traffic), f, indent=1)
+        print('wrote traffic.json', {k: round(v / 1e6, 1) for k, v in traffic.items()})
     return per
 
 

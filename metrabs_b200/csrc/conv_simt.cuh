@@ -287,11 +287,11 @@ __device__ __forceinline__ float fast_act(float x) {  // compile-time activation
   }
 }
 
-template <int STRIDE, int ACT>
-__global__ void __launch_bounds__(256) dwconv3x3_pool_bf16_kernel(ConvParams p, float* __restrict__ pooled) {
+template <int STRIDE, int ACT, int OW = 4>
+__global__ void __launch_bounds__(256, OW == 2 ? 3 : 2) dwconv3x3_pool_bf16_kernel(ConvParams p, float* __restrict__ pooled) {
   pdl_trigger();
   pdl_wait();
-  constexpr int OW = 4;                          // outputs per thread along W
+  // OW outputs per thread along W
   constexpr int NCOL = (OW - 1) * STRIDE + 3;    // input columns feeding them
   const __nv_bfloat16* __restrict__ in = reinterpret_cast<const __nv_bfloat16*>(p.in);
   __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(p.out);

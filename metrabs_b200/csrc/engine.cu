@@ -625,8 +625,9 @@ bool dw_strip_eligible(const Op& op) {
 }
 
 // number of partial pooling slices the fused depthwise kernel writes (= its gridDim.y)
+constexpr int kDwOW = 2;  // outputs per thread along W in dwconv3x3_pool_bf16_kernel (2: 3 CTAs/SM; 4: 2 CTAs/SM, fewer loads)
 int dw_pool_slices(const Op& dw) {
-  const int strips = dw.Hout * ((dw.Wout + 3) / 4);
+  const int strips = dw.Hout * ((dw.Wout + kDwOW - 1) / kDwOW);
   return std::min((strips + 7) / 8, kPoolSlices);
 }
 
@@ -702,14 +703,14 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
           float* pooled = op.fused_pool ? (float*)buf_ptr(ws, BUF_SMALL0, features) : nullptr;
           dim3 grid((op.Cout / 8 + 31) / 32, dw_pool_slices(op), B), block(32, 8);
           if (op.act == ACT_SILU) {
-            if (op.stride == 1) launch_k(dwconv3x3_pool_bf16_kernel<1, ACT_SILU>, dim3(grid), dim3(block), 0, st, p, pooled);
-            else launch_k(dwconv3x3_pool_bf16_kernel<2, ACT_SILU>, dim3(grid), dim3(block), 0, st, p, pooled);
+            if (op.stride == 1) launch_k(dwconv3x3_pool_bf16_kernel<1, ACT_SILU, kDwOW>, dim3(grid), dim3(block), 0, st, p, pooled);
+            else launch_k(dwconv3x3_pool_bf16_kernel<2, ACT_SILU, kDwOW>, dim3(grid), dim3(block), 0, st, p, pooled);
           } else if (op.act == ACT_RELU) {
-            if (op.stride == 1) launch_k(dwconv3x3_pool_bf16_kernel<1, ACT_RELU>, dim3(grid), dim3(block), 0, st, p, pooled);
-            else launch_k(dwconv3x3_pool_bf16_kernel<2, ACT_RELU>, dim3(grid), dim3(block), 0, st, p, pooled);
+            if (op.stride == 1) launch_k(dwconv3x3_pool_bf16_kernel<1, ACT_RELU, kDwOW>, dim3(grid), dim3(block), 0, st, p, pooled);
+            else launch_k(dwconv3x3_pool_bf16_kernel<2, ACT_RELU, kDwOW>, dim3(grid), dim3(block), 0, st, p, pooled);
           } else {
-            if (op.stride == 1) launch_k(dwconv3x3_pool_bf16_kernel<1, ACT_HSWISH>, dim3(grid), dim3(block), 0, st, p, pooled);
-            else launch_k(dwconv3x3_pool_bf16_kernel<2, ACT_HSWISH>, dim3(grid), dim3(block), 0, st, p, pooled);
+            if (op.stride == 1) launch_k(dwconv3x3_pool_bf16_kernel<1, ACT_HSWISH, kDwOW>, dim3(grid), dim3(block), 0, st, p, pooled);
+            else launch_k(dwconv3x3_pool_bf16_kernel<2, ACT_HSWISH, kDwOW>, dim3(grid), dim3(block), 0, st, p, pooled);
           }
         } else {
           size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);

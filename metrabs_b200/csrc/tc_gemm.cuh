@@ -323,7 +323,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // warp-uniform by construction (shuffle from lane 0): lets the compiler keep the accumulator address in a uniform
+  // register instead of re-broadcasting it with an ELECT / R2UR loop in front of every tcgen05.mma
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   pdl_trigger();  // the next kernel may start its own prologue on SMs this grid has left
   pdl_wait();     // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 

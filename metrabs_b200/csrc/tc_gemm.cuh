@@ -201,6 +201,8 @@ struct TcConvParams {
   int M;        // mode 0: number of rows
   int Cout, Cin;
   int bn;       // N-tile stride, multiple of 64 (the MMA N of a tile is its valid width rounded up to 16)
+  int b_rows;   // rows of the weight TMA box: bn, or Cout rounded up to 16 when one N tile covers Cout (no zero-fill rows)
+  int npatch;   // mode 2: resident patch buffers (2..4)
   int n_tiles, m_tiles, kchunks, taps;
   int nstages, stage_stride;  // operand ring depth and stage size in bytes (A at +0, B at +a_bytes)
   int patch_off, patch_bytes; // mode 2: the two resident patches sit at the tail of the ring region
@@ -210,6 +212,7 @@ struct TcConvParams {
   int debug;    // MTB_TC_DEBUG bits (perf experiments only): 1 = skip the TMA store, 2 = skip the epilogue math + staging,
                 // 4 = skip the residual load, 8 = skip the patch loads (mode 2)
   int bk;       // K elements per ring stage (host-side copy of the BK template argument)
+  int trace_cta; // the CTA that writes the clock64 trace
 };
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -271,6 +274,75 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
   return d;
 }
 
+// variants taking shared-window byte addresses (the issuer loops keep barrier / tile addresses as plain 32-bit offsets)
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait_a(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz
+      printf("metrabs_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait_a(bar, parity)) mbar_wait_slow(bar, parity);
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_a(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// keeps a loop-invariant value in a register (opaque to the optimiser, so it is not rematerialised from the constant bank)
+__device__ __forceinline__ int pin(int v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ uint32_t pin(uint32_t v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+// one lane of a converged warp (elect.sync): the issue idiom that keeps operands in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred px;\nelect.sync _|px, 0xffffffff;\nselp.u32 %0, 1, 0, px;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+// persistent tile walk t = first, first + step, ...: (m_blk, n_blk) = (t / n_tiles, t % n_tiles) without a division per tile
+struct TileWalk {
+  int m_blk, n_blk, dm, dn, n_tiles;
+  __device__ __forceinline__ TileWalk(int first, int step, int nt) : m_blk(first / nt), n_blk(first % nt), dm(step / nt), dn(step % nt), n_tiles(nt) {}
+  __device__ __forceinline__ void next() {
+    m_blk += dm;
+    n_blk += dn;
+    if (n_blk >= n_tiles) { n_blk -= n_tiles; ++m_blk; }
+  }
+};
+
 // ACT: epilogue activation; RES: 0 no residual, 1 residual added AFTER the activation (EfficientNet), 2 BEFORE (ResNet);
 // BK: K elements per ring stage: 64 (128B-swizzled rows) or 32 (64B-swizzled rows).
 //
@@ -282,7 +354,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
 //   warp 9     B-operand (weights) TMA producer
 //   warp 10    TMEM allocator + single-thread tcgen05.mma issuer
 //   warp 11    second patch loader (mode 2)
-template <int ACT, int RES, int BK>
+template <int ACT, int RES, int BK, bool PATCH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const TcConvParams p) {
@@ -293,13 +365,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty = bars + TCV_MAX_STAGES;            // [8]
   uint64_t* tmem_full = bars + 2 * TCV_MAX_STAGES;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;               // [2]
-  uint64_t* patch_full = tmem_empty + 2;              // [2]
-  uint64_t* patch_empty = patch_full + 2;             // [2]
-  uint64_t* scaled = patch_empty + 2;                 // [12] mode 0 + SE: A tile of the stage multiplied by the SE scale
+  uint64_t* patch_full = tmem_empty + 2;              // [4]
+  uint64_t* patch_empty = patch_full + 4;             // [4]
+  uint64_t* scaled = patch_empty + 4;                 // [12] mode 0 + SE: A tile of the stage multiplied by the SE scale
   uint32_t* tmem_slot = (uint32_t*)(scaled + TCV_MAX_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool patch_mode = p.mode == 2;
+  constexpr bool patch_mode = PATCH;  // compile-time: each kernel carries one operand pipeline (smaller hot code)
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -314,6 +386,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], TCV_EPI_WARPS);
+    }
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&patch_full[i], p.b_resident ? 3 : 2);   // one arrive per loader warp
       mbar_init(&patch_empty[i], 1);  // tcgen05.commit
     }
@@ -329,138 +403,229 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   pdl_trigger();  // the next kernel may start its own prologue on SMs this grid has left
   pdl_wait();     // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
+  long long cta_t0 = 0;
+  unsigned long long cta_g0 = 0;
+  if (p.trace && threadIdx.x == 0) {
+    cta_t0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_g0));
+  }
   const int total_tiles = p.m_tiles * p.n_tiles;
   const uint32_t a_bytes = patch_mode ? 0u : (uint32_t)TC_BM * BK * 2;
-  const uint32_t b_bytes = (uint32_t)p.bn * BK * 2;
+  const uint32_t b_bytes = (uint32_t)p.b_rows * BK * 2;
   const int nstages = p.nstages;
   const int planes = p.kchunks * (BK / 8);  // 16-byte channel chunks per pixel in the patch (zero beyond Cin/8)
 
-  if (warp == 8) {
-    if (!patch_mode) {
-      // ===== A-operand TMA producer =====
-      if (lane == 0) {
-        int stage = 0, tr = 0;
-        uint32_t phase = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-          const int m_blk = t / p.n_tiles;
-          int b = 0, ih0 = 0, iw0 = 0;
-          if (p.mode == 1) {
-            int tw = m_blk % p.tiles_w;
-            int th = (m_blk / p.tiles_w) % p.tiles_h;
-            b = m_blk / (p.tiles_w * p.tiles_h);
-            ih0 = th * TC_TILE_H * p.stride - p.pad_t;
-            iw0 = tw * TC_TILE_W * p.stride - p.pad_l;
+  // The three single-issuer roles run with their whole warp CONVERGED and elect one lane per issue (the CUTLASS idiom):
+  // operands stay in uniform registers.  Under `if (lane == 0)` the compiler had to assume divergence, moved every
+  // descriptor / coordinate through R2UR and wrapped each UTCHMMA / UTMALDG in an ELECT loop: ~100 dependent instructions
+  // (~570 cycles, measured with the in-kernel trace and ncu's source view) per k-block whatever the MMA shape.
+  const bool trace_on = p.trace != nullptr && (int)blockIdx.x == p.trace_cta;
+  // loop-invariant kernel parameters of the issuer loops, pinned in registers (the compiler otherwise re-reads them from
+  // the constant bank inside the loops: each LDC sits on the single-warp critical path)
+  const int num_kb = pin(p.taps * p.kchunks);
+  const uint32_t stage_stride = pin((uint32_t)p.stage_stride);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+  if (warp == 8 && !patch_mode) {
+    // ===== A-operand TMA producer =====
+    uint32_t stage = 0, phase = 0, sa = smem_base;
+    int tr = 0;
+    const int kchunks = pin(p.kchunks);
+    TileWalk tw_(blockIdx.x, gridDim.x, p.n_tiles);
+    if (p.mode == 0) {
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
+        const int row0 = tw_.m_blk * TC_BM;
+#pragma unroll 1
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx_a(full0 + stage * 8, a_bytes);
+            tma_load_2d_a(sa, &tmA, full0 + stage * 8, kc * BK, row0);
+            if (trace_on && tr < 256) p.trace[tr++] = clock64();
           }
-          const int row0 = m_blk * TC_BM;
-          for (int r = 0; r < p.R; ++r)
-            for (int s_ = 0; s_ < p.S; ++s_)
-              for (int kc = 0; kc < p.kchunks; ++kc) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                uint8_t* sa = smem + stage * p.stage_stride;
-                mbar_expect_tx(&full[stage], a_bytes);
-                if (p.mode == 0) tma_load_2d(sa, &tmA, &full[stage], kc * BK, row0);
-                else tma_load_4d(sa, &tmA, &full[stage], kc * BK, iw0 + s_ * p.dil, ih0 + r * p.dil, b);
-                if (p.trace && blockIdx.x == 0 && tr < 256) p.trace[tr++] = clock64();
-                if (++stage == nstages) { stage = 0; phase ^= 1; }
-              }
+          __syncwarp();
+          sa += stage_stride;
+          if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; sa = smem_base; }
         }
+      }
+    } else {
+      const int R = pin(p.R), S = pin(p.S), dil = pin(p.dil);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
+        const int m_blk = tw_.m_blk;
+        const int tw = m_blk % p.tiles_w;
+        const int th = (m_blk / p.tiles_w) % p.tiles_h;
+        const int b = m_blk / (p.tiles_w * p.tiles_h);
+        const int ih0 = th * TC_TILE_H * p.stride - p.pad_t;
+        const int iw0 = tw * TC_TILE_W * p.stride - p.pad_l;
+        for (int r = 0; r < R; ++r)
+          for (int s_ = 0; s_ < S; ++s_)
+            for (int kc = 0; kc < kchunks; ++kc) {
+              mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+              if (elect_one()) {
+                mbar_expect_tx_a(full0 + stage * 8, a_bytes);
+                tma_load_4d_a(sa, &tmA, full0 + stage * 8, kc * BK, iw0 + s_ * dil, ih0 + r * dil, b);
+                if (trace_on && tr < 256) p.trace[tr++] = clock64();
+              }
+              __syncwarp();
+              sa += stage_stride;
+              if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; sa = smem_base; }
+            }
       }
     }
   } else if (warp == 9) {
     // ===== B-operand (weights) TMA producer =====
-    if (lane == 0 && p.b_resident) {
+    if (p.b_resident) {
       // the whole weight panel stays in the ring: slot kb <- k-block kb, loaded once
-      int kb = 0;
-      for (int tap = 0; tap < p.taps; ++tap)
-        for (int kc = 0; kc < p.kchunks; ++kc, ++kb) {
-          mbar_expect_tx(&full[kb], b_bytes);
-          tma_load_2d(smem + kb * p.stage_stride, &tmB, &full[kb], tap * p.Cin + kc * BK, 0);
-        }
-    } else if (lane == 0) {
-      int stage = 0, tr = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int n_blk = t % p.n_tiles;
-        const int nrow = n_blk * p.bn;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          int col = tap * p.Cin;
-          for (int kc = 0; kc < p.kchunks; ++kc, col += BK) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t* sb = smem + stage * p.stage_stride + a_bytes;
-            mbar_expect_tx(&full[stage], b_bytes);
-            tma_load_2d(sb, &tmB, &full[stage], col, nrow);
-            if (++stage == nstages) { stage = 0; phase ^= 1; }
+      if (lane == 0) {
+        int kb = 0;
+        for (int tap = 0; tap < p.taps; ++tap)
+          for (int kc = 0; kc < p.kchunks; ++kc, ++kb) {
+            mbar_expect_tx(&full[kb], b_bytes);
+            tma_load_2d(smem + kb * p.stage_stride, &tmB, &full[kb], tap * p.Cin + kc * BK, 0);
+          }
+      }
+    } else {
+      uint32_t stage = 0, phase = 0, sb = smem_base + a_bytes;
+      const int taps = pin(p.taps), kchunks = pin(p.kchunks), Cin = pin(p.Cin), bn = pin(p.bn);
+      TileWalk tw_(blockIdx.x, gridDim.x, p.n_tiles);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
+        const int nrow = tw_.n_blk * bn;
+        for (int tap = 0; tap < taps; ++tap) {
+          int col = tap * Cin;
+#pragma unroll 1
+          for (int kc = 0; kc < kchunks; ++kc, col += BK) {
+            mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx_a(full0 + stage * 8, b_bytes);
+              tma_load_2d_a(sb, &tmB, full0 + stage * 8, col, nrow);
+            }
+            __syncwarp();
+            sb += stage_stride;
+            if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; sb = smem_base + a_bytes; }
           }
         }
       }
     }
   } else if (warp == 10) {
-    // ===== MMA issuer (one elected thread) =====
-    if (lane == 0) {
-      int stage = 0, tr = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      int pb = 0;
-      uint32_t pb_phase = 0;
-      const uint32_t smem_a0 = smem_u32(smem);
-      // constant high words of the operand descriptors: SBO | version 1 | layout type
-      const uint32_t hi_sw = (uint32_t)((8 * BK * 2) >> 4) | (1u << 14) | ((BK == 64 ? 2u : 4u) << 29);
-      const uint32_t hi_patch = (uint32_t)((TC_PATCH_W * 16) >> 4) | (1u << 14);
-      const uint32_t lbo_patch = (uint32_t)(TC_PLANE_BYTES >> 4) << 16;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int n_blk = t % p.n_tiles;
-        const int n_valid = min(p.bn, p.Cout - n_blk * p.bn);
+    // ===== MMA issuer (whole warp walks the pipeline, one elected lane issues) =====
+    int tr = 0;
+    uint32_t acc = 0, acc_phase = 0, pb = 0, pb_phase = 0;
+    // constant high words of the operand descriptors: SBO | version 1 | layout type
+    constexpr uint32_t hi_sw = (uint32_t)((8 * BK * 2) >> 4) | (1u << 14) | ((BK == 64 ? 2u : 4u) << 29);
+    constexpr uint32_t hi_patch = (uint32_t)((TC_PATCH_W * 16) >> 4) | (1u << 14);
+    constexpr uint32_t lbo_patch = (uint32_t)(TC_PLANE_BYTES >> 4) << 16;
+    constexpr uint32_t plane16 = TC_PLANE_BYTES >> 4;
+    const uint32_t stride16 = stage_stride >> 4;
+    const uint32_t base16 = smem_base >> 4;   // shared-window offsets stay below 2^18: the 14-bit address field never wraps
+    const uint32_t b_off16 = a_bytes >> 4;
+    const uint32_t fullw0 = p.a_scale ? smem_u32(scaled) : full0;
+    const uint32_t tmem_full0 = smem_u32(tmem_full), tmem_empty0 = smem_u32(tmem_empty);
+    const uint32_t patch_full0 = smem_u32(patch_full), patch_empty0 = smem_u32(patch_empty);
+    const int bn = pin(p.bn), Cout = pin(p.Cout);
+    TileWalk tw_(blockIdx.x, gridDim.x, p.n_tiles);
+    if (!patch_mode) {
+      // ---- modes 0 / 1: both operands stream through the ring; the k-block loop does not depend on the tap ----
+      uint32_t stage = 0, phase = 0, a16 = base16;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
+        const int n_valid = min(bn, Cout - tw_.n_blk * bn);
         const uint32_t idesc = umma_idesc_bf16((n_valid + 15) & ~15);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        mbar_wait_a(tmem_empty0 + acc * 8, acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_MAX_BN;
-        uint32_t patch_addr = 0;
-        if (patch_mode) {
-          mbar_wait(&patch_full[pb], pb_phase);
+        const uint32_t d_tmem = tmem_base + acc * TC_MAX_BN;
+#pragma unroll 1
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait_a(fullw0 + stage * 8, phase);
           tc_fence_after();
-          patch_addr = smem_a0 + p.patch_off + pb * p.patch_bytes;
-        }
-        uint32_t first = 0;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          // mode 2, tap (r,s): the same patch, start shifted by r rows and s pixels; 8-row groups = patch rows (SBO), the
-          // two 16-byte K chunks of one MMA are one plane apart (LBO)
-          const uint32_t tap_off = patch_mode ? (uint32_t)((tap / 3) * TC_PATCH_W + (tap % 3)) * 16 : 0u;
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            if (!p.b_resident || t == (int)blockIdx.x) {
-              mbar_wait(p.a_scale ? &scaled[stage] : &full[stage], phase);
-              tc_fence_after();
-            }
-            if (p.trace && blockIdx.x == 0 && tr < 256) p.trace[256 + tr++] = clock64();
-            const uint32_t sa = smem_a0 + stage * p.stage_stride;
-            const uint32_t sb_lo = (sa + a_bytes) >> 4;
-            if (patch_mode) {
-              const uint32_t a_lo = (patch_addr + (uint32_t)(kc * (BK / 8)) * TC_PLANE_BYTES + tap_off) >> 4;
+          if (elect_one()) {
+            if (trace_on && tr < 256) p.trace[256 + tr++] = clock64();
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                umma_bf16(d_tmem, make_desc(((a_lo + (uint32_t)(2 * k) * (TC_PLANE_BYTES >> 4)) & 0x3FFF) | lbo_patch, hi_patch),
-                          make_desc((sb_lo + 2 * k) & 0x3FFF, hi_sw), idesc, first | (uint32_t)k);
-              }
-            } else {
-              const uint32_t sa_lo = sa >> 4;
-#pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                umma_bf16(d_tmem, make_desc((sa_lo + 2 * k) & 0x3FFF, hi_sw), make_desc((sb_lo + 2 * k) & 0x3FFF, hi_sw), idesc,
-                          first | (uint32_t)k);
-              }
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(d_tmem, make_desc(a16 + 2 * k, hi_sw), make_desc(a16 + b_off16 + 2 * k, hi_sw), idesc, (uint32_t)(kb | k));
+            umma_commit_a(empty0 + stage * 8);  // frees the ring slot once these MMAs have read it
+            if (kb == num_kb - 1) {
+              if (trace_on && tr < 256) p.trace[256 + tr++] = -clock64();  // (negative) all MMAs of the tile issued
+              umma_commit_a(tmem_full0 + acc * 8);  // accumulator complete -> epilogue
             }
-            first = 1;
-            if (!p.b_resident) umma_commit(&empty[stage]);  // frees the ring slot once these MMAs have read it
-            if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          a16 += stride16;
+          if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; a16 = base16; }
         }
-        if (p.b_resident) { stage = 0; phase = 0; }  // resident weights: slot kb <-> k-block kb for every tile
-        if (p.trace && blockIdx.x == 0 && tr < 256) p.trace[256 + tr++] = -clock64();  // (negative) all MMAs of the tile issued
-        if (patch_mode) {
-          umma_commit(&patch_empty[pb]);  // the patch may be overwritten once this tile's MMAs have read it
-          if (++pb == 2) { pb = 0; pb_phase ^= 1; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else {
+      // ---- mode 2: A = the resident (tile + halo) patch.  Tap (r,s): the same patch, start shifted by r rows and s pixels;
+      //      8-row groups = patch rows (SBO), the two 16-byte K chunks of one MMA are one plane apart (LBO) ----
+      const bool b_res = p.b_resident != 0;
+      const int kchunks = pin(p.kchunks);
+      const uint32_t patch_off16 = (uint32_t)p.patch_off >> 4, patch_bytes16 = (uint32_t)p.patch_bytes >> 4;
+      uint32_t stage = 0, phase = 0, b16 = base16;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
+        const int n_valid = min(bn, Cout - tw_.n_blk * bn);
+        const uint32_t idesc = umma_idesc_bf16((n_valid + 15) & ~15);
+        mbar_wait_a(tmem_empty0 + acc * 8, acc_phase ^ 1);
+        mbar_wait_a(patch_full0 + pb * 8, pb_phase);
+        if (b_res && t == (int)blockIdx.x)
+          for (int kb = 0; kb < num_kb; ++kb) mbar_wait_a(full0 + kb * 8, 0);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TC_MAX_BN;
+        const uint32_t patch16 = base16 + patch_off16 + pb * patch_bytes16;
+        if (b_res) {
+          // weights resident (slot kb <-> k-block kb): nothing to wait for inside the tile, one elected lane issues it all
+          if (elect_one()) {
+            if (trace_on && tr < 256) p.trace[256 + tr++] = clock64();
+            uint32_t bk16 = base16, first = 0;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              uint32_t a_lo = patch16 + (uint32_t)((tap / 3) * TC_PATCH_W + (tap % 3));
+#pragma unroll 1
+              for (int kc = 0; kc < kchunks; ++kc) {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_bf16(d_tmem, make_desc((a_lo + (uint32_t)(2 * k) * plane16) | lbo_patch, hi_patch), make_desc(bk16 + 2 * k, hi_sw),
+                            idesc, first | (uint32_t)k);
+                first = 1;
+                a_lo += (BK / 8) * plane16;
+                bk16 += stride16;
+              }
+            }
+            if (trace_on && tr < 256) p.trace[256 + tr++] = -clock64();
+            umma_commit_a(patch_empty0 + pb * 8);  // the patch may be overwritten once this tile's MMAs have read it
+            umma_commit_a(tmem_full0 + acc * 8);    // accumulator complete -> epilogue
+          }
+          __syncwarp();
+        } else {
+          uint32_t first = 0;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            uint32_t a_lo = patch16 + (uint32_t)((tap / 3) * TC_PATCH_W + (tap % 3));
+#pragma unroll 1
+            for (int kc = 0; kc < kchunks; ++kc) {
+              mbar_wait_a(full0 + stage * 8, phase);
+              tc_fence_after();
+              if (elect_one()) {
+                if (trace_on && tr < 256) p.trace[256 + tr++] = clock64();
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_bf16(d_tmem, make_desc((a_lo + (uint32_t)(2 * k) * plane16) | lbo_patch, hi_patch), make_desc(b16 + 2 * k, hi_sw),
+                            idesc, first | (uint32_t)k);
+                umma_commit_a(empty0 + stage * 8);
+              }
+              __syncwarp();
+              first = 1;
+              a_lo += (BK / 8) * plane16;
+              b16 += stride16;
+              if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; b16 = base16; }
+            }
+          }
+          if (elect_one()) {
+            if (trace_on && tr < 256) p.trace[256 + tr++] = -clock64();
+            umma_commit_a(patch_empty0 + pb * 8);
+            umma_commit_a(tmem_full0 + acc * 8);
+          }
+          __syncwarp();
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++pb == (uint32_t)p.npatch) { pb = 0; pb_phase ^= 1; }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -483,7 +648,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         srow[h] = p.a_scale + (size_t)(rok[h] ? m / p.a_scale_P : 0) * p.Cin;
       }
       for (int kc = 0; kc < p.kchunks; ++kc) {
-        mbar_wait(&full[stage], phase);
+        mbar_wait_a(smem_u32(&full[stage]), phase);
         uint8_t* sa = smem + stage * p.stage_stride;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -510,7 +675,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             *reinterpret_cast<uint4*>(rowp + pos * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
           }
         }
-        fence_proxy_async();
+        if (!(p.debug & 256)) fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&scaled[stage]);
         if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -525,7 +690,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const __nv_bfloat16* __restrict__ in = (const __nv_bfloat16*)p.res_in;
     const int real_planes = p.Cin >> 3;
     const int items = TC_PATCH_H * TC_PATCH_W * planes;
-    int pb = 0, ltr = 0;
+    // two tiles of copies in flight per loader warp: tile t+1 is issued before tile t is waited for and handed over
+    int pb = 0, pb_sig = 0, pending = 0, ltr = 0;
     uint32_t pb_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int m_blk = t / p.n_tiles;
@@ -533,10 +699,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int th = (m_blk / p.tiles_w) % p.tiles_h;
       const int b = m_blk / (p.tiles_w * p.tiles_h);
       const int ih0 = th * TC_PT_H - p.pad_t, iw0 = tw * TC_PT_W - p.pad_l;
-      mbar_wait(&patch_empty[pb], pb_phase ^ 1);
-      if (p.trace && blockIdx.x == 0 && warp == 8 && lane == 0 && ltr < 256) p.trace[ltr++] = clock64();  // patch slot free
+      uint32_t slot_free = 1;
+      if (pending) {  // warp-uniform poll (lane 0 decides)
+        slot_free = lane == 0 ? (uint32_t)mbar_try_wait(&patch_empty[pb], pb_phase ^ 1) : 0u;
+        slot_free = __shfl_sync(0xffffffffu, slot_free, 0);
+      }
+      if (!slot_free) {
+        // the next buffer is still being read: hand the tile in flight over first instead of holding it back
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (!(p.debug & 256)) fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&patch_full[pb_sig]);
+        if (++pb_sig == p.npatch) pb_sig = 0;
+        pending = 0;
+      }
+      mbar_wait_a(smem_u32(&patch_empty[pb]), pb_phase ^ 1);
+      if (p.trace && (int)blockIdx.x == p.trace_cta && warp == 8 && lane == 0 && ltr < 256) p.trace[ltr++] = clock64();  // patch slot free
       uint8_t* patch = smem + p.patch_off + pb * p.patch_bytes;
-      for (int i = lt; i < items; i += nload) {
+      for (int i = lt; i < items && !(p.debug & 64); i += nload) {
         const int j = i % planes, pix = i / planes;
         const int ph = pix / TC_PATCH_W, pw = pix - ph * TC_PATCH_W;
         const int ih = ih0 + ph, iw = iw0 + pw;
@@ -544,12 +724,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const __nv_bfloat16* src = ok ? in + ((size_t)(b * p.Hin + ih) * p.Win + iw) * p.Cin + j * 8 : in;
         cp_async_16(patch + j * TC_PLANE_BYTES + pix * 16, src, ok ? 16u : 0u);
       }
-      cp_async_wait_all();
-      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (++pb == p.npatch) { pb = 0; pb_phase ^= 1; }
+      if (++pending == 2) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");  // the older of the two tiles has landed
+        if (!(p.debug & 256)) fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&patch_full[pb_sig]);
+        if (p.trace && (int)blockIdx.x == p.trace_cta && warp == 8 && lane == 0 && ltr < 256) p.trace[ltr++] = clock64();  // patch staged
+        if (++pb_sig == p.npatch) pb_sig = 0;
+        --pending;
+      }
+    }
+    if (pending) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (!(p.debug & 256)) fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&patch_full[pb]);
-      if (p.trace && blockIdx.x == 0 && warp == 8 && lane == 0 && ltr < 256) p.trace[ltr++] = clock64();  // patch staged
-      if (++pb == 2) { pb = 0; pb_phase ^= 1; }
+      if (lane == 0) mbar_arrive(&patch_full[pb_sig]);
     }
   }
   if (warp < TCV_EPI_WARPS) {
@@ -581,14 +772,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         valid = oh < p.Hout && ow < p.Wout;
         off = ((size_t)(b * p.Hout + oh) * p.Wout + ow) * p.Cout;
       }
-      mbar_wait(&tmem_full[acc], acc_phase);
+      mbar_wait_a(smem_u32(&tmem_full[acc]), acc_phase);
       tc_fence_after();
-      if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && etr < 256) p.trace[512 + etr++] = clock64();
+      if (p.trace && (int)blockIdx.x == p.trace_cta && threadIdx.x == 0 && etr < 256) p.trace[512 + etr++] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_MAX_BN;
       const int nchunks = (n_valid + 63) >> 6;
       bool released = false;
       // two warp groups (par 0 / 1) alternate the 64-column chunks; one-chunk tiles alternate between the groups tile by tile
-      for (int ch = par ^ (nchunks == 1 ? (tile_i & 1) : 0); ch < nchunks; ch += 2) {
+      for (int ch = par ^ (nchunks == 1 ? (tile_i & 1) : 0); ch < nchunks && !(p.debug & 128); ch += 2) {
         const int c0 = ch * 64;
         const int ncols = min(64, n_valid - c0);  // multiple of 8
         // bias of the chunk -> this warp's staging (64 floats), broadcast-read below
@@ -656,7 +847,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             *reinterpret_cast<uint4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = ov;
           }
         }
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        if (!(p.debug & 256)) fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
         if (lane == 0 && !(p.debug & 1)) {
           if (p.mode == 0) tma_store_2d(&tmO, slab, n0 + c0, m_blk * TC_BM + q * 32);
@@ -670,7 +861,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       }
-      if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && etr < 256) p.trace[512 + etr++] = clock64();
+      if (p.trace && (int)blockIdx.x == p.trace_cta && threadIdx.x == 0 && etr < 256) p.trace[512 + etr++] = clock64();
       ++tile_i;
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -678,6 +869,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (p.trace && threadIdx.x == 0) {  // per-CTA totals: cycles and nanoseconds from start to drained pipeline
+    unsigned long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    p.trace[768 + 2 * blockIdx.x] = clock64() - cta_t0;
+    p.trace[768 + 2 * blockIdx.x + 1] = (long long)(g1 - cta_g0);
+  }
   if (warp == 10) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -857,23 +1054,26 @@ inline int tc_pick_bn(int cout, int m_tiles, int num_kb, int bk) {
   return best;
 }
 
-template <int ACT, int RES, int BK>
+template <int ACT, int RES, int BK, bool PATCH>
 inline const char* tc_conv_launch_k(int grid, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const TcConvParams& q,
                                     cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_conv_kernel<ACT, RES, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCV_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_conv_kernel<ACT, RES, BK, PATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCV_SMEM_BYTES) !=
+        cudaSuccess)
       return "cannot raise dynamic shared memory for tc_conv_kernel";
     attr_set = true;
   }
-  launch_k(tc_conv_kernel<ACT, RES, BK>, dim3(grid), dim3(TC_THREADS), TCV_SMEM_BYTES, st, a, b, o, q);
+  launch_k(tc_conv_kernel<ACT, RES, BK, PATCH>, dim3(grid), dim3(TC_THREADS), TCV_SMEM_BYTES, st, a, b, o, q);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 template <int ACT, int RES>
 inline const char* tc_conv_launch_t(int grid, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const TcConvParams& q,
                                     cudaStream_t st) {
-  return q.bk == 32 ? tc_conv_launch_k<ACT, RES, 32>(grid, a, b, o, q, st) : tc_conv_launch_k<ACT, RES, 64>(grid, a, b, o, q, st);
+  if (q.mode == 2)
+    return q.bk == 32 ? tc_conv_launch_k<ACT, RES, 32, true>(grid, a, b, o, q, st) : tc_conv_launch_k<ACT, RES, 64, true>(grid, a, b, o, q, st);
+  return q.bk == 32 ? tc_conv_launch_k<ACT, RES, 32, false>(grid, a, b, o, q, st) : tc_conv_launch_k<ACT, RES, 64, false>(grid, a, b, o, q, st);
 }
 
 template <int ACT>
@@ -933,14 +1133,22 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
   q.bn = bn;
   {
     const int a_bytes = q.mode == 2 ? 0 : TC_BM * q.bk * 2;
-    q.stage_stride = (a_bytes + bn * q.bk * 2 + 1023) / 1024 * 1024;
+    // weight box: no zero-fill rows when a single N tile covers Cout (a 256-row box for Cout = 32 cost 8x the shared-memory
+    // fill and kept the weights from staying resident)
+    q.b_rows = (p.Cout + bn - 1) / bn == 1 ? (p.Cout + 15) / 16 * 16 : bn;
+    q.stage_stride = (a_bytes + q.b_rows * q.bk * 2 + 1023) / 1024 * 1024;
     q.patch_bytes = q.mode == 2 ? (planes0 * TC_PLANE_BYTES + 1023) / 1024 * 1024 : 0;
-    q.patch_off = TCV_RING_BYTES - 2 * q.patch_bytes;
+    const int num_kb = q.taps * q.kchunks;
+    // four patch buffers when the weights still fit next to them (two loads in flight + one consumed + one ready)
+    q.npatch = 2;
+    if (q.mode == 2 && (p.Cout + bn - 1) / bn == 1 && num_kb <= TCV_MAX_STAGES &&
+        num_kb * q.stage_stride + 4 * q.patch_bytes <= TCV_RING_BYTES)
+      q.npatch = 4;
+    q.patch_off = TCV_RING_BYTES - q.npatch * q.patch_bytes;
     const int ring = q.mode == 2 ? q.patch_off : TCV_RING_BYTES;
     q.nstages = ring / q.stage_stride;
     if (q.nstages > TCV_MAX_STAGES) q.nstages = TCV_MAX_STAGES;
     if (q.nstages < 2) return "operand ring too small for this tile";
-    const int num_kb = q.taps * q.kchunks;
     q.b_resident = (q.mode == 2 && (p.Cout + bn - 1) / bn == 1 && num_kb <= q.nstages) ? 1 : 0;
     if (q.b_resident) q.nstages = num_kb;
   }
@@ -949,7 +1157,7 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
     const char* e = q.mode == 0 ? make_tmap_2d(&w.mapA, p.in, (uint64_t)q.M, (uint64_t)p.Cin, TC_BM, (uint32_t)q.bk)
                                 : make_tmap_nhwc(&w.mapA, p.in, p.B, p.Hin, p.Win, p.Cin, (uint32_t)p.stride, (uint32_t)q.bk);
     if (e) return e;
-    e = make_tmap_2d(&w.mapB, w.d_w, (uint64_t)p.Cout, (uint64_t)w.taps * p.Cin, (uint32_t)bn, (uint32_t)q.bk);
+    e = make_tmap_2d(&w.mapB, w.d_w, (uint64_t)p.Cout, (uint64_t)w.taps * p.Cin, (uint32_t)q.b_rows, (uint32_t)q.bk);
     if (e) return e;
     // output boxes are per epilogue warp: 32 tile rows x 64 channels
     e = q.mode == 0 ? make_tmap_2d(&w.mapO, p.out, (uint64_t)q.M, (uint64_t)p.Cout, 32)
@@ -961,9 +1169,12 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
     w.cached_bn = bn;
   }
   const int total = q.m_tiles * q.n_tiles;
-  const int grid = total < 148 ? total : 148;
+  int grid = total < 148 ? total : 148;
+  { static int g_env = -1; if (g_env < 0) { const char* e = getenv("MTB_TC_GRID"); g_env = e ? atoi(e) : 0; } if (g_env > 0 && g_env < grid) grid = g_env; }
   const int res_mode = p.res ? (res_first ? 2 : 1) : 0;
   q.trace = nullptr;
+  q.trace_cta = 0;
+  { const char* e = getenv("MTB_TC_TRACE_CTA"); if (e) q.trace_cta = atoi(e); }
   static const char* trace_env = getenv("MTB_TC_TRACE");  // "<Cin>x<Cout>": trace the first launch of that shape
   static long long* trace_buf = nullptr;
   static bool traced = false;
@@ -971,17 +1182,33 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
   if (trace_env && !traced) {
     int ci = 0, co = 0;
     if (sscanf(trace_env, "%dx%d", &ci, &co) == 2 && ci == p.Cin && co == p.Cout) {
-      if (!trace_buf) cudaMalloc(&trace_buf, 768 * sizeof(long long));
-      cudaMemsetAsync(trace_buf, 0, 768 * sizeof(long long), st);
+      if (!trace_buf) cudaMalloc(&trace_buf, 1088 * sizeof(long long));
+      cudaMemsetAsync(trace_buf, 0, 1088 * sizeof(long long), st);
       q.trace = trace_buf;
       dump = traced = true;
     }
   }
   const char* err = tc_conv_dispatch(p.act, res_mode, grid, w.mapA, w.mapB, w.mapO, q, st);
   if (dump && !err) {
-    std::vector<long long> hbuf(768);
+    std::vector<long long> hbuf(1088);
     cudaStreamSynchronize(st);
-    cudaMemcpy(hbuf.data(), trace_buf, 768 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(hbuf.data(), trace_buf, 1088 * sizeof(long long), cudaMemcpyDeviceToHost);
+    {
+      long long cmin = 1LL << 60, cmax = 0, nmin = 1LL << 60, nmax = 0;
+      double csum = 0, nsum = 0;
+      for (int i = 0; i < grid; ++i) {
+        long long c = hbuf[768 + 2 * i], n = hbuf[768 + 2 * i + 1];
+        cmin = c < cmin ? c : cmin; cmax = c > cmax ? c : cmax; nmin = n < nmin ? n : nmin; nmax = n > nmax ? n : nmax;
+        csum += (double)c; nsum += (double)n;
+      }
+      if (q.debug & 32) {
+        fprintf(stderr, "  per-CTA cycles:");
+        for (int i = 0; i < grid; ++i) fprintf(stderr, " %lld", hbuf[768 + 2 * i] / 1000);
+        fprintf(stderr, "\n");
+      }
+      fprintf(stderr, "  per-CTA totals: cycles min %lld mean %.0f max %lld | ns min %lld mean %.0f max %lld | CTA0 %lld cyc %lld ns\n", cmin,
+              csum / grid, cmax, nmin, nsum / grid, nmax, hbuf[768], hbuf[769]);
+    }
     long long t0 = hbuf[0] ? hbuf[0] : hbuf[256];
     if (t0 < 0) t0 = -t0;
     fprintf(stderr, "MTB_TC_TRACE Cin=%d Cout=%d mode=%d bk=%d bn=%d kb/tile=%d tiles=%d grid=%d\n", p.Cin, p.Cout, q.mode, q.bk, q.bn,
@@ -989,7 +1216,7 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
     const char* names[3] = {"producer(TMA issued)", "mma(full wait done)", "epilogue(tmem_full done / tile end)"};
     for (int r = 0; r < 3; ++r) {
       fprintf(stderr, "  %s:", names[r]);
-      for (int i = 0; i < 70 && hbuf[r * 256 + i]; ++i) {
+      for (int i = 0; i < ((q.debug & 32) ? 256 : 70) && hbuf[r * 256 + i]; ++i) {
         long long v = hbuf[r * 256 + i];
         if (v < 0) fprintf(stderr, " [%lld]", -v - t0);
         else fprintf(stderr, " %lld", v - t0);

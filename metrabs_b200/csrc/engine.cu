@@ -54,6 +54,8 @@ struct Op {
   bool small_io = false;  // squeeze-excitation FCs on [B,1,1,C] fp32 tensors
   float pre_scale[3] = {2.f, 2.f, 2.f}, pre_shift[3] = {-1.f, -1.f, -1.f};  // stem input affine (PreprocLayer: x*2-1)
   bool fused_pool = false;  // bf16 modes: this depthwise op also produces the SE pooled means (next op is skipped)
+  bool se_fused = false;    // fc1 of a squeeze-excitation whose fc1 + fc2 run as one se_fused_kernel launch
+  bool se_skip = false;     // fc2 of such a block (its output is written by the fc1 op's launch)
   bool res_first = false;  // residual added BEFORE the activation (ResNet); EfficientNet adds it after
   int pool_src = -1;       // fc1: index of the OP_POOL op that produces its input (fused pooling leaves partial slices)
   int ksplit = 1;          // split-K (squeeze-excitation fc1): raw sums, bias/act deferred to the consumer
@@ -619,13 +621,22 @@ struct ProfScope {
 };
 
 // shapes covered by dwconv3x3_pool_bf16_kernel
+bool se_fused_enabled() {  // MTB_SE_FUSED=1 enables the one-launch squeeze-excitation (measured SLOWER than split-K fc1 + reduce + fc2: every CTA streams the whole weight matrices through one SM; 76 vs 36 us per block at 2 x 0.9 MB)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTB_SE_FUSED");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 bool dw_strip_eligible(const Op& op) {
   return op.type == OP_DW && op.R == 3 && op.S == 3 && op.dil == 1 && op.Cout % 8 == 0 && (op.stride == 1 || op.stride == 2) &&
          (op.act == ACT_SILU || op.act == ACT_RELU || op.act == ACT_HSWISH);
 }
 
 // number of partial pooling slices the fused depthwise kernel writes (= its gridDim.y)
-constexpr int kDwOW = 2;  // outputs per thread along W in dwconv3x3_pool_bf16_kernel (2: 3 CTAs/SM; 4: 2 CTAs/SM, fewer loads)
+constexpr int kDwOW = 4;  // outputs per thread along W in dwconv3x3_pool_bf16_kernel (measured: 4 -> 3.65 ms, 2 -> 4.25 ms per 128 crops)
 int dw_pool_slices(const Op& dw) {
   const int strips = dw.Hout * ((dw.Wout + kDwOW - 1) / kDwOW);
   return std::min((strips + 7) / 8, kPoolSlices);
@@ -719,6 +730,28 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
       } else if (op.type == OP_MAXPOOL) {
         size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
         launch_k(maxpool_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, st, p);
+      } else if (op.small_io && op.se_fused) {
+        // squeeze-excitation fc1 + fc2 in one launch over the partial pooling slices of the depthwise kernel
+        const Op& f2 = *(&op + 1);
+        const int slices = dw_pool_slices(h->ops[op.pool_src - 1]);
+        static bool attr_set = false;
+        if (!attr_set) {
+          cudaFuncSetAttribute(se_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+          cudaFuncSetAttribute(se_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+          attr_set = true;
+        }
+        // one crop per CTA while that still leaves SMs idle, two beyond (halves the L2 weight traffic)
+        const int cpb = B > 148 ? 2 : 1;
+        const size_t smem = ((size_t)cpb * op.Cin + 17 * cpb * op.Cout) * sizeof(float);
+        float* dst = (float*)buf_ptr(ws, f2.out_buf, features);
+        if (cpb == 1)
+          launch_k(se_fused_kernel<1>, dim3(B), dim3(SE_THREADS), smem, st, (const float*)p.in, slices, (size_t)B * op.Cin,
+                   (const float*)op.d_w, (const float*)op.d_bias, (const float*)f2.d_w, (const float*)f2.d_bias, dst, B, op.Cin, op.Cout,
+                   op.act, f2.act);
+        else
+          launch_k(se_fused_kernel<2>, dim3((B + 1) / 2), dim3(SE_THREADS), smem, st, (const float*)p.in, slices, (size_t)B * op.Cin,
+                   (const float*)op.d_w, (const float*)op.d_bias, (const float*)f2.d_w, (const float*)f2.d_bias, dst, B, op.Cin, op.Cout,
+                   op.act, f2.act);
       } else if (op.small_io) {
         if (op.pool_src > 0 && h->ops[op.pool_src].fused_pool) {  // input = partial pooling slices of the depthwise kernel
           p.a_splits = dw_pool_slices(h->ops[op.pool_src - 1]);
@@ -763,6 +796,7 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
 
 int run_op(mtb_handle* h, const Op& op, const float* crops, int B, const Workspace& ws, void* features, cudaStream_t st) {
   if (op.type == OP_POOL && op.fused_pool) return MTB_OK;  // produced by the preceding depthwise kernel
+  if (op.se_skip) return MTB_OK;                            // produced by the fc1 op's se_fused_kernel launch
   if (is_bf16(h)) return run_op_t<__nv_bfloat16>(h, op, crops, B, ws, features, st);
   return run_op_t<float>(h, op, crops, B, ws, features, st);
 }
@@ -1004,10 +1038,20 @@ int mtb_finalize_weights(mtb_handle* h) {
   DeviceGuard g(h->cfg.device);
   for (void* p : h->dev_allocs) cudaFree(p);
   h->dev_allocs.clear();
-  for (auto& op : h->ops) op.fused_pool = false;
+  for (auto& op : h->ops) op.fused_pool = op.se_fused = op.se_skip = false;
   for (size_t i = 0; i + 1 < h->ops.size(); ++i) {
     const bool fuse = h->cfg.precision == MTB_PRECISION_BF16_TC && dw_strip_eligible(h->ops[i]) && h->ops[i + 1].type == OP_POOL;
     if (fuse) h->ops[i].fused_pool = h->ops[i + 1].fused_pool = true;
+    // fc1 + fc2 behind a fused pool run as one launch when both weight matrices stream through one SM quickly enough
+    // (<= 2 MB; EfficientNetV2-L stage 7 with 2 x 2.4 MB keeps the split-K path) and fit the kernel's register tiling
+    if (fuse && i + 3 < h->ops.size() && se_fused_enabled()) {
+      Op& f1 = h->ops[i + 2];
+      Op& f2 = h->ops[i + 3];
+      const bool ok = f1.small_io && f2.small_io && f1.pool_src == (int)i + 1 && f2.Cin == f1.Cout && f2.Cout == f1.Cin &&
+                      f1.Cout <= 32 * SE_MAX_JPL && f1.Cin % 4 == 0 && (size_t)f1.Cin * f1.Cout * 8 <= (2u << 20) &&
+                      ((size_t)2 * f1.Cin + 34 * f1.Cout) * sizeof(float) <= 96 * 1024;
+      if (ok) { f1.se_fused = true; f2.se_skip = true; }
+    }
   }
   for (auto& op : h->ops) {
     int rc = prepare_op_weights(h, op);
@@ -1412,6 +1456,7 @@ int mtb_debug_run_op(mtb_handle* h, int op_index, const float* in, const float* 
   o.out_buf = (o.type == OP_POOL || o.small_io) ? BUF_SMALL0 + 1 : 2;
   o.tc.cached_in = nullptr;  // the copy must not reuse a tensor map encoded for other buffers
   o.fused_pool = false;      // in isolation a depthwise op does not pool and a pool op runs its own kernel
+  o.se_fused = o.se_skip = false;
   rc = run_op(h, o, crops, batch, ws, nullptr, st);
   if (rc) return rc;
   void* src = buf_ptr(ws, o.out_buf, nullptr);

@@ -1,0 +1,5 @@
+timeout 900 python -m pytest tests/test_gpu_tc.py -q -x 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -x 2>&1 | tail -2
+echo "=== op profile"; timeout 300 python scripts/op_profile.py --batch 128 --top 12 2>&1 | cut -c1-250 | tail -15
+echo "=== bench bf16 B=256"; timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-1800
+echo "=== bench bf16 B=256 no se fusion"; MTB_DISABLE_SE_FUSED=1 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-200

@@ -17,6 +17,7 @@
 #include "conv_simt.cuh"
 #include "decode.cuh"
 #include "tc_gemm.cuh"
+#include "dw_tma.cuh"
 
 using namespace mtb;
 
@@ -66,7 +67,9 @@ struct Op {
   float* d_w = nullptr;     // fp32 [R*S*Cin][Cout]  (dw: [R*S][C])
   float* d_bias = nullptr;  // fp32 [Cout]
   TcWeights tc;             // bf16 K-major copy + TMA descriptor state for the tcgen05 path
+  mutable DwTmaCache dw_cache;  // input tensor map of the TMA-staged depthwise kernel
   double flops = 0;         // 2*MACs per crop
+  int stage = 0;            // EfficientNet stage (1-based; 0 = stem / last conv / other backbones): unit of crop chunking
 };
 
 }  // namespace
@@ -85,6 +88,7 @@ struct mtb_handle {
   int small_c = 0;                 // capacity of one small buffer, floats per crop
   int64_t launches = 0;
   double flops_per_crop = 0;
+  std::vector<int> stage_chunks;   // built-in crop-chunk size per EfficientNet stage (index = stage, 0 = whole batch)
   // host-path staging
   void* stage = nullptr;
   size_t stage_bytes = 0;
@@ -229,6 +233,7 @@ void plan_effnet(mtb_handle* h) {
   }
   for (int si = 0; si < c.n_stages; ++si) {
     const mtb_stage& st = c.stages[si];
+    const size_t stage_first_op = h->ops.size();
     for (int bi = 0; bi < st.layers; ++bi) {
       const bool first = bi == 0;
       const int cin = first ? st.cin : st.cout;
@@ -278,6 +283,7 @@ void plan_effnet(mtb_handle* h) {
         P.cur = t3;
       }
     }
+    for (size_t k = stage_first_op; k < h->ops.size(); ++k) h->ops[k].stage = si + 1;
   }
   {
     char key[64];
@@ -561,6 +567,7 @@ int prepare_op_weights(mtb_handle* h, Op& op) {
 // --------------------------------------------------------------------------------------------- workspace
 struct Workspace {
   char* base;
+  int b0 = 0;  // first crop of the chunk being executed: big-buffer / feature tensors are addressed at their [b0:] slice
   size_t big_stride, small_stride;
   size_t off_small, off_features, off_logits, off_c2d, off_c3d, off_n2d, off_partial, total;
 };
@@ -590,6 +597,13 @@ void* buf_ptr(const Workspace& w, int id, void* features) {
   if (id < 0) return nullptr;
   if (id < kNumBig) return w.base + w.big_stride * id;
   return w.base + w.off_small + w.small_stride * (id - BUF_SMALL0);
+}
+
+// activation tensor [B,hh,ww,cc] in buffer `id`, at the current chunk's first crop (small [B,C] buffers are per-chunk scratch)
+void* act_ptr(const mtb_handle* h, const Workspace& w, int id, void* features, int hh, int ww, int cc) {
+  char* base = (char*)buf_ptr(w, id, features);
+  if (!base || id >= kNumBig) return base;
+  return base + (size_t)w.b0 * hh * ww * cc * (h->cfg.precision != MTB_PRECISION_FP32 ? 2 : 4);
 }
 
 // ---------------------------------------------------------------------------------------------- profiler
@@ -637,7 +651,25 @@ bool dw_strip_eligible(const Op& op) {
 
 // number of partial pooling slices the fused depthwise kernel writes (= its gridDim.y)
 constexpr int kDwOW = 4;  // outputs per thread along W in dwconv3x3_pool_bf16_kernel (measured: 4 -> 3.65 ms, 2 -> 4.25 ms per 128 crops)
+// stride-1 3x3 depthwise ops run the TMA-staged kernel (dw_tma.cuh); MTB_DW_TMA=0 falls back to the strip kernel (A/B runs)
+bool dw_tma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTB_DW_TMA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+DwTmaPlan dw_tma_plan_for(const Op& op) {
+  DwTmaPlan none;
+  if (!dw_tma_enabled() || !dw_strip_eligible(op) || op.stride != 1 || op.Hin != op.Hout || op.Win != op.Wout) return none;
+  DwTmaPlan pl = dw_tma_plan(op.Hout, op.Wout);
+  if (!pl.ok || pl.n_rb > kPoolSlices) return none;
+  return pl;
+}
 int dw_pool_slices(const Op& dw) {
+  const DwTmaPlan pl = dw_tma_plan_for(dw);
+  if (pl.ok) return pl.n_rb;
   const int strips = dw.Hout * ((dw.Wout + kDwOW - 1) / kDwOW);
   return std::min((strips + 7) / 8, kPoolSlices);
 }
@@ -672,7 +704,7 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
   if (op.type == OP_CONV && op.tc.ready && op.scale_buf != BUF_NONE && !(tc_fuse_se() && op.R == 1 && op.stride == 1)) {
     // squeeze-excitation scale applied in place ahead of a tensor-core conv that cannot fuse it (1x1 stride-1 projections
     // apply it to the A tiles in shared memory inside tc_conv_kernel)
-    void* x = buf_ptr(ws, op.in_buf, features);
+    void* x = act_ptr(h, ws, op.in_buf, features, op.Hin, op.Win, op.Cin);
     const double bytes = 2.0 * B * op.Hin * op.Win * op.Cin * elem_size(h);
     ProfScope ps(h, KC_SE_SCALE, 0.0, bytes, st);
     const char* e = tc_se_scale_launch(x, (const float*)buf_ptr(ws, op.scale_buf, features), B, op.Hin * op.Win, op.Cin, st);
@@ -683,7 +715,8 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
   switch (op.type) {
     case OP_STEM: {
       StemParams p;
-      p.in = crops; p.out = buf_ptr(ws, op.out_buf, features); p.w = op.d_w; p.bias = op.d_bias;
+      p.in = crops + (size_t)ws.b0 * op.Cin * op.Hin * op.Win;
+      p.out = act_ptr(h, ws, op.out_buf, features, op.Hout, op.Wout, op.Cout); p.w = op.d_w; p.bias = op.d_bias;
       for (int i = 0; i < 3; ++i) { p.pre_scale[i] = op.pre_scale[i]; p.pre_shift[i] = op.pre_shift[i]; }
       p.pre_scale[3] = 1.f; p.pre_shift[3] = 0.f;
       p.B = B; p.Hin = op.Hin; p.Win = op.Win; p.Cin = op.Cin; p.Hout = op.Hout; p.Wout = op.Wout; p.Cout = op.Cout;
@@ -701,9 +734,9 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
     case OP_DW:
     case OP_MAXPOOL: {
       ConvParams p;
-      p.in = buf_ptr(ws, op.in_buf, features);
-      p.out = buf_ptr(ws, op.out_buf, features);
-      p.res = buf_ptr(ws, op.res_buf, features);
+      p.in = act_ptr(h, ws, op.in_buf, features, op.Hin, op.Win, op.Cin);
+      p.out = act_ptr(h, ws, op.out_buf, features, op.Hout, op.Wout, op.Cout);
+      p.res = act_ptr(h, ws, op.res_buf, features, op.Hout, op.Wout, op.Cout);
       p.a_scale = (const float*)buf_ptr(ws, op.scale_buf, features);
       p.w = op.d_w; p.bias = op.d_bias;
       p.B = B; p.Hin = op.Hin; p.Win = op.Win; p.Cin = op.Cin; p.Hout = op.Hout; p.Wout = op.Wout; p.Cout = op.Cout;
@@ -712,6 +745,14 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
       if (op.type == OP_DW) {
         if (h->cfg.precision == MTB_PRECISION_BF16_TC && dw_strip_eligible(op)) {
           float* pooled = op.fused_pool ? (float*)buf_ptr(ws, BUF_SMALL0, features) : nullptr;
+          const DwTmaPlan tma_plan = dw_tma_plan_for(op);
+          if (tma_plan.ok) {
+            const char* e = dw_tma_launch(op.dw_cache, tma_plan, p.in, p.out, op.d_w, op.d_bias, pooled, B, op.Hout, op.Wout, op.Cout,
+                                          op.pad_t, op.pad_l, op.act, st);
+            if (e) return fail(h, MTB_ERR_CUDA, "depthwise (TMA) launch %s: %s", op.name.c_str(), e);
+            h->launches++;
+            break;
+          }
           dim3 grid((op.Cout / 8 + 31) / 32, dw_pool_slices(op), B), block(32, 8);
           if (op.act == ACT_SILU) {
             if (op.stride == 1) launch_k(dwconv3x3_pool_bf16_kernel<1, ACT_SILU, kDwOW>, dim3(grid), dim3(block), 0, st, p, pooled);
@@ -783,7 +824,7 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
     }
     case OP_POOL: {
       dim3 grid((op.Cin + 127) / 128, B), block(32, 8);
-      launch_k(pool_mean_kernel<T>, dim3(grid), dim3(block), 0, st, (const T*)buf_ptr(ws, op.in_buf, features),
+      launch_k(pool_mean_kernel<T>, dim3(grid), dim3(block), 0, st, (const T*)act_ptr(h, ws, op.in_buf, features, op.Hin, op.Win, op.Cin),
                                                    (float*)buf_ptr(ws, op.out_buf, features), op.Hin * op.Win, op.Cin);
       h->launches++;
       break;
@@ -799,6 +840,55 @@ int run_op(mtb_handle* h, const Op& op, const float* crops, int B, const Workspa
   if (op.se_skip) return MTB_OK;                            // produced by the fc1 op's se_fused_kernel launch
   if (is_bf16(h)) return run_op_t<__nv_bfloat16>(h, op, crops, B, ws, features, st);
   return run_op_t<float>(h, op, crops, B, ws, features, st);
+}
+
+// Crop chunking: the ops of one EfficientNet stage run chunk by chunk (all ops of the stage on crops [b0, b0+n), then the
+// next chunk), so that a chunk's expanded / depthwise tensors are still in the 126 MB L2 when the next op of the block
+// reads them, instead of round-tripping through HBM at batch 256.  MTB_CHUNKS="c1,c2,..." gives the chunk (crops) per
+// stage, 0 = whole batch; unset = the built-in policy below.
+int stage_chunk(const mtb_handle* h, int stage, int B) {
+  static std::vector<int> env;
+  static bool parsed = false;
+  if (!parsed) {
+    parsed = true;
+    const char* e = getenv("MTB_CHUNKS");
+    if (e) {
+      env.push_back(-1);  // marks "explicit"
+      for (const char* q = e; *q;) {
+        env.push_back(atoi(q));
+        while (*q && *q != ',') ++q;
+        if (*q == ',') ++q;
+      }
+    }
+  }
+  if (stage <= 0 || h->cfg.precision != MTB_PRECISION_BF16_TC) return B;
+  int c = 0;
+  if (!env.empty()) c = stage < (int)env.size() ? env[stage] : 0;
+  else c = stage < (int)h->stage_chunks.size() ? h->stage_chunks[stage] : 0;
+  return (c <= 0 || c > B) ? B : c;
+}
+
+int run_backbone(mtb_handle* h, const float* crops, int B, Workspace& ws, void* features, cudaStream_t st) {
+  const size_t n = h->ops.size();
+  size_t i = 0;
+  while (i < n) {
+    size_t j = i + 1;
+    while (j < n && h->ops[j].stage == h->ops[i].stage) ++j;
+    const int chunk = stage_chunk(h, h->ops[i].stage, B);
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+      ws.b0 = b0;
+      const int nb = std::min(chunk, B - b0);
+      for (size_t k = i; k < j; ++k) {
+        h->prof_cur_op = (int)k;
+        int rc = run_op(h, h->ops[k], crops, nb, ws, features, st);
+        if (rc) { ws.b0 = 0; return rc; }
+      }
+    }
+    i = j;
+  }
+  ws.b0 = 0;
+  h->prof_cur_op = -1;
+  return MTB_OK;
 }
 
 int check_common(mtb_handle* h, int B, size_t ws_bytes, const void* workspace) {
@@ -1118,13 +1208,7 @@ int mtb_backbone_forward(mtb_handle* h, const float* crops, int batch, void* fea
   DeviceGuard g(h->cfg.device);
   h->launches = 0;
   Workspace ws = layout(h, batch, workspace);
-  for (size_t i = 0; i < h->ops.size(); ++i) {
-    h->prof_cur_op = (int)i;
-    rc = run_op(h, h->ops[i], crops, batch, ws, features, (cudaStream_t)stream);
-    if (rc) return rc;
-  }
-  h->prof_cur_op = -1;
-  return MTB_OK;
+  return run_backbone(h, crops, batch, ws, features, (cudaStream_t)stream);
 }
 
 int mtb_head_decode(mtb_handle* h, const void* features, int batch, float* coords2d, float* coords3d_rel,
@@ -1214,12 +1298,8 @@ int mtb_forward(mtb_handle* h, const float* crops, const float* intrinsics, int 
   h->launches = 0;
   Workspace ws = layout(h, batch, workspace);
   void* features = ws.base + ws.off_features;
-  for (size_t i = 0; i < h->ops.size(); ++i) {
-    h->prof_cur_op = (int)i;
-    rc = run_op(h, h->ops[i], crops, batch, ws, features, st);
-    if (rc) return rc;
-  }
-  h->prof_cur_op = -1;
+  rc = run_backbone(h, crops, batch, ws, features, st);
+  if (rc) return rc;
   float* c2d = (float*)(ws.base + ws.off_c2d);
   float* c3d = (float*)(ws.base + ws.off_c3d);
   rc = head_decode_impl(h, features, batch, c2d, c3d, ws, st);
@@ -1455,6 +1535,8 @@ int mtb_debug_run_op(mtb_handle* h, int op_index, const float* in, const float* 
   if (scale) { o.scale_buf = BUF_SMALL0 + 2; put(scale, o.scale_buf, (size_t)batch * o.Cin, true); }
   o.out_buf = (o.type == OP_POOL || o.small_io) ? BUF_SMALL0 + 1 : 2;
   o.tc.cached_in = nullptr;  // the copy must not reuse a tensor map encoded for other buffers
+  o.tc.map_sets.clear();
+  o.dw_cache = DwTmaCache();
   o.fused_pool = false;      // in isolation a depthwise op does not pool and a pool op runs its own kernel
   o.se_fused = o.se_skip = false;
   rc = run_op(h, o, crops, batch, ws, nullptr, st);

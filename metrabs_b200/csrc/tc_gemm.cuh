@@ -213,6 +213,7 @@ struct TcConvParams {
                 // 4 = skip the residual load, 8 = skip the patch loads (mode 2)
   int bk;       // K elements per ring stage (host-side copy of the BK template argument)
   int trace_cta; // the CTA that writes the clock64 trace
+  int rot;       // modes 0 / 1: rotate the start of each CTA's K loop (see the A producer); 0 with the fused SE scalers
 };
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -432,11 +433,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int tr = 0;
     const int kchunks = pin(p.kchunks);
     TileWalk tw_(blockIdx.x, gridDim.x, p.n_tiles);
+    // K rotation: CTA i starts every tile's K loop at k-block (i mod num_kb) and wraps.  Without it all CTAs of a wave
+    // read the SAME weight k-block at the same time and the few L2 slices holding those lines serialise 148 requests
+    // per line (long-K / one-N-tile projection GEMMs ran at ~3000 cycles per k-block against ~460 of MMA work).
+    const int rot_kb = p.rot ? (int)(blockIdx.x % (unsigned)num_kb) : 0;
     if (p.mode == 0) {
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
         const int row0 = tw_.m_blk * TC_BM;
+        int kc = rot_kb;
 #pragma unroll 1
-        for (int kc = 0; kc < kchunks; ++kc) {
+        for (int i = 0; i < kchunks; ++i) {
           mbar_wait_a(empty0 + stage * 8, phase ^ 1);
           if (elect_one()) {
             mbar_expect_tx_a(full0 + stage * 8, a_bytes);
@@ -444,12 +450,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (trace_on && tr < 256) p.trace[tr++] = clock64();
           }
           __syncwarp();
+          if (++kc == kchunks) kc = 0;
           sa += stage_stride;
           if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; sa = smem_base; }
         }
       }
     } else {
       const int R = pin(p.R), S = pin(p.S), dil = pin(p.dil);
+      const int tap0 = rot_kb / kchunks, kc0 = rot_kb - tap0 * kchunks, r0 = tap0 / S, s0 = tap0 - r0 * S;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
         const int m_blk = tw_.m_blk;
         const int tw = m_blk % p.tiles_w;
@@ -457,19 +465,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int b = m_blk / (p.tiles_w * p.tiles_h);
         const int ih0 = th * TC_TILE_H * p.stride - p.pad_t;
         const int iw0 = tw * TC_TILE_W * p.stride - p.pad_l;
-        for (int r = 0; r < R; ++r)
-          for (int s_ = 0; s_ < S; ++s_)
-            for (int kc = 0; kc < kchunks; ++kc) {
-              mbar_wait_a(empty0 + stage * 8, phase ^ 1);
-              if (elect_one()) {
-                mbar_expect_tx_a(full0 + stage * 8, a_bytes);
-                tma_load_4d_a(sa, &tmA, full0 + stage * 8, kc * BK, iw0 + s_ * dil, ih0 + r * dil, b);
-                if (trace_on && tr < 256) p.trace[tr++] = clock64();
-              }
-              __syncwarp();
-              sa += stage_stride;
-              if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; sa = smem_base; }
-            }
+        int r = r0, s_ = s0, kc = kc0;
+#pragma unroll 1
+        for (int i = 0; i < num_kb; ++i) {
+          mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx_a(full0 + stage * 8, a_bytes);
+            tma_load_4d_a(sa, &tmA, full0 + stage * 8, kc * BK, iw0 + s_ * dil, ih0 + r * dil, b);
+            if (trace_on && tr < 256) p.trace[tr++] = clock64();
+          }
+          __syncwarp();
+          if (++kc == kchunks) {
+            kc = 0;
+            if (++s_ == S) { s_ = 0; if (++r == R) r = 0; }
+          }
+          sa += stage_stride;
+          if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; sa = smem_base; }
+        }
       }
     }
   } else if (warp == 9) {
@@ -487,22 +499,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
       uint32_t stage = 0, phase = 0, sb = smem_base + a_bytes;
       const int taps = pin(p.taps), kchunks = pin(p.kchunks), Cin = pin(p.Cin), bn = pin(p.bn);
+      // same K rotation as the A producer (mode 2 keeps the natural order: its MMA loop derives the patch offset from it)
+      const int rot_kb = (p.rot && !patch_mode) ? (int)(blockIdx.x % (unsigned)num_kb) : 0;
+      const int tap0 = rot_kb / kchunks, kc0 = rot_kb - tap0 * kchunks;
       TileWalk tw_(blockIdx.x, gridDim.x, p.n_tiles);
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
         const int nrow = tw_.n_blk * bn;
-        for (int tap = 0; tap < taps; ++tap) {
-          int col = tap * Cin;
+        int tap = tap0, kc = kc0;
 #pragma unroll 1
-          for (int kc = 0; kc < kchunks; ++kc, col += BK) {
-            mbar_wait_a(empty0 + stage * 8, phase ^ 1);
-            if (elect_one()) {
-              mbar_expect_tx_a(full0 + stage * 8, b_bytes);
-              tma_load_2d_a(sb, &tmB, full0 + stage * 8, col, nrow);
-            }
-            __syncwarp();
-            sb += stage_stride;
-            if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; sb = smem_base + a_bytes; }
+        for (int i = 0; i < num_kb; ++i) {
+          mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx_a(full0 + stage * 8, b_bytes);
+            tma_load_2d_a(sb, &tmB, full0 + stage * 8, tap * Cin + kc * BK, nrow);
           }
+          __syncwarp();
+          if (++kc == kchunks) { kc = 0; if (++tap == taps) tap = 0; }
+          sb += stage_stride;
+          if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; sb = smem_base + a_bytes; }
         }
       }
     }
@@ -964,6 +978,16 @@ struct TcWeights {
   mutable const void* cached_in = nullptr;
   mutable const void* cached_out = nullptr;
   mutable int cached_B = -1, cached_bn = 0;
+  // conv path: tensor maps per (input, output, batch, N tile) - a crop-chunked forward launches the same op on several
+  // buffer slices per step, and re-encoding three maps per launch would sit on the host's launch path
+  struct MapSet {
+    CUtensorMap a, b, o;
+    const void* in = nullptr;
+    const void* out = nullptr;
+    int B = -1, bn = 0;
+  };
+  mutable std::vector<MapSet> map_sets;
+  mutable size_t map_rr = 0;
 };
 
 inline bool tc_fuse_se() {
@@ -1153,20 +1177,34 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
     if (q.b_resident) q.nstages = num_kb;
   }
   q.n_tiles = (p.Cout + bn - 1) / bn;
-  if (w.cached_in != p.in || w.cached_out != p.out || w.cached_B != p.B || w.cached_bn != bn) {
-    const char* e = q.mode == 0 ? make_tmap_2d(&w.mapA, p.in, (uint64_t)q.M, (uint64_t)p.Cin, TC_BM, (uint32_t)q.bk)
-                                : make_tmap_nhwc(&w.mapA, p.in, p.B, p.Hin, p.Win, p.Cin, (uint32_t)p.stride, (uint32_t)q.bk);
+  {
+    static int rot_env = -1;  // MTB_TC_ROT=0 disables the K rotation (A/B measurements)
+    if (rot_env < 0) { const char* e = getenv("MTB_TC_ROT"); rot_env = (e && e[0] == '0') ? 0 : 1; }
+    q.rot = (rot_env && q.mode != 2 && q.a_scale == nullptr) ? 1 : 0;
+  }
+  const TcWeights::MapSet* ms = nullptr;
+  for (const TcWeights::MapSet& c : w.map_sets)
+    if (c.in == p.in && c.out == p.out && c.B == p.B && c.bn == bn) { ms = &c; break; }
+  if (!ms) {
+    TcWeights::MapSet c;
+    const char* e = q.mode == 0 ? make_tmap_2d(&c.a, p.in, (uint64_t)q.M, (uint64_t)p.Cin, TC_BM, (uint32_t)q.bk)
+                                : make_tmap_nhwc(&c.a, p.in, p.B, p.Hin, p.Win, p.Cin, (uint32_t)p.stride, (uint32_t)q.bk);
     if (e) return e;
-    e = make_tmap_2d(&w.mapB, w.d_w, (uint64_t)p.Cout, (uint64_t)w.taps * p.Cin, (uint32_t)q.b_rows, (uint32_t)q.bk);
+    e = make_tmap_2d(&c.b, w.d_w, (uint64_t)p.Cout, (uint64_t)w.taps * p.Cin, (uint32_t)q.b_rows, (uint32_t)q.bk);
     if (e) return e;
     // output boxes are per epilogue warp: 32 tile rows x 64 channels
-    e = q.mode == 0 ? make_tmap_2d(&w.mapO, p.out, (uint64_t)q.M, (uint64_t)p.Cout, 32)
-                    : make_tmap_nhwc(&w.mapO, p.out, p.B, p.Hout, p.Wout, p.Cout, 1, TC_BK, (uint32_t)q.tile_w, (uint32_t)(32 / q.tile_w));
+    e = q.mode == 0 ? make_tmap_2d(&c.o, p.out, (uint64_t)q.M, (uint64_t)p.Cout, 32)
+                    : make_tmap_nhwc(&c.o, p.out, p.B, p.Hout, p.Wout, p.Cout, 1, TC_BK, (uint32_t)q.tile_w, (uint32_t)(32 / q.tile_w));
     if (e) return e;
-    w.cached_in = p.in;
-    w.cached_out = p.out;
-    w.cached_B = p.B;
-    w.cached_bn = bn;
+    c.in = p.in; c.out = p.out; c.B = p.B; c.bn = bn;
+    if (w.map_sets.size() < 16) {
+      w.map_sets.push_back(c);
+      ms = &w.map_sets.back();
+    } else {
+      w.map_sets[w.map_rr % 16] = c;
+      ms = &w.map_sets[w.map_rr % 16];
+      ++w.map_rr;
+    }
   }
   const int total = q.m_tiles * q.n_tiles;
   int grid = total < 148 ? total : 148;
@@ -1188,7 +1226,7 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
       dump = traced = true;
     }
   }
-  const char* err = tc_conv_dispatch(p.act, res_mode, grid, w.mapA, w.mapB, w.mapO, q, st);
+  const char* err = tc_conv_dispatch(p.act, res_mode, grid, ms->a, ms->b, ms->o, q, st);
   if (dump && !err) {
     std::vector<long long> hbuf(1088);
     cudaStreamSynchronize(st);

@@ -33,6 +33,7 @@ struct DwTmaParams {
   int strips_w, bands, nstrips;  // per item: column strips, row runs per crop, G * bands * strips_w
   int stage_bytes;
   float inv_hw;
+  int rev;             // walk the items last-to-first (see dw_tma_launch)
 };
 
 struct DwTmaPlan {
@@ -84,6 +85,46 @@ inline const char* make_tmap_dw(CUtensorMap* m, const void* ptr, uint64_t B, uin
   return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(dw) failed";
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): two IEEE fp32 operations per issued instruction, bit-identical to the
+// scalar fmaf / fmul / fadd.  The kernel is issue-bound (ncu: 56 % issue-active with 2 warps per scheduler), so halving
+// the FMA instruction count is worth more than any memory-side change.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// activation of a pair; SiLU(x) = h + h * tanh(h), h = x / 2 (same arithmetic as fast_act<ACT_SILU>)
+template <int ACT>
+__device__ __forceinline__ f32x2 f2_act(f32x2 x) {
+  if constexpr (ACT == ACT_SILU) {
+    const f32x2 h = f2_mul(x, f2_pack(0.5f, 0.5f));
+    float h0, h1;
+    f2_unpack(h, h0, h1);
+    return f2_fma(h, f2_pack(fast_tanh(h0), fast_tanh(h1)), h);
+  } else {
+    float x0, x1;
+    f2_unpack(x, x0, x1);
+    return f2_pack(fast_act<ACT>(x0), fast_act<ACT>(x1));
+  }
+}
+
 template <int ACT>
 __global__ void __launch_bounds__(DWT_THREADS, 2)
 dw3x3s1_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwTmaParams p) {
@@ -110,7 +151,8 @@ dw3x3s1_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwTmaParams p
   const int strips_per_crop = p.bands * p.strips_w;
   const int own_ch = tid & 63, own_g0 = tid >> 6;  // blocksum owner: channel own_ch, crops own_g0, own_g0 + 2, ...
 
-  auto issue = [&](int it, int stage) {
+  auto issue = [&](int it_, int stage) {
+    const int it = p.rev ? p.items - 1 - it_ : it_;
     const int cg = it % p.n_cg;
     const int t2 = it / p.n_cg;
     const int rb = t2 % p.n_rb, bg = t2 / p.n_rb;
@@ -120,9 +162,10 @@ dw3x3s1_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwTmaParams p
 
   if (tid == 0 && (int)blockIdx.x < p.items) issue(blockIdx.x, 0);
   int li = 0;
-  for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++li) {
+  for (int it_ = blockIdx.x; it_ < p.items; it_ += gridDim.x, ++li) {
     const int stage = li & 1;
-    if (tid == 0 && it + (int)gridDim.x < p.items) issue(it + gridDim.x, stage ^ 1);
+    if (tid == 0 && it_ + (int)gridDim.x < p.items) issue(it_ + gridDim.x, stage ^ 1);
+    const int it = p.rev ? p.items - 1 - it_ : it_;
     const int cg = it % p.n_cg;
     const int t2 = it / p.n_cg;
     const int rb = t2 % p.n_rb, bg = t2 / p.n_rb;
@@ -131,8 +174,8 @@ dw3x3s1_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwTmaParams p
     const int b0 = bg * p.G, row0 = rb * p.BH;
     const int rows_item = min(p.BH, p.H - row0);  // output rows of this item
 
-    // this thread's 8 channels: 9 taps + bias, fp32, in registers for the whole item
-    float w[9][8], bias[8];
+    // this thread's 8 channels: 9 taps + bias, fp32 pairs (channels 2k, 2k+1), in registers for the whole item
+    f32x2 w[9][4], bias[4];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
@@ -140,8 +183,8 @@ dw3x3s1_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwTmaParams p
         w0 = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)t * p.C + c));
         w1 = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)t * p.C + c + 4));
       }
-      w[t][0] = w0.x; w[t][1] = w0.y; w[t][2] = w0.z; w[t][3] = w0.w;
-      w[t][4] = w1.x; w[t][5] = w1.y; w[t][6] = w1.z; w[t][7] = w1.w;
+      w[t][0] = f2_pack(w0.x, w0.y); w[t][1] = f2_pack(w0.z, w0.w);
+      w[t][2] = f2_pack(w1.x, w1.y); w[t][3] = f2_pack(w1.z, w1.w);
     }
     {
       float4 b0v = make_float4(0.f, 0.f, 0.f, 0.f), b1v = b0v;
@@ -149,8 +192,8 @@ dw3x3s1_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwTmaParams p
         b0v = __ldg(reinterpret_cast<const float4*>(p.bias + c));
         b1v = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
       }
-      bias[0] = b0v.x; bias[1] = b0v.y; bias[2] = b0v.z; bias[3] = b0v.w;
-      bias[4] = b1v.x; bias[5] = b1v.y; bias[6] = b1v.z; bias[7] = b1v.w;
+      bias[0] = f2_pack(b0v.x, b0v.y); bias[1] = f2_pack(b0v.z, b0v.w);
+      bias[2] = f2_pack(b1v.x, b1v.y); bias[3] = f2_pack(b1v.z, b1v.w);
     }
     if (p.pooled) {
       for (int g = own_g0; g < p.G; g += 2) blocksum[g][own_ch] = 0.f;
@@ -160,9 +203,9 @@ dw3x3s1_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwTmaParams p
 
     for (int s0 = 0; s0 < p.nstrips; s0 += 16) {
       const int s = s0 + sidx;
-      float psum[8];
+      f32x2 psum[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) psum[k] = 0.f;
+      for (int k = 0; k < 4; ++k) psum[k] = f2_pack(0.f, 0.f);
       if (s < p.nstrips && c_ok) {
         const int g = s / strips_per_crop;
         const int rem = s - g * strips_per_crop;
@@ -174,28 +217,19 @@ dw3x3s1_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwTmaParams p
         if (b < p.B && rows_run > 0) {
           const uint8_t* prow = patch + (size_t)((g * PHB + orow0) * PW + ow0) * 128;
           __nv_bfloat16* obase = p.out + ((size_t)(b * p.H + row0 + orow0) * p.W + ow0) * p.C + c;
-          float acc[3][DWT_OW][8];
+          f32x2 acc[3][DWT_OW][4];
 #pragma unroll
           for (int pr = 0; pr < DWT_RUN + 2; ++pr) {
             if (pr < rows_run + 2) {
               // one input row of the run (OW + 2 pixels x 8 channels, each read and unpacked once); it is tap row r of output
-              // row pr - r (slot (pr - r) % 3), and r = 0 starts that output row from the bias
-              if (pr < DWT_RUN) {
-#pragma unroll
-                for (int i = 0; i < DWT_OW; ++i)
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) acc[pr % 3][i][k] = bias[k];
-              }
+              // row pr - r (slot (pr - r) % 3); the first tap of an output row (r = 0, s = 0) starts from the bias
 #pragma unroll
               for (int x = 0; x < DWT_OW + 2; ++x) {
                 const uint4 raw = *reinterpret_cast<const uint4*>(prow + (size_t)(pr * PW + x) * 128);
                 const unsigned wd[4] = {raw.x, raw.y, raw.z, raw.w};
-                float v[8];
+                f32x2 v[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  v[2 * k] = __uint_as_float(wd[k] << 16);
-                  v[2 * k + 1] = __uint_as_float(wd[k] & 0xffff0000u);
-                }
+                for (int k = 0; k < 4; ++k) v[k] = f2_pack(__uint_as_float(wd[k] << 16), __uint_as_float(wd[k] & 0xffff0000u));
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                   const int o = pr - r;  // compile-time
@@ -205,7 +239,8 @@ dw3x3s1_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwTmaParams p
                     const int s_ = x - i;  // compile-time
                     if (s_ >= 0 && s_ < 3) {
 #pragma unroll
-                      for (int k = 0; k < 8; ++k) acc[o % 3][i][k] = fmaf(v[k], w[r * 3 + s_][k], acc[o % 3][i][k]);
+                      for (int k = 0; k < 4; ++k)
+                        acc[o % 3][i][k] = f2_fma(v[k], w[r * 3 + s_][k], (r == 0 && s_ == 0) ? bias[k] : acc[o % 3][i][k]);
                     }
                   }
                 }
@@ -221,10 +256,11 @@ dw3x3s1_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwTmaParams p
                     __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                      const float a0 = fast_act<ACT>(acc[slot][i][2 * k]), a1 = fast_act<ACT>(acc[slot][i][2 * k + 1]);
+                      const f32x2 a = f2_act<ACT>(acc[slot][i][k]);
+                      float a0, a1;
+                      f2_unpack(a, a0, a1);
                       o2[k] = __floats2bfloat162_rn(a0, a1);
-                      psum[2 * k] += a0;
-                      psum[2 * k + 1] += a1;
+                      psum[k] = f2_add(psum[k], a);
                     }
                     *reinterpret_cast<uint4*>(orow + (size_t)i * p.C) = ov;
                   }
@@ -236,8 +272,8 @@ dw3x3s1_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const DwTmaParams p
       }
       if (p.pooled) {
         // fixed-order reduction of this pass: strip slots -> (crop, channel) owner threads
-        *reinterpret_cast<float4*>(&red[sidx][j * 8]) = make_float4(psum[0], psum[1], psum[2], psum[3]);
-        *reinterpret_cast<float4*>(&red[sidx][j * 8 + 4]) = make_float4(psum[4], psum[5], psum[6], psum[7]);
+        *reinterpret_cast<ulonglong2*>(&red[sidx][j * 8]) = make_ulonglong2(psum[0], psum[1]);
+        *reinterpret_cast<ulonglong2*>(&red[sidx][j * 8 + 4]) = make_ulonglong2(psum[2], psum[3]);
         __syncthreads();
         for (int g = own_g0; g < p.G; g += 2) {
           // strip slots of crop g in this pass: [g * strips_per_crop, (g + 1) * strips_per_crop) - s0, clipped
@@ -282,6 +318,14 @@ inline const char* dw_tma_launch(DwTmaCache& cache, const DwTmaPlan& plan, const
   p.nstrips = plan.G * p.bands * p.strips_w;
   p.stage_bytes = 128 * (W + 2) * (plan.BH + 2) * plan.G;
   p.inv_hw = 1.0f / (float)(H * W);
+  {
+    // Serpentine traversal (MTB_DW_REV=1, off unless measured faster): the expand GEMM before this op wrote its output
+    // first-crop-to-last, so the END of the tensor is what the L2 still holds; walking the items last-to-first reads that
+    // part from L2, and leaves the BEGINNING of this op's output in L2 for the projection GEMM that follows.
+    static int rev_env = -1;
+    if (rev_env < 0) { const char* e = getenv("MTB_DW_REV"); rev_env = (e && e[0] == '1') ? 1 : 0; }
+    p.rev = rev_env;
+  }
   if (cache.in != in || cache.B != B) {
     const char* e = make_tmap_dw(&cache.map, in, (uint64_t)B, (uint64_t)H, (uint64_t)W, (uint64_t)C, (uint32_t)(W + 2),
                                  (uint32_t)(plan.BH + 2), (uint32_t)plan.G);

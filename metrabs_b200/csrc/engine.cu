@@ -18,6 +18,7 @@
 #include "decode.cuh"
 #include "tc_gemm.cuh"
 #include "dw_tma.cuh"
+#include "se_cluster.cuh"
 
 using namespace mtb;
 
@@ -57,6 +58,7 @@ struct Op {
   bool fused_pool = false;  // bf16 modes: this depthwise op also produces the SE pooled means (next op is skipped)
   bool se_fused = false;    // fc1 of a squeeze-excitation whose fc1 + fc2 run as one se_fused_kernel launch
   bool se_skip = false;     // fc2 of such a block (its output is written by the fc1 op's launch)
+  bool se_cluster = false;  // with se_fused: the launch is se_cluster_kernel (8-CTA clusters) instead of se_fused_kernel
   bool res_first = false;  // residual added BEFORE the activation (ResNet); EfficientNet adds it after
   int pool_src = -1;       // fc1: index of the OP_POOL op that produces its input (fused pooling leaves partial slices)
   int ksplit = 1;          // split-K (squeeze-excitation fc1): raw sums, bias/act deferred to the consumer
@@ -69,7 +71,7 @@ struct Op {
   TcWeights tc;             // bf16 K-major copy + TMA descriptor state for the tcgen05 path
   mutable DwTmaCache dw_cache;  // input tensor map of the TMA-staged depthwise kernel
   double flops = 0;         // 2*MACs per crop
-  int stage = 0;            // EfficientNet stage (1-based; 0 = stem / last conv / other backbones): unit of crop chunking
+  int stage = 0;            // EfficientNet stage (1-based; 0 = stem / last conv / other backbones)
 };
 
 }  // namespace
@@ -88,7 +90,6 @@ struct mtb_handle {
   int small_c = 0;                 // capacity of one small buffer, floats per crop
   int64_t launches = 0;
   double flops_per_crop = 0;
-  std::vector<int> stage_chunks;   // built-in crop-chunk size per EfficientNet stage (index = stage, 0 = whole batch)
   // host-path staging
   void* stage = nullptr;
   size_t stage_bytes = 0;
@@ -567,7 +568,7 @@ int prepare_op_weights(mtb_handle* h, Op& op) {
 // --------------------------------------------------------------------------------------------- workspace
 struct Workspace {
   char* base;
-  int b0 = 0;  // first crop of the chunk being executed: big-buffer / feature tensors are addressed at their [b0:] slice
+  int b0 = 0;  // first crop the ops address (0: every op runs on the whole batch; kept for batch-slice experiments)
   size_t big_stride, small_stride;
   size_t off_small, off_features, off_logits, off_c2d, off_c3d, off_n2d, off_partial, total;
 };
@@ -599,7 +600,7 @@ void* buf_ptr(const Workspace& w, int id, void* features) {
   return w.base + w.off_small + w.small_stride * (id - BUF_SMALL0);
 }
 
-// activation tensor [B,hh,ww,cc] in buffer `id`, at the current chunk's first crop (small [B,C] buffers are per-chunk scratch)
+// activation tensor [B,hh,ww,cc] in buffer `id`, from crop w.b0 on (small [B,C] buffers are never sliced)
 void* act_ptr(const mtb_handle* h, const Workspace& w, int id, void* features, int hh, int ww, int cc) {
   char* base = (char*)buf_ptr(w, id, features);
   if (!base || id >= kNumBig) return base;
@@ -611,7 +612,9 @@ struct ProfScope {
   mtb_handle* h;
   cudaStream_t st;
   bool on;
-  ProfScope(mtb_handle* h_, int cls, double flops, double bytes, cudaStream_t st_) : h(h_), st(st_) {
+  // per_op = false keeps the launch out of the per-op table (the in-place SE scale pass is a class of its own; counting it
+  // under the projection GEMM's op index made that GEMM look twice as slow as it is)
+  ProfScope(mtb_handle* h_, int cls, double flops, double bytes, cudaStream_t st_, bool per_op = true) : h(h_), st(st_) {
     on = (h->prof_mask >> cls) & 1u;
     if (!on) return;
     if (h->prof_used + 2 > h->prof_events.size()) {
@@ -622,7 +625,7 @@ struct ProfScope {
       }
     }
     h->prof_cls.push_back(cls);
-    h->prof_op.push_back(h->prof_cur_op);
+    h->prof_op.push_back(per_op ? h->prof_cur_op : -1);
     h->prof_flops.push_back(flops);
     h->prof_bytes.push_back(bytes);
     cudaEventRecord(h->prof_events[h->prof_used], st);
@@ -640,6 +643,15 @@ bool se_fused_enabled() {  // MTB_SE_FUSED=1 enables the one-launch squeeze-exci
   if (v < 0) {
     const char* e = getenv("MTB_SE_FUSED");
     v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+bool se_cluster_enabled() {  // MTB_SE_CLUSTER=0: keep split-K fc1 + reduce + fc2 (three launches) for A/B runs
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTB_SE_CLUSTER");
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
 }
@@ -701,12 +713,12 @@ double op_bytes(const mtb_handle* h, const Op& op, int B) {
 template <typename T>
 int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Workspace& ws, void* features,
              cudaStream_t st) {
-  if (op.type == OP_CONV && op.tc.ready && op.scale_buf != BUF_NONE && !(tc_fuse_se() && op.R == 1 && op.stride == 1)) {
+  if (op.type == OP_CONV && op.tc.ready && op.scale_buf != BUF_NONE && !tc_can_fuse_se(op.R, op.stride, op.Cin)) {
     // squeeze-excitation scale applied in place ahead of a tensor-core conv that cannot fuse it (1x1 stride-1 projections
     // apply it to the A tiles in shared memory inside tc_conv_kernel)
     void* x = act_ptr(h, ws, op.in_buf, features, op.Hin, op.Win, op.Cin);
     const double bytes = 2.0 * B * op.Hin * op.Win * op.Cin * elem_size(h);
-    ProfScope ps(h, KC_SE_SCALE, 0.0, bytes, st);
+    ProfScope ps(h, KC_SE_SCALE, 0.0, bytes, st, false);
     const char* e = tc_se_scale_launch(x, (const float*)buf_ptr(ws, op.scale_buf, features), B, op.Hin * op.Win, op.Cin, st);
     if (e) return fail(h, MTB_ERR_CUDA, "se scale %s: %s", op.name.c_str(), e);
     h->launches++;
@@ -771,6 +783,20 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
       } else if (op.type == OP_MAXPOOL) {
         size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
         launch_k(maxpool_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, st, p);
+      } else if (op.small_io && op.se_fused && op.se_cluster) {
+        // squeeze-excitation fc1 + fc2 in one cluster launch over the partial pooling slices of the depthwise kernel
+        const Op& f2 = *(&op + 1);
+        const int slices = dw_pool_slices(h->ops[op.pool_src - 1]);
+        const size_t smem = sec_smem_bytes(op.Cin, op.Cout);
+        static bool attr_set = false;
+        if (!attr_set) {
+          cudaFuncSetAttribute(se_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sec_smem_bytes(SEC_MAX_C, 32 * SEC_MAX_JPL));
+          attr_set = true;
+        }
+        const int groups = (B + SEC_CB - 1) / SEC_CB;
+        launch_k(se_cluster_kernel, dim3(groups * SEC_CL), dim3(SEC_THREADS), smem, st, (const float*)p.in, slices, (size_t)B * op.Cin,
+                 (const float*)op.d_w, (const float*)op.d_bias, (const float*)f2.d_w, (const float*)f2.d_bias,
+                 (float*)buf_ptr(ws, f2.out_buf, features), B, op.Cin, op.Cout, op.act, f2.act);
       } else if (op.small_io && op.se_fused) {
         // squeeze-excitation fc1 + fc2 in one launch over the partial pooling slices of the depthwise kernel
         const Op& f2 = *(&op + 1);
@@ -842,51 +868,15 @@ int run_op(mtb_handle* h, const Op& op, const float* crops, int B, const Workspa
   return run_op_t<float>(h, op, crops, B, ws, features, st);
 }
 
-// Crop chunking: the ops of one EfficientNet stage run chunk by chunk (all ops of the stage on crops [b0, b0+n), then the
-// next chunk), so that a chunk's expanded / depthwise tensors are still in the 126 MB L2 when the next op of the block
-// reads them, instead of round-tripping through HBM at batch 256.  MTB_CHUNKS="c1,c2,..." gives the chunk (crops) per
-// stage, 0 = whole batch; unset = the built-in policy below.
-int stage_chunk(const mtb_handle* h, int stage, int B) {
-  static std::vector<int> env;
-  static bool parsed = false;
-  if (!parsed) {
-    parsed = true;
-    const char* e = getenv("MTB_CHUNKS");
-    if (e) {
-      env.push_back(-1);  // marks "explicit"
-      for (const char* q = e; *q;) {
-        env.push_back(atoi(q));
-        while (*q && *q != ',') ++q;
-        if (*q == ',') ++q;
-      }
-    }
-  }
-  if (stage <= 0 || h->cfg.precision != MTB_PRECISION_BF16_TC) return B;
-  int c = 0;
-  if (!env.empty()) c = stage < (int)env.size() ? env[stage] : 0;
-  else c = stage < (int)h->stage_chunks.size() ? h->stage_chunks[stage] : 0;
-  return (c <= 0 || c > B) ? B : c;
-}
-
+// Crop chunking (running a stage chunk by chunk so that its intermediates stay in the 126 MB L2) was built and measured
+// in round 1: 29.5 ms vs 22.7 ms per 256 crops - these kernels are latency / issue bound at 32-128 crops, not bandwidth
+// bound, so smaller launches lose more than L2 residency wins.  The executor therefore runs every op on the whole batch.
 int run_backbone(mtb_handle* h, const float* crops, int B, Workspace& ws, void* features, cudaStream_t st) {
-  const size_t n = h->ops.size();
-  size_t i = 0;
-  while (i < n) {
-    size_t j = i + 1;
-    while (j < n && h->ops[j].stage == h->ops[i].stage) ++j;
-    const int chunk = stage_chunk(h, h->ops[i].stage, B);
-    for (int b0 = 0; b0 < B; b0 += chunk) {
-      ws.b0 = b0;
-      const int nb = std::min(chunk, B - b0);
-      for (size_t k = i; k < j; ++k) {
-        h->prof_cur_op = (int)k;
-        int rc = run_op(h, h->ops[k], crops, nb, ws, features, st);
-        if (rc) { ws.b0 = 0; return rc; }
-      }
-    }
-    i = j;
+  for (size_t k = 0; k < h->ops.size(); ++k) {
+    h->prof_cur_op = (int)k;
+    int rc = run_op(h, h->ops[k], crops, B, ws, features, st);
+    if (rc) return rc;
   }
-  ws.b0 = 0;
   h->prof_cur_op = -1;
   return MTB_OK;
 }
@@ -1128,7 +1118,7 @@ int mtb_finalize_weights(mtb_handle* h) {
   DeviceGuard g(h->cfg.device);
   for (void* p : h->dev_allocs) cudaFree(p);
   h->dev_allocs.clear();
-  for (auto& op : h->ops) op.fused_pool = op.se_fused = op.se_skip = false;
+  for (auto& op : h->ops) op.fused_pool = op.se_fused = op.se_skip = op.se_cluster = false;
   for (size_t i = 0; i + 1 < h->ops.size(); ++i) {
     const bool fuse = h->cfg.precision == MTB_PRECISION_BF16_TC && dw_strip_eligible(h->ops[i]) && h->ops[i + 1].type == OP_POOL;
     if (fuse) h->ops[i].fused_pool = h->ops[i + 1].fused_pool = true;
@@ -1141,6 +1131,13 @@ int mtb_finalize_weights(mtb_handle* h) {
                       f1.Cout <= 32 * SE_MAX_JPL && f1.Cin % 4 == 0 && (size_t)f1.Cin * f1.Cout * 8 <= (2u << 20) &&
                       ((size_t)2 * f1.Cin + 34 * f1.Cout) * sizeof(float) <= 96 * 1024;
       if (ok) { f1.se_fused = true; f2.se_skip = true; }
+    }
+    if (fuse && i + 3 < h->ops.size() && se_cluster_enabled() && !h->ops[i + 2].se_fused) {
+      Op& f1 = h->ops[i + 2];
+      Op& f2 = h->ops[i + 3];
+      const bool ok = f1.small_io && f2.small_io && f1.pool_src == (int)i + 1 && f2.Cin == f1.Cout && f2.Cout == f1.Cin &&
+                      sec_eligible(f1.Cin, f1.Cout);
+      if (ok) { f1.se_fused = f1.se_cluster = true; f2.se_skip = true; }
     }
   }
   for (auto& op : h->ops) {

@@ -183,8 +183,8 @@ constexpr int TC_TILE_W = 16, TC_TILE_H = 8;        // spatial M tile of mode 1 
 constexpr int TC_PT_W = 8, TC_PT_H = 16, TC_PATCH_W = TC_PT_W + 2, TC_PATCH_H = TC_PT_H + 2;
 constexpr int TC_PLANE_BYTES = TC_PATCH_W * TC_PATCH_H * 16;   // 2880
 constexpr int TC_PATCH_MAX_PLANES = 12;                          // Cin <= 96
-constexpr int TC_THREADS = 416;  // warps 0-7 epilogue; 8 A producer / patch loader; 9 B producer; 10 MMA + TMEM; 11 patch loader /
-                                 // SE scaler; 12 SE scaler
+constexpr int TC_THREADS = 480;  // warps 0-7 epilogue; 8 A producer / patch loader; 9 B producer; 10 MMA + TMEM; 11 patch loader /
+                                 // SE scaler; 12-14 SE scalers
 constexpr int TCV_EPI_WARPS = 8;
 
 struct TcConvParams {
@@ -382,7 +382,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < TCV_MAX_STAGES; ++i) {
       mbar_init(&full[i], patch_mode ? 1 : 2);  // one arrive.expect_tx per TMA producer
       mbar_init(&empty[i], 1);                  // tcgen05.commit
-      mbar_init(&scaled[i], 2);                 // one arrive per scaler warp
+      mbar_init(&scaled[i], 4);                 // one arrive per scaler warp
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -433,9 +433,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int tr = 0;
     const int kchunks = pin(p.kchunks);
     TileWalk tw_(blockIdx.x, gridDim.x, p.n_tiles);
-    // K rotation: CTA i starts every tile's K loop at k-block (i mod num_kb) and wraps.  Without it all CTAs of a wave
-    // read the SAME weight k-block at the same time and the few L2 slices holding those lines serialise 148 requests
-    // per line (long-K / one-N-tile projection GEMMs ran at ~3000 cycles per k-block against ~460 of MMA work).
+    // K rotation (opt-in, MTB_TC_ROT=1): CTA i starts every tile's K loop at k-block (i mod num_kb) and wraps, so that the
+    // CTAs of a wave do not read the SAME weight k-block at the same time.  Hypothesis was L2 same-line serialisation on
+    // the long-K / one-N-tile projection GEMMs; measured: no change (2.354 vs 2.357 ms per 18 launches), so it is off.
     const int rot_kb = p.rot ? (int)(blockIdx.x % (unsigned)num_kb) : 0;
     if (p.mode == 0) {
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
@@ -644,55 +644,57 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   }
-  if ((warp == 11 || warp == 12) && p.a_scale != nullptr) {
-    // ===== squeeze-excitation scalers (mode 0): once the TMA has landed a stage, multiply its A tile IN SHARED MEMORY by
-    // s[crop(row)][k] (models the reference's `scale * x` ahead of the projection conv, backbones/efficientnet.py:110-173),
-    // then hand the stage to the MMA warp.  Thread t owns tile rows t and t+64. =====
-    const int lt = (warp - 11) * 32 + lane;  // 0..63
-    int stage = 0;
-    uint32_t phase = 0;
+  if (warp >= 11 && p.a_scale != nullptr) {
+    // ===== squeeze-excitation scalers (mode 0, BK = 64; warps 11-14): once the TMA has landed a stage, multiply its A tile
+    // IN SHARED MEMORY by s[crop(row)][k] (the reference's `scale * x` ahead of the projection conv,
+    // backbones/efficientnet.py:110-173; fp32 product rounded once to bf16 = bit-identical to se_scale_kernel), then hand
+    // the stage to the MMA warp.  Warp w owns tile rows [32w, 32w+32); a quarter-warp (8 lanes) covers one 128-byte row, so
+    // every 16-byte shared-memory access of the warp is bank-conflict free (thread-per-row, the first version, was 8-way
+    // conflicted and 2.5x slower than the separate pass). =====
+    const int sw = warp - 11;
+    const int sub = lane >> 3, pos = lane & 7;
+    uint32_t stage = 0, phase = 0;
+    const int kchunks = pin(p.kchunks), Cin = pin(p.Cin);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int m_blk = t / p.n_tiles;
-      const float* srow[2];
-      bool rok[2];
+      const int m0 = m_blk * TC_BM + sw * 32 + sub;
+      int soff[8];            // crop(row) * Cin for this thread's 8 rows (row = 32 sw + 4 it + sub)
+      uint32_t rok = 0;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int m = m_blk * TC_BM + lt + h * 64;
-        rok[h] = m < p.M;
-        srow[h] = p.a_scale + (size_t)(rok[h] ? m / p.a_scale_P : 0) * p.Cin;
+      for (int it = 0; it < 8; ++it) {
+        const int m = m0 + it * 4;
+        const bool ok = m < p.M;
+        rok |= ok ? (1u << it) : 0u;
+        soff[it] = (ok ? m / p.a_scale_P : 0) * Cin;
       }
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        mbar_wait_a(smem_u32(&full[stage]), phase);
-        uint8_t* sa = smem + stage * p.stage_stride;
+#pragma unroll 1
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait_a(full0 + stage * 8, phase);
+        uint8_t* sa = smem + stage * stage_stride + (sw * 32 + sub) * 128 + pos * 16;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int r = lt + h * 64;
-          if (!rok[h]) continue;
-          uint8_t* rowp = sa + r * (BK * 2);
+        for (int it = 0; it < 8; ++it) {
+          // 128B swizzle: logical 16-byte chunk (pos ^ (row & 7)) sits at physical position pos; row & 7 = 4 (it & 1) + sub
+          const int k = kc * 64 + ((pos ^ (((it & 1) << 2) | sub)) << 3);
+          if (!((rok >> it) & 1u) || k >= Cin) continue;  // K tail / M tail: the tile holds TMA zero fill there
+          uint4* ptr = reinterpret_cast<uint4*>(sa + it * 512);
+          uint4 v = *ptr;
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.a_scale + soff[it] + k));
+          const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.a_scale + soff[it] + k + 4));
+          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          unsigned wd[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int pos = 0; pos < BK / 8; ++pos) {
-            const int chunk = pos ^ (r & (BK / 8 - 1));          // swizzle: 16-byte chunk `chunk` sits at position `pos`
-            const int k = kc * BK + chunk * 8;
-            if (k >= p.Cin) continue;                            // K tail: the tile holds TMA zero fill there
-            uint4 v = *reinterpret_cast<uint4*>(rowp + pos * 16);
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(srow[h] + k));
-            const float4 s1 = __ldg(reinterpret_cast<const float4*>(srow[h] + k + 4));
-            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            unsigned wd[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float lo = __uint_as_float(wd[i] << 16) * sc[2 * i];
-              const float hi = __uint_as_float(wd[i] & 0xffff0000u) * sc[2 * i + 1];
-              __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
-              wd[i] = *reinterpret_cast<unsigned*>(&pk);
-            }
-            *reinterpret_cast<uint4*>(rowp + pos * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+          for (int i = 0; i < 4; ++i) {
+            const float lo = __uint_as_float(wd[i] << 16) * sc[2 * i];
+            const float hi = __uint_as_float(wd[i] & 0xffff0000u) * sc[2 * i + 1];
+            __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+            wd[i] = *reinterpret_cast<unsigned*>(&pk);
           }
+          *ptr = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         }
-        if (!(p.debug & 256)) fence_proxy_async();
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&scaled[stage]);
-        if (++stage == nstages) { stage = 0; phase ^= 1; }
+        if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; }
       }
     }
   }
@@ -990,6 +992,10 @@ struct TcWeights {
   mutable size_t map_rr = 0;
 };
 
+// MTB_FUSE_SE=1: the scaler warps of tc_conv_kernel apply the squeeze-excitation scale to the A tiles in shared memory.
+// Off by default - measured at 256 crops (r1): the projection GEMMs stream A from HBM with a 3-stage ring and are latency
+// bound (~2100 cycles per 44 KB stage); the scaling hand-off (full -> scaled -> MMA) lengthens every stage's round trip,
+// so the fused GEMMs got slower by as much as the separate se_scale_kernel pass costs (23.96 vs 22.65 ms per step).
 inline bool tc_fuse_se() {
   static int v = -1;
   if (v < 0) {
@@ -998,6 +1004,8 @@ inline bool tc_fuse_se() {
   }
   return v == 1;
 }
+// the scaler warps of tc_conv_kernel handle flat 1x1 GEMMs with 128-byte (BK = 64) A rows
+inline bool tc_can_fuse_se(int R, int stride, int cin) { return tc_fuse_se() && R == 1 && stride == 1 && cin > 32 && cin % 8 == 0; }
 
 inline bool tc_patch_disabled() {  // MTB_DISABLE_PATCH=1: 3x3 convs fall back to the per-tap TMA mode (A/B testing)
   static int v = -1;
@@ -1123,11 +1131,8 @@ inline const char* tc_conv_dispatch(int act, int res_mode, int grid, const CUten
 
 inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool res_first, cudaStream_t st) {
   TcConvParams q;
-  // Squeeze-excitation scale fused into the A tiles in shared memory (scaler warps 11-12): implemented and correct, but
-  // MEASURED SLOWER than the separate in-place pass (projection GEMMs 1.05 -> 2.5 ms per 24 launches at 128 crops: two
-  // warps cannot rescale a 16 KB tile within a k-block period, and the extra hand-off sits on the pipeline's critical
-  // path), so it is opt-in (MTB_FUSE_SE=1) and the default keeps se_scale_kernel.
-  q.a_scale = (tc_fuse_se() && p.R == 1 && p.stride == 1) ? p.a_scale : nullptr;
+  // Squeeze-excitation scale fused into the A tiles in shared memory (scaler warps 11-14; opt-in, see tc_fuse_se()).
+  q.a_scale = tc_can_fuse_se(p.R, p.stride, p.Cin) ? p.a_scale : nullptr;
   q.a_scale_P = p.Hin * p.Win;
   q.res = p.res; q.bias = w.d_bias;
   const int bk0 = p.Cin <= 32 ? 32 : 64;  // 64B-swizzled half-width stages only when they do not add k-blocks
@@ -1178,8 +1183,8 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
   }
   q.n_tiles = (p.Cout + bn - 1) / bn;
   {
-    static int rot_env = -1;  // MTB_TC_ROT=0 disables the K rotation (A/B measurements)
-    if (rot_env < 0) { const char* e = getenv("MTB_TC_ROT"); rot_env = (e && e[0] == '0') ? 0 : 1; }
+    static int rot_env = -1;  // MTB_TC_ROT=1 enables the K rotation (measured: no effect on the projection GEMMs, so off)
+    if (rot_env < 0) { const char* e = getenv("MTB_TC_ROT"); rot_env = (e && e[0] == '1') ? 1 : 0; }
     q.rot = (rot_env && q.mode != 2 && q.a_scale == nullptr) ? 1 : 0;
   }
   const TcWeights::MapSet* ms = nullptr;

@@ -158,3 +158,4 @@ def test_bf16_forward_deviation_is_reported(H):
         errs[prec] = (H.rel_err(feats, stages['features']), H.rel_err(out, ref))
     print('bf16 deviation from the fp32 oracle (features, joints):', errs)
     assert errs['bf16'][0] < max(3 * errs['bf16_simt'][0], 0.05)
+

@@ -31,6 +31,18 @@ inline bool pdl_enabled() {
   return v == 1;
 }
 
+// Scoped PDL for a chain of tiny dependent launches (the squeeze-excitation FCs): their launch latency, not their work, is
+// what the step pays for, and a small early-launched grid does not hold the SM slots a 210 KB tensor-core CTA would.
+inline int& pdl_force_depth() {
+  static thread_local int d = 0;
+  return d;
+}
+struct PdlScope {
+  bool on;
+  explicit PdlScope(bool enable) : on(enable) { if (on) ++pdl_force_depth(); }
+  ~PdlScope() { if (on) --pdl_force_depth(); }
+};
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -42,7 +54,7 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl_enabled() || pdl_force_depth() > 0) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 

@@ -319,11 +319,11 @@ inline const char* dw_tma_launch(DwTmaCache& cache, const DwTmaPlan& plan, const
   p.stage_bytes = 128 * (W + 2) * (plan.BH + 2) * plan.G;
   p.inv_hw = 1.0f / (float)(H * W);
   {
-    // Serpentine traversal (MTB_DW_REV=1, off unless measured faster): the expand GEMM before this op wrote its output
+    // Serpentine traversal (MTB_DW_REV=0 disables; measured 22.47 vs 22.58 ms per step): the expand GEMM before this op wrote its output
     // first-crop-to-last, so the END of the tensor is what the L2 still holds; walking the items last-to-first reads that
     // part from L2, and leaves the BEGINNING of this op's output in L2 for the projection GEMM that follows.
     static int rev_env = -1;
-    if (rev_env < 0) { const char* e = getenv("MTB_DW_REV"); rev_env = (e && e[0] == '1') ? 1 : 0; }
+    if (rev_env < 0) { const char* e = getenv("MTB_DW_REV"); rev_env = (e && e[0] == '0') ? 0 : 1; }
     p.rev = rev_env;
   }
   if (cache.in != in || cache.B != B) {

@@ -647,11 +647,15 @@ bool se_fused_enabled() {  // MTB_SE_FUSED=1 enables the one-launch squeeze-exci
   return v == 1;
 }
 
-bool se_cluster_enabled() {  // MTB_SE_CLUSTER=0: keep split-K fc1 + reduce + fc2 (three launches) for A/B runs
+// MTB_SE_CLUSTER=1: squeeze-excitation fc1 + fc2 as one 8-CTA-cluster launch (se_cluster.cuh).  Off by default - measured
+// at 256 crops (r1): 2.10 ms per step against 1.95 ms for split-K fc1 + reduce + fc2; every cluster re-reads both weight
+// matrices (32 clusters x 1.8 MB in stage 6) and those same-line L2 reads serialise, whereas the tiled fc GEMMs read each
+// weight from only four CTAs.  Variants (16 crops per cluster, fc2 slice prefetched by bulk copies) were slower still.
+bool se_cluster_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MTB_SE_CLUSTER");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
 }
@@ -710,15 +714,26 @@ double op_bytes(const mtb_handle* h, const Op& op, int B) {
 }
 
 // ---------------------------------------------------------------------------------------------- executor
+bool pdl_se_enabled() {  // MTB_PDL_SE=1: programmatic dependent launch for the squeeze-excitation chain only
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTB_PDL_SE");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <typename T>
 int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Workspace& ws, void* features,
              cudaStream_t st) {
+  PdlScope pdl_scope(pdl_se_enabled() && op.small_io);
   if (op.type == OP_CONV && op.tc.ready && op.scale_buf != BUF_NONE && !tc_can_fuse_se(op.R, op.stride, op.Cin)) {
     // squeeze-excitation scale applied in place ahead of a tensor-core conv that cannot fuse it (1x1 stride-1 projections
     // apply it to the A tiles in shared memory inside tc_conv_kernel)
     void* x = act_ptr(h, ws, op.in_buf, features, op.Hin, op.Win, op.Cin);
     const double bytes = 2.0 * B * op.Hin * op.Win * op.Cin * elem_size(h);
     ProfScope ps(h, KC_SE_SCALE, 0.0, bytes, st, false);
+    PdlScope pdl_scale(pdl_se_enabled());
     const char* e = tc_se_scale_launch(x, (const float*)buf_ptr(ws, op.scale_buf, features), B, op.Hin * op.Win, op.Cin, st);
     if (e) return fail(h, MTB_ERR_CUDA, "se scale %s: %s", op.name.c_str(), e);
     h->launches++;
@@ -787,16 +802,31 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
         // squeeze-excitation fc1 + fc2 in one cluster launch over the partial pooling slices of the depthwise kernel
         const Op& f2 = *(&op + 1);
         const int slices = dw_pool_slices(h->ops[op.pool_src - 1]);
-        const size_t smem = sec_smem_bytes(op.Cin, op.Cout);
+        // MTB_SE_CB (crops per cluster, 8 | 16) and MTB_SE_STAGE_W2 (prefetch the fc2 weight slice into shared memory) are
+        // A/B switches; the defaults are the measured best
+        static int cb_env = -1, st_env = -1;
+        if (cb_env < 0) { const char* e = getenv("MTB_SE_CB"); cb_env = (e && atoi(e) == 16) ? 16 : 8; }
+        if (st_env < 0) { const char* e = getenv("MTB_SE_STAGE_W2"); st_env = (e && e[0] == '1') ? 1 : 0; }
+        const int cb = cb_env;
+        bool stage_w2 = st_env && sec_stage_w2(op.Cin, op.Cout);
+        size_t smem = sec_smem_bytes(op.Cin, op.Cout, cb, stage_w2);
+        if (smem > 220 * 1024) { stage_w2 = false; smem = sec_smem_bytes(op.Cin, op.Cout, cb, false); }
         static bool attr_set = false;
         if (!attr_set) {
-          cudaFuncSetAttribute(se_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sec_smem_bytes(SEC_MAX_C, 32 * SEC_MAX_JPL));
+          cudaFuncSetAttribute(se_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+          cudaFuncSetAttribute(se_cluster_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
           attr_set = true;
         }
-        const int groups = (B + SEC_CB - 1) / SEC_CB;
-        launch_k(se_cluster_kernel, dim3(groups * SEC_CL), dim3(SEC_THREADS), smem, st, (const float*)p.in, slices, (size_t)B * op.Cin,
-                 (const float*)op.d_w, (const float*)op.d_bias, (const float*)f2.d_w, (const float*)f2.d_bias,
-                 (float*)buf_ptr(ws, f2.out_buf, features), B, op.Cin, op.Cout, op.act, f2.act);
+        const int groups = (B + cb - 1) / cb;
+        float* dst = (float*)buf_ptr(ws, f2.out_buf, features);
+        if (cb == 16)
+          launch_k(se_cluster_kernel<16>, dim3(groups * SEC_CL), dim3(SEC_THREADS), smem, st, (const float*)p.in, slices, (size_t)B * op.Cin,
+                   (const float*)op.d_w, (const float*)op.d_bias, (const float*)f2.d_w, (const float*)f2.d_bias, dst, B, op.Cin, op.Cout,
+                   op.act, f2.act, stage_w2 ? 1 : 0);
+        else
+          launch_k(se_cluster_kernel<8>, dim3(groups * SEC_CL), dim3(SEC_THREADS), smem, st, (const float*)p.in, slices, (size_t)B * op.Cin,
+                   (const float*)op.d_w, (const float*)op.d_bias, (const float*)f2.d_w, (const float*)f2.d_bias, dst, B, op.Cin, op.Cout,
+                   op.act, f2.act, stage_w2 ? 1 : 0);
       } else if (op.small_io && op.se_fused) {
         // squeeze-excitation fc1 + fc2 in one launch over the partial pooling slices of the depthwise kernel
         const Op& f2 = *(&op + 1);

@@ -13,21 +13,27 @@
 namespace mtb {
 
 constexpr int SEC_CL = 8;        // CTAs per cluster
-constexpr int SEC_CB = 8;        // crops per cluster
+constexpr int SEC_CB_MAX = 16;   // crops per cluster: template argument CB = 8 or 16
 constexpr int SEC_THREADS = 256;
 constexpr int SEC_MAX_JPL = 5;   // hidden units per lane: csq <= 160
 constexpr int SEC_MAX_C = 4096;
 
 inline int sec_slice(int C) { return ((C + 4 * SEC_CL - 1) / (4 * SEC_CL)) * 4; }
-inline size_t sec_smem_bytes(int C, int csq) {
-  return ((size_t)SEC_CB * sec_slice(C) + (size_t)(SEC_THREADS / 32) * SEC_CB * csq + 2 * (size_t)SEC_CB * csq) * sizeof(float);
+inline size_t sec_base_floats(int C, int csq, int cb) {
+  return (size_t)cb * sec_slice(C) + (size_t)(SEC_THREADS / 32) * cb * csq + 2 * (size_t)cb * csq;
+}
+// the CTA's fc2 weight slice [csq][KS] is prefetched into shared memory by bulk copies when it fits (<= 128 KB)
+inline bool sec_stage_w2(int C, int csq) { return (size_t)csq * sec_slice(C) * sizeof(float) <= 128 * 1024; }
+inline size_t sec_smem_bytes(int C, int csq, int cb, bool stage_w2) {
+  return (sec_base_floats(C, csq, cb) + (stage_w2 ? (size_t)csq * sec_slice(C) : 0)) * sizeof(float) + 16;
 }
 inline bool sec_eligible(int C, int csq) { return C % 4 == 0 && csq % 4 == 0 && csq <= 32 * SEC_MAX_JPL && C <= SEC_MAX_C; }
 
+template <int SEC_CB>
 __global__ void __cluster_dims__(SEC_CL, 1, 1) __launch_bounds__(SEC_THREADS)
 se_cluster_kernel(const float* __restrict__ pooled, int slices, size_t slice_stride, const float* __restrict__ w1,
                   const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
-                  float* __restrict__ scale, int B, int C, int csq, int act1, int act2) {
+                  float* __restrict__ scale, int B, int C, int csq, int act1, int act2, int stage_w2) {
   pdl_trigger();
   pdl_wait();
   namespace cg = cooperative_groups;
@@ -43,6 +49,26 @@ se_cluster_kernel(const float* __restrict__ pooled, int slices, size_t slice_str
   float* hcta = hp + NW * SEC_CB * csq;        // [CB][csq]  this CTA's fc1 partial (read by the whole cluster)
   float* hid = hcta + SEC_CB * csq;            // [CB][csq]  hidden activations (complete)
   const int k0 = rank * KS, k1 = min(k0 + KS, C);
+  // fc2 weight slice w2[:, k0:k1] -> shared memory, one bulk copy per hidden unit, in flight during the squeeze and fc1
+  // (the fc2 loop was a chain of dependent L2 round trips: 96-160 rows x ~800 cycles with four loads in flight)
+  float* w2s = hid + SEC_CB * csq;             // [csq][KS]
+  __shared__ __align__(8) unsigned long long w2_bar;
+  const int nw2 = k1 > k0 ? k1 - k0 : 0;       // floats per row of the slice (multiple of 4)
+  if (stage_w2 && nw2 > 0) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&w2_bar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&w2_bar)),
+                   "r"((unsigned)(csq * nw2 * 4))
+                   : "memory");
+    }
+    __syncthreads();
+    for (int j = tid; j < csq; j += SEC_THREADS)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       (unsigned)__cvta_generic_to_shared(w2s + (size_t)j * KS)),
+                   "l"(w2 + (size_t)j * C + k0), "r"((unsigned)(nw2 * 4)), "r"((unsigned)__cvta_generic_to_shared(&w2_bar))
+                   : "memory");
+  }
 
   // squeezed input: sum of the depthwise kernel's partial-mean slices
   for (int i = tid; i < SEC_CB * KS; i += SEC_THREADS) {
@@ -67,7 +93,7 @@ se_cluster_kernel(const float* __restrict__ pooled, int slices, size_t slice_str
     // Each cluster therefore starts its row loop at its own rotation (fixed per cluster: still deterministic).
     const int nrows = k1 > k0 + warp ? (k1 - k0 - warp + NW - 1) / NW : 0;
     int ri = nrows > 0 ? (int)((blockIdx.x / SEC_CL) * 5u % (unsigned)nrows) : 0;
-#pragma unroll 4
+#pragma unroll 8
     for (int n = 0; n < nrows; ++n) {
       const int k = k0 + warp + ri * NW;
       if (++ri == nrows) ri = 0;
@@ -106,6 +132,14 @@ se_cluster_kernel(const float* __restrict__ pooled, int slices, size_t slice_str
     hid[i] = apply_act(v, act1);
   }
   cluster.sync();  // every remote read of hcta is done (a CTA may exit) and hid is visible to this CTA's threads
+  if (stage_w2 && nw2 > 0) {  // the weight slice has landed
+    unsigned ok = 0;
+    while (!ok)
+      asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], 0;\nselp.u32 %0, 1, 0, P1;\n}\n"
+                   : "=r"(ok)
+                   : "r"((unsigned)__cvta_generic_to_shared(&w2_bar))
+                   : "memory");
+  }
   // fc2 over this CTA's N slice: thread = (channel quad, half of the crops); rows of w2 are C contiguous floats
   const int n1 = min(k0 + KS, C);
   const int nq = n1 > k0 ? (n1 - k0) >> 2 : 0;
@@ -117,9 +151,10 @@ se_cluster_kernel(const float* __restrict__ pooled, int slices, size_t slice_str
 #pragma unroll
     for (int c = 0; c < SEC_CB / 2; ++c) o[c] = bv;
     int j = (int)((blockIdx.x / SEC_CL) * 7u % (unsigned)csq);  // per-cluster rotation of the row order (see fc1)
-#pragma unroll 4
+#pragma unroll 8
     for (int jj = 0; jj < csq; ++jj) {
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(w2 + (size_t)j * C + n));
+      const float4 wv = stage_w2 ? *reinterpret_cast<const float4*>(w2s + (size_t)j * KS + q * 4)
+                                 : __ldg(reinterpret_cast<const float4*>(w2 + (size_t)j * C + n));
 #pragma unroll
       for (int c = 0; c < SEC_CB / 2; ++c) {
         const float hv = hid[(cbase + c) * csq + j];

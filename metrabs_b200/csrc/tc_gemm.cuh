@@ -214,6 +214,7 @@ struct TcConvParams {
   int bk;       // K elements per ring stage (host-side copy of the BK template argument)
   int trace_cta; // the CTA that writes the clock64 trace
   int rot;       // modes 0 / 1: rotate the start of each CTA's K loop (see the A producer); 0 with the fused SE scalers
+  int epi_single;  // mode 0, long K: ONE epilogue slab per warp; the freed 32 KB extend the operand ring to 176 KB
 };
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -763,7 +764,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===== epilogue =====
     const int q = warp & 3, par = warp >> 2;
     const int row = q * 32 + lane;
-    uint8_t* slabs = smem + TCV_EPI_OFF + warp * 2 * TCV_SLAB_BYTES;
+    // long-K GEMMs (epi_single) run an epilogue once per >= 8 k-blocks: one staging slab per warp is enough there, and the
+    // other 32 KB buy one more operand stage in flight (those GEMMs stream A from HBM and are bound by bytes in flight)
+    uint8_t* slabs = p.epi_single ? smem + TCV_EPI_OFF + 8 * TCV_SLAB_BYTES + warp * TCV_SLAB_BYTES
+                                  : smem + TCV_EPI_OFF + warp * 2 * TCV_SLAB_BYTES;
     float* bias_s = (float*)(smem + TCV_BIAS_OFF + warp * 256);
     int acc = 0, etr = 0, tile_i = 0;
     uint32_t acc_phase = 0, slab_count = 0;
@@ -805,8 +809,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane * 4 < ncols) bv = *reinterpret_cast<const float4*>(p.bias + n0 + c0 + lane * 4);
           *reinterpret_cast<float4*>(bias_s + lane * 4) = bv;
         }
-        uint8_t* slab = slabs + (slab_count & 1) * TCV_SLAB_BYTES;
-        if (lane == 0) tma_store_wait_read<1>();  // the store that last read this slab (2 chunks ago) is done with it
+        uint8_t* slab = slabs + (p.epi_single ? 0u : (slab_count & 1)) * TCV_SLAB_BYTES;
+        if (lane == 0) {  // the store that last read this slab (2 chunks ago; the previous one with a single slab) is done with it
+          if (p.epi_single) tma_store_wait_read<0>();
+          else tma_store_wait_read<1>();
+        }
         __syncwarp();
         // two halves of 32 columns (keeps the live register set under the 128-register budget of a 416-thread CTA)
 #pragma unroll
@@ -1174,7 +1181,18 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
         num_kb * q.stage_stride + 4 * q.patch_bytes <= TCV_RING_BYTES)
       q.npatch = 4;
     q.patch_off = TCV_RING_BYTES - q.npatch * q.patch_bytes;
-    const int ring = q.mode == 2 ? q.patch_off : TCV_RING_BYTES;
+    int ring = q.mode == 2 ? q.patch_off : TCV_RING_BYTES;
+    q.epi_single = 0;
+    {
+      static int es_env = -1;  // MTB_TC_EPI_SINGLE=0 keeps the double-buffered epilogue slabs everywhere (A/B runs)
+      if (es_env < 0) { const char* e = getenv("MTB_TC_EPI_SINGLE"); es_env = (e && e[0] == '0') ? 0 : 1; }
+      const int ring_ext = TCV_RING_BYTES + 8 * TCV_SLAB_BYTES;
+      if (es_env && q.mode == 0 && num_kb >= 8 && ring_ext / q.stage_stride > ring / q.stage_stride &&
+          ring / q.stage_stride < TCV_MAX_STAGES) {
+        q.epi_single = 1;
+        ring = ring_ext;
+      }
+    }
     q.nstages = ring / q.stage_stride;
     if (q.nstages > TCV_MAX_STAGES) q.nstages = TCV_MAX_STAGES;
     if (q.nstages < 2) return "operand ring too small for this tile";

@@ -13,7 +13,9 @@ P = os.path.join(ROOT, 'profiles')
 tag = sys.argv[1] if len(sys.argv) > 1 else 'r1'
 
 KEYS = ['ID', 'Kernel Name', 'Grid Size', 'Block Size', 'gpu__time_duration.sum', 'dram__bytes_read.sum',
-        'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'dram__bytes_write.sum', 'lts__t_sector_hit_rate.pct', 'l1tex__m_xbar2l1tex_read_bytes.sum',
+        'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'launch__registers_per_thread', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
@@ -24,9 +26,13 @@ KEYS = ['ID', 'Kernel Name', 'Grid Size', 'Block Size', 'gpu__time_duration.sum'
 
 def full_summary(rep, out):
     path = os.path.join(G, rep)
-    if not os.path.exists(path):
+    pre = path.replace('.ncu-rep', '.raw.csv')   # raw page exported on the GPU box (the report itself was too big to bring back)
+    if os.path.exists(path):
+        raw = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    elif os.path.exists(pre):
+        raw = open(pre).read()
+    else:
         return
-    raw = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr = rows[0]
     idx = [hdr.index(k) for k in KEYS if k in hdr]
@@ -92,6 +98,10 @@ launch_list('bench_launches.csv', f'{tag}_bench_launch_list_ncu.csv', f'{tag}_be
 full_summary('tc_conv_r1_final.ncu-rep', f'{tag}_tc_conv_kernel_ncu_full_summary.csv')
 full_summary('dwconv_r1.ncu-rep', f'{tag}_dwconv3x3_pool_kernel_ncu_full_summary.csv')
 full_summary('softargmax_r1.ncu-rep', f'{tag}_softargmax_and_fused_head_ncu_full_summary.csv')
+# captures of the re-entry session: TMA-staged depthwise kernel and the stage-5 projection GEMM (1344 -> 224, one N tile)
+full_summary('r1_dw_tma.ncu-rep', f'{tag}_dw3x3s1_tma_kernel_ncu_full_summary.csv')
+full_summary('r1_dw_tma_v2.ncu-rep', f'{tag}_dw3x3s1_tma_kernel_ffma2_ncu_full_summary.csv')
+full_summary('r1_tc_project.ncu-rep', f'{tag}_tc_conv_kernel_projection_1344x224_ncu_full_summary.csv')
 hs = os.path.join(G, 'head_sweep.jsonl')
 if os.path.exists(hs):
     with open(hs) as f, open(os.path.join(P, f'{tag}_head_sweep.jsonl'), 'w') as o:

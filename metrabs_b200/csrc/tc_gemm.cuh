@@ -792,14 +792,27 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         valid = oh < p.Hout && ow < p.Wout;
         off = ((size_t)(b * p.Hout + oh) * p.Wout + ow) * p.Cout;
       }
+      const int nchunks = (n_valid + 63) >> 6;
+      const int ch_first = par ^ (nchunks == 1 ? (tile_i & 1) : 0);
+      // residual of this warp's FIRST half-chunk of the tile: issued BEFORE the accumulator wait, so its HBM round trip
+      // overlaps the tile's MMAs instead of starting when they end (the 32->32 stage-1 conv has one half-chunk per tile:
+      // its whole epilogue latency was this load)
+      uint4 rv_pre[4];
+      if constexpr (RES != 0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          rv_pre[g] = make_uint4(0u, 0u, 0u, 0u);
+          if (ch_first < nchunks && valid && ch_first * 64 + g * 8 < n_valid && !(p.debug & 4))
+            rv_pre[g] = *reinterpret_cast<const uint4*>(res + off + n0 + ch_first * 64 + g * 8);
+        }
+      }
       mbar_wait_a(smem_u32(&tmem_full[acc]), acc_phase);
       tc_fence_after();
       if (p.trace && (int)blockIdx.x == p.trace_cta && threadIdx.x == 0 && etr < 256) p.trace[512 + etr++] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_MAX_BN;
-      const int nchunks = (n_valid + 63) >> 6;
       bool released = false;
       // two warp groups (par 0 / 1) alternate the 64-column chunks; one-chunk tiles alternate between the groups tile by tile
-      for (int ch = par ^ (nchunks == 1 ? (tile_i & 1) : 0); ch < nchunks && !(p.debug & 128); ch += 2) {
+      for (int ch = ch_first; ch < nchunks && !(p.debug & 128); ch += 2) {
         const int c0 = ch * 64;
         const int ncols = min(64, n_valid - c0);  // multiple of 8
         // bias of the chunk -> this warp's staging (64 floats), broadcast-read below
@@ -825,7 +838,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               rv[g] = make_uint4(0u, 0u, 0u, 0u);
-              if (valid && cb + g * 8 < ncols && !(p.debug & 4)) rv[g] = *reinterpret_cast<const uint4*>(res + off + n0 + c0 + cb + g * 8);
+              if (hf == 0 && ch == ch_first) rv[g] = rv_pre[g];
+              else if (valid && cb + g * 8 < ncols && !(p.debug & 4)) rv[g] = *reinterpret_cast<const uint4*>(res + off + n0 + c0 + cb + g * 8);
             }
           }
           uint32_t v[32];

@@ -158,6 +158,21 @@ class Engine:
                                 _stream_ptr(self.device)), self._h)
         return out
 
+    def capture_forward(self, crops, intrinsics, out):
+        """Captures one forward on fixed device buffers into a CUDA graph (mtb_forward never synchronises or allocates, so
+        the ~290 launches of a step replay as one graph launch without the per-launch gaps of stream submission).
+        Returns an object with ``replay()``; refill ``crops`` / ``intrinsics`` in place between replays and read ``out``.
+        Run at least one plain ``forward`` on the same buffers first (tensor maps, kernel attributes, workspace)."""
+        b, s = crops.shape[0], self.cfg.proc_side
+        crops = self._check_in(crops, (b, 3, s, s))
+        k = self._check_in(intrinsics, (b, 3, 3))
+        self.workspace(b)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.forward(crops, k, out=out)
+        graph._mtb_keepalive = (crops, k, out)
+        return graph
+
     def forward_host(self, crops_host, intrinsics_host, out_host=None):
         """End-to-end call on HOST tensors (pinned for full-speed copies): H2D + forward + D2H + stream sync."""
         b = crops_host.shape[0]

@@ -41,9 +41,8 @@ def parse():
     ap.add_argument('--precision', default=os.environ.get('MTB_BENCH_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
     ap.add_argument('--cpu-sample', type=int, default=8, help='crops per CPU-baseline forward')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--graph', type=int, default=int(os.environ.get('MTB_BENCH_GRAPH', '1')),
-                    help='1 (default): the `value` region replays the forward from a CUDA graph (Engine.capture_forward; '
-                         'mtb_forward never syncs or allocates); 0: plain stream launches')
+    ap.add_argument('--graph', type=int, default=int(os.environ.get('MTB_BENCH_GRAPH', '0')),
+                    help='1: replay the forward from a CUDA graph in the `value` region (mtb_forward never syncs or allocates)')
     return ap.parse_args()
 
 
@@ -284,6 +283,12 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    graph = None
+    if args.graph and world == 1:
+        step()
+        torch.cuda.synchronize()
+        graph = eng.capture_forward(crops_d, k_d, out_d)
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -297,51 +302,33 @@ def run_b200(args):
     dom_name = max(prof_all, key=lambda n: prof_all[n]['ms'])
     dom_cls = prof_all[dom_name]['cls']
     total_ms_all = sum(v['ms'] for v in prof_all.values())
-    launches_per_step = eng.last_launch_count + (1 if world > 1 else 0)
 
-    # The timed region replays the forward from a CUDA graph (the launches of a step become one graph launch; the joints
-    # all-gather of the multi-GPU path stays a stream launch behind it).  The dominant kernel class is bracketed by
-    # cudaEventRecord pairs INSIDE the captured forward (event-record nodes), so after the K replays those events hold
-    # the per-launch times of the last timed step.  Anything going wrong in capture falls back to plain stream launches.
     barrier()
-    graph = None
-    if args.graph:
-        try:
-            eng.profile_begin([dom_cls])
-            graph = eng.capture_forward(crops_d, k_d, out_d)
-            for _ in range(2):
-                graph.replay()
-            torch.cuda.synchronize()
-        except Exception as e:  # noqa: BLE001
-            print(f'bench: CUDA-graph capture failed ({e!r}); timing plain stream launches', file=sys.stderr)
-            graph = None
-            try:
-                eng.profile_end()
-            except Exception:  # noqa: BLE001
-                pass
-            torch.cuda.synchronize()
-    if graph is None:
-        eng.profile_begin([dom_cls])
-
-    def timed_step():
-        if graph is not None:
+    graph_ms = None
+    if graph is not None:  # CUDA-graph replay of the same K steps (no per-kernel events inside): reported beside `value`
+        for _ in range(2):
             graph.replay()
-            if world > 1:
-                return eng.allgather(out_d)
-            return out_d
-        return step()
-
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        g0.record()
+        for _ in range(args.steps):
+            graph.replay()
+        g1.record()
+        torch.cuda.synchronize()
+        graph_ms = g0.elapsed_time(g1)
+    eng.profile_begin([dom_cls])
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_begin = sampler.mark()
     ev0.record()
+    launches = 0
     for _ in range(args.steps):
-        timed_step()
+        step()
+        launches += eng.last_launch_count + (1 if world > 1 else 0)
     ev1.record()
     barrier()
     t_end = sampler.mark()
     elapsed_ms = ev0.elapsed_time(ev1)
-    launches = launches_per_step * args.steps
     prof_dom = eng.profile_end()[dom_name]
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
 
@@ -390,8 +377,7 @@ def run_b200(args):
                    'backbone_gflop_per_crop': flops_crop / 1e9,
                    'tensor_util_of_peak': value / world * flops_crop / 1e12 / pk['tflops'],
                    'peaks': pk['source'],
-                   'submission': 'CUDA graph replay of the forward (Engine.capture_forward)' if graph is not None
-                   else 'plain stream launches'},
+                   'cuda_graph_replay_crops_per_s': (world * B * args.steps / (graph_ms / 1e3)) if graph_ms else None},
         'e2e': {'value': e2e, 'unit': 'crops/s', 'h2d_bytes_per_step': B * 3 * S * S * 4 + B * 36,
                 'd2h_bytes_per_step': B * J * 3 * 4},
         'gpu_launches': launches,

@@ -148,6 +148,16 @@ int mtb_forward(mtb_handle* h, const float* crops, const float* intrinsics, int 
 int mtb_forward_host(mtb_handle* h, const float* host_crops, const float* host_intrinsics, int batch,
                      float* host_coords3d_abs, void* stream);
 
+/* Pipelined form of the same call for back-to-back batches (the reference's caller feeds chunk after chunk,
+ * multiperson_model.py:190-207): `submit` enqueues the H2D copies of this batch on an internal copy stream and the forward +
+ * joints read-back on `stream` behind them, and returns without synchronising; `wait` blocks until that slot's joints are
+ * in `host_coords3d_abs`.  Two slots (0/1): submit batch i+1 on the other slot before waiting for batch i, and its
+ * host->device copy overlaps batch i's forward.  Host buffers must be pinned for the copies to be asynchronous and must
+ * stay valid until the matching wait. */
+int mtb_forward_host_submit(mtb_handle* h, const float* host_crops, const float* host_intrinsics, int batch,
+                            float* host_coords3d_abs, int slot, void* stream);
+int mtb_forward_host_wait(mtb_handle* h, int slot);
+
 /* Multi-GPU: crops shard across ranks; one all-gather of the decoded joints over NVLink.
  * mtb_comm_* wrap a NCCL communicator owned by the handle (libnccl is dlopen'ed). */
 int mtb_comm_unique_id(void* id128 /* host, 128 bytes */);

@@ -53,6 +53,8 @@ _SIGNATURES = {
     'mtb_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                               C.c_void_p]),
     'mtb_forward_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    'mtb_forward_host_submit': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    'mtb_forward_host_wait': (C.c_int, [C.c_void_p, C.c_int]),
     'mtb_comm_unique_id': (C.c_int, [C.c_void_p]),
     'mtb_comm_init': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     'mtb_allgather_joints': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

@@ -94,6 +94,17 @@ struct mtb_handle {
   void* stage = nullptr;
   size_t stage_bytes = 0;
   int stage_batch = 0;
+  // pipelined host path (mtb_forward_host_submit / _wait): two input/output slots, one shared workspace, a copy stream
+  struct HostSlot {
+    void* buf = nullptr;       // [crops | intrinsics | joints] device staging of this slot
+    size_t bytes = 0;
+    cudaEvent_t h2d_done = nullptr, done = nullptr;
+    bool used = false;         // `done` has been recorded at least once
+  };
+  HostSlot slots[2];
+  void* pipe_ws = nullptr;
+  size_t pipe_ws_bytes = 0;
+  cudaStream_t copy_stream = nullptr;
   // profiler
   unsigned prof_mask = 0;
   std::vector<cudaEvent_t> prof_events;  // pairs
@@ -1087,6 +1098,14 @@ int mtb_destroy(mtb_handle* h) {
       cudaError_t e = cudaFree(h->stage);
       if (trace) fprintf(stderr, "mtb_destroy: stage freed (%s)\n", cudaGetErrorString(e));
     }
+    for (auto& sl : h->slots) {
+      if (sl.buf) cudaFree(sl.buf);
+      if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
+      if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (h->pipe_ws) cudaFree(h->pipe_ws);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    cudaGetLastError();
     for (size_t i = 0; i < h->prof_events.size(); ++i) {
       cudaError_t e = cudaEventDestroy(h->prof_events[i]);
       if (trace && (i < 2 || e != cudaSuccess)) fprintf(stderr, "mtb_destroy: event %zu destroyed (%s)\n", i, cudaGetErrorString(e));
@@ -1350,7 +1369,6 @@ int mtb_forward_host(mtb_handle* h, const float* host_crops, const float* host_i
   if (need > h->stage_bytes) {  // grows only when a larger batch than ever before arrives
     CUDA_TRY(h, cudaStreamSynchronize(st));
     if (h->stage) cudaFree(h->stage);
-  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     h->stage = nullptr;
     h->stage_bytes = 0;
     CUDA_TRY(h, cudaMalloc(&h->stage, need));
@@ -1367,6 +1385,66 @@ int mtb_forward_host(mtb_handle* h, const float* host_crops, const float* host_i
   if (rc) return rc;
   CUDA_TRY(h, cudaMemcpyAsync(host_coords3d_abs, d_out, (size_t)batch * h->cfg.n_joints * 3 * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(h, cudaStreamSynchronize(st));
+  return MTB_OK;
+}
+
+int mtb_forward_host_submit(mtb_handle* h, const float* host_crops, const float* host_intrinsics, int batch,
+                            float* host_coords3d_abs, int slot, void* stream) {
+  if (!h) return fail(nullptr, MTB_ERR_INVALID_ARG, "null handle");
+  if (!h->finalized) return fail(h, MTB_ERR_NOT_FINALIZED, "mtb_finalize_weights has not been called");
+  if (!host_crops || !host_intrinsics || !host_coords3d_abs || batch <= 0 || slot < 0 || slot > 1)
+    return fail(h, MTB_ERR_INVALID_ARG, "null/invalid argument");
+  DeviceGuard g(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t S = h->cfg.proc_side;
+  const size_t crops_b = align_up((size_t)batch * 3 * S * S * 4, 1024), k_b = align_up((size_t)batch * 9 * 4, 1024),
+               out_b = align_up((size_t)batch * h->cfg.n_joints * 3 * 4, 1024);
+  const size_t ws_b = layout(h, batch, nullptr).total;
+  mtb_handle::HostSlot& sl = h->slots[slot];
+  if (!h->copy_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  if (!sl.h2d_done) {
+    CUDA_TRY(h, cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  }
+  if (crops_b + k_b + out_b > sl.bytes || ws_b > h->pipe_ws_bytes) {  // grows only when a larger batch than ever before arrives
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    if (crops_b + k_b + out_b > sl.bytes) {
+      if (sl.buf) cudaFree(sl.buf);
+      sl.buf = nullptr; sl.bytes = 0;
+      CUDA_TRY(h, cudaMalloc(&sl.buf, crops_b + k_b + out_b));
+      sl.bytes = crops_b + k_b + out_b;
+    }
+    if (ws_b > h->pipe_ws_bytes) {
+      if (h->pipe_ws) cudaFree(h->pipe_ws);
+      h->pipe_ws = nullptr; h->pipe_ws_bytes = 0;
+      CUDA_TRY(h, cudaMalloc(&h->pipe_ws, ws_b));
+      h->pipe_ws_bytes = ws_b;
+    }
+  }
+  char* base = (char*)sl.buf;
+  float* d_crops = (float*)base;
+  float* d_k = (float*)(base + crops_b);
+  float* d_out = (float*)(base + crops_b + k_b);
+  // copy stream: this slot's staging is free once its previous forward + read-back have completed
+  if (sl.used) CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, sl.done, 0));
+  CUDA_TRY(h, cudaMemcpyAsync(d_crops, host_crops, (size_t)batch * 3 * S * S * 4, cudaMemcpyHostToDevice, h->copy_stream));
+  CUDA_TRY(h, cudaMemcpyAsync(d_k, host_intrinsics, (size_t)batch * 9 * 4, cudaMemcpyHostToDevice, h->copy_stream));
+  CUDA_TRY(h, cudaEventRecord(sl.h2d_done, h->copy_stream));
+  // compute stream: forward of this step behind its own copy (and behind the previous step's forward: one workspace)
+  CUDA_TRY(h, cudaStreamWaitEvent(st, sl.h2d_done, 0));
+  int rc = mtb_forward(h, d_crops, d_k, batch, d_out, h->pipe_ws, h->pipe_ws_bytes, stream);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(host_coords3d_abs, d_out, (size_t)batch * h->cfg.n_joints * 3 * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaEventRecord(sl.done, st));
+  sl.used = true;
+  return MTB_OK;
+}
+
+int mtb_forward_host_wait(mtb_handle* h, int slot) {
+  if (!h || slot < 0 || slot > 1) return fail(h, MTB_ERR_INVALID_ARG, "null handle / invalid slot");
+  DeviceGuard g(h->cfg.device);
+  if (!h->slots[slot].used) return MTB_OK;
+  CUDA_TRY(h, cudaEventSynchronize(h->slots[slot].done));
   return MTB_OK;
 }
 

@@ -186,6 +186,20 @@ class Engine:
                                      out_host.data_ptr(), _stream_ptr(self.device)), self._h)
         return out_host
 
+    def forward_host_submit(self, crops_host, intrinsics_host, out_host, slot):
+        """Pipelined end-to-end call (mtb_forward_host_submit): enqueues H2D (copy stream) + forward + D2H for this batch on
+        slot 0/1 and returns at once.  Host tensors must be pinned fp32 contiguous and stay alive until
+        ``forward_host_wait(slot)``; submit the next batch on the other slot before waiting and its copy overlaps this
+        batch's forward."""
+        for t in (crops_host, intrinsics_host, out_host):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError('forward_host_submit takes contiguous fp32 host tensors')
+        check(lib().mtb_forward_host_submit(self._h, crops_host.data_ptr(), intrinsics_host.data_ptr(), crops_host.shape[0],
+                                            out_host.data_ptr(), int(slot), _stream_ptr(self.device)), self._h)
+
+    def forward_host_wait(self, slot):
+        check(lib().mtb_forward_host_wait(self._h, int(slot)), self._h)
+
     # ---- multi-GPU ------------------------------------------------------------------------------------------
     def comm_init(self, rank, world_size, broadcast_fn):
         """``broadcast_fn(bytes_or_None) -> bytes`` distributes rank 0's 128-byte NCCL unique id."""

@@ -137,6 +137,20 @@ def test_tiny_model_golden(H, golden_dir, fname):
     out_h = eng.forward_host(crops.pin_memory(), k.pin_memory())
     assert torch.equal(out_h, out.cpu())  # the path is deterministic (split-K partials are summed in a fixed order)
     assert eng.last_launch_count > 0
+    # pipelined host entry points (two slots, copy stream): the next batch is submitted before the previous one is waited
+    # for, slots are reused, and every batch's joints equal the synchronous call's bit for bit
+    ch, kh = crops.float().contiguous().pin_memory(), k.float().contiguous().pin_memory()
+    outs = [torch.empty(out_h.shape, dtype=torch.float32).pin_memory() for _ in range(2)]
+    eng.forward_host_submit(ch, kh, outs[0], 0)
+    eng.forward_host_submit(ch, kh, outs[1], 1)
+    eng.forward_host_wait(0)
+    eng.forward_host_wait(1)
+    eng.forward_host_wait(0)  # waiting twice is harmless
+    assert torch.equal(outs[0], out_h) and torch.equal(outs[1], out_h)
+    outs[0].zero_()
+    eng.forward_host_submit(ch, kh, outs[0], 0)
+    eng.forward_host_wait(0)
+    assert torch.equal(outs[0], out_h)
 
 
 @pytest.mark.parametrize('name,side,j,batch,fname', [

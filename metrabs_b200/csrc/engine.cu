@@ -1365,7 +1365,7 @@ static int forward_body(mtb_handle* h, const float* crops, const float* intrinsi
 }
 
 // MTB_GRAPH=1 (opt-in until measured on the GPU box): mtb_forward captures its own launches into a CUDA graph the second
-// time it sees the same (buffers, batch, stream) and replays that graph from then on - the ~660 launches of a step were
+// time it sees the same (buffers, batch, stream) and replays that graph from then on - the 465 launches of a step were
 // 8-9 % faster as one graph launch than as stream submissions (bench.py --graph 1).  A profiling window bypasses it
 // (events cannot be timed inside a graph), any capture failure falls back to plain launches for that key.
 static bool graph_enabled() {

@@ -160,7 +160,7 @@ class Engine:
 
     def capture_forward(self, crops, intrinsics, out):
         """Captures one forward on fixed device buffers into a CUDA graph (mtb_forward never synchronises or allocates, so
-        the ~290 launches of a step replay as one graph launch without the per-launch gaps of stream submission).
+        the ~465 launches of a step replay as one graph launch without the per-launch gaps of stream submission).
         Returns an object with ``replay()``; refill ``crops`` / ``intrinsics`` in place between replays and read ``out``.
         Run at least one plain ``forward`` on the same buffers first (tensor maps, kernel attributes, workspace)."""
         b, s = crops.shape[0], self.cfg.proc_side

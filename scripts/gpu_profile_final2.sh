@@ -12,7 +12,7 @@ echo "=== bench c3 EffNetV2-L@384, 32 crops/GPU"; timeout 600 python bench.py --
 timeout 600 python scripts/head_sweep.py > gpurun_out/head_sweep.jsonl 2> gpurun_out/head_sweep.err; tail -1 gpurun_out/head_sweep.jsonl | cut -c1-200
 echo "=== op profile"; timeout 300 python scripts/op_profile.py --batch 256 --top 45 2>&1 | cut -c1-250 > gpurun_out/op_profile_final.txt; head -2 gpurun_out/op_profile_final.txt | cut -c1-400
 echo "=== ncu launch list"
-timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 1450 -c 574 --csv --log-file gpurun_out/bench_launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 1450 -c 465 --csv --log-file gpurun_out/bench_launches.csv \
   python bench.py --steps 2 --warmup 3 --batch 256 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; wc -l gpurun_out/bench_launches.csv
 echo "=== ncu full: tensor-core conv/GEMM kernel"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:tc_conv_kernel -s 60 -c 3 -o gpurun_out/tc_conv_r1_final python scripts/op_profile.py --batch 128 > gpurun_out/ncu3.log 2>&1; tail -1 gpurun_out/ncu3.log

@@ -340,31 +340,51 @@ def run_b200(args):
     ref_out = out_h.clone()
     e2e_mode = 'synchronous mtb_forward_host per step'
     e2e_ms = None
-    if not os.environ.get('MTB_BENCH_SYNC_E2E'):
+    pipe_ok = not os.environ.get('MTB_BENCH_SYNC_E2E')
+    pipe_ms = None
+    if pipe_ok:
+        out_hs = [torch.empty(B, J, 3).pin_memory(), torch.empty(B, J, 3).pin_memory()]
         try:
-            out_hs = [torch.empty(B, J, 3).pin_memory(), torch.empty(B, J, 3).pin_memory()]
             for s_ in (0, 1):  # warm both slots (staging allocations)
                 eng.forward_host_submit(crops_h, k_h, out_hs[s_], s_)
                 eng.forward_host_wait(s_)
-            barrier()
-            t0 = time.perf_counter()
-            for i in range(args.steps):
-                s_ = i & 1
-                eng.forward_host_wait(s_)  # the step that used this slot two steps ago has delivered its joints
-                eng.forward_host_submit(crops_h, k_h, out_hs[s_], s_)
-                if world > 1:
-                    eng.allgather(out_d)
-            eng.forward_host_wait(0)
-            eng.forward_host_wait(1)
-            barrier()
-            ms = (time.perf_counter() - t0) * 1e3
-            if torch.equal(out_hs[0], ref_out) and torch.equal(out_hs[1], ref_out):
-                e2e_ms = ms
-                e2e_mode = 'pipelined mtb_forward_host_submit/_wait, 2 slots (H2D of step i+1 overlaps the forward of step i)'
-            else:
-                print('bench: pipelined host path disagrees with mtb_forward_host; timing the synchronous loop', file=sys.stderr)
         except Exception as e:  # noqa: BLE001
-            print(f'bench: pipelined host path failed ({e!r}); timing the synchronous loop', file=sys.stderr)
+            print(f'bench: pipelined host path failed ({e!r})', file=sys.stderr)
+            pipe_ok = False
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            s_ = i & 1
+            if pipe_ok:
+                try:
+                    eng.forward_host_wait(s_)  # the step that used this slot two steps ago has delivered its joints
+                    eng.forward_host_submit(crops_h, k_h, out_hs[s_], s_)
+                except Exception as e:  # noqa: BLE001
+                    print(f'bench: pipelined host path failed ({e!r})', file=sys.stderr)
+                    pipe_ok = False
+            if world > 1:  # every rank issues the same number of collectives whatever happened above
+                eng.allgather(out_d)
+        if pipe_ok:
+            try:
+                eng.forward_host_wait(0)
+                eng.forward_host_wait(1)
+            except Exception as e:  # noqa: BLE001
+                print(f'bench: pipelined host path failed ({e!r})', file=sys.stderr)
+                pipe_ok = False
+        barrier()
+        pipe_ms = (time.perf_counter() - t0) * 1e3
+        if pipe_ok and not (torch.equal(out_hs[0], ref_out) and torch.equal(out_hs[1], ref_out)):
+            print('bench: pipelined host path disagrees with mtb_forward_host', file=sys.stderr)
+            pipe_ok = False
+    if world > 1:  # the fallback decision is collective: either every rank reports the pipelined loop or none does
+        flag = torch.tensor([1 if pipe_ok else 0], device=device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        pipe_ok = bool(flag.item())
+    if pipe_ok:
+        e2e_ms = pipe_ms
+        e2e_mode = 'pipelined mtb_forward_host_submit/_wait, 2 slots (H2D of step i+1 overlaps the forward of step i)'
+    else:
+        print('bench: timing the synchronous mtb_forward_host loop', file=sys.stderr)
     if e2e_ms is None:
         barrier()
         t0 = time.perf_counter()

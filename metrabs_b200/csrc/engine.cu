@@ -18,6 +18,7 @@
 #include "decode.cuh"
 #include "tc_gemm.cuh"
 #include "dw_tma.cuh"
+#include "tc_gemm_pair.cuh"
 #include "se_cluster.cuh"
 
 using namespace mtb;
@@ -70,6 +71,7 @@ struct Op {
   float* d_bias = nullptr;  // fp32 [Cout]
   TcWeights tc;             // bf16 K-major copy + TMA descriptor state for the tcgen05 path
   mutable DwTmaCache dw_cache;  // input tensor map of the TMA-staged depthwise kernel
+  mutable TcPairMaps pair_maps; // tensor maps of the (opt-in, MTB_TC_PAIR=1) cta_group::2 GEMM
   double flops = 0;         // 2*MACs per crop
   int stage = 0;            // EfficientNet stage (1-based; 0 = stem / last conv / other backbones)
 };
@@ -889,6 +891,9 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
           e = cudaGetLastError();
         }
         if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "launch %s: %s", op.name.c_str(), cudaGetErrorString(e));
+      } else if (op.tc.ready && tc_pair_eligible(p) && !(op.scale_buf != BUF_NONE && tc_can_fuse_se(op.R, op.stride, op.Cin))) {
+        const char* e = tc_pair_launch(op.tc, op.pair_maps, p, op.res_first, st);  // opt-in CTA-pair GEMM (never run yet)
+        if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 pair launch %s: %s", op.name.c_str(), e);
       } else if (op.tc.ready) {
         const char* e = tc_conv_launch(op.tc, p, op.res_first, st);
         if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 launch %s: %s", op.name.c_str(), e);
@@ -1719,6 +1724,7 @@ int mtb_debug_run_op(mtb_handle* h, int op_index, const float* in, const float* 
   o.tc.cached_in = nullptr;  // the copy must not reuse a tensor map encoded for other buffers
   o.tc.map_sets.clear();
   o.dw_cache = DwTmaCache();
+  o.pair_maps = TcPairMaps();
   o.fused_pool = false;      // in isolation a depthwise op does not pool and a pool op runs its own kernel
   o.se_fused = o.se_skip = false;
   rc = run_op(h, o, crops, batch, ws, nullptr, st);

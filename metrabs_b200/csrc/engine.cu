@@ -737,6 +737,15 @@ double op_bytes(const mtb_handle* h, const Op& op, int B) {
 }
 
 // ---------------------------------------------------------------------------------------------- executor
+// the projection conv of this op would run as a CTA-pair GEMM that applies the SE scale itself (MTB_TC_PAIR=1 + MTB_TC_PAIR_SCALE=1)
+bool op_pair_fuses_scale(const Op& op, int B) {
+  if (op.type != OP_CONV || !op.tc.ready || op.scale_buf == BUF_NONE) return false;
+  ConvParams q;
+  q.R = op.R; q.S = op.S; q.stride = op.stride; q.Cin = op.Cin; q.Cout = op.Cout; q.B = B; q.Hout = op.Hout; q.Wout = op.Wout;
+  q.act = op.act;
+  return tc_pair_fuses_scale(q, true);
+}
+
 bool pdl_se_enabled() {  // MTB_PDL_SE=1: programmatic dependent launch for the squeeze-excitation chain only
   static int v = -1;
   if (v < 0) {
@@ -750,7 +759,8 @@ template <typename T>
 int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Workspace& ws, void* features,
              cudaStream_t st) {
   PdlScope pdl_scope(pdl_se_enabled() && op.small_io);
-  if (op.type == OP_CONV && op.tc.ready && op.scale_buf != BUF_NONE && !tc_can_fuse_se(op.R, op.stride, op.Cin)) {
+  if (op.type == OP_CONV && op.tc.ready && op.scale_buf != BUF_NONE && !tc_can_fuse_se(op.R, op.stride, op.Cin) &&
+      !op_pair_fuses_scale(op, B)) {
     // squeeze-excitation scale applied in place ahead of a tensor-core conv that cannot fuse it (1x1 stride-1 projections
     // apply it to the A tiles in shared memory inside tc_conv_kernel)
     void* x = act_ptr(h, ws, op.in_buf, features, op.Hin, op.Win, op.Cin);
@@ -892,7 +902,7 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
         }
         if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "launch %s: %s", op.name.c_str(), cudaGetErrorString(e));
       } else if (op.tc.ready && tc_pair_eligible(p) && !(op.scale_buf != BUF_NONE && tc_can_fuse_se(op.R, op.stride, op.Cin))) {
-        const char* e = tc_pair_launch(op.tc, op.pair_maps, p, op.res_first, st);  // opt-in CTA-pair GEMM (never run yet)
+        const char* e = tc_pair_launch(op.tc, op.pair_maps, p, op.res_first, op_pair_fuses_scale(op, B), st);  // opt-in, never run yet
         if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 pair launch %s: %s", op.name.c_str(), e);
       } else if (op.tc.ready) {
         const char* e = tc_conv_launch(op.tc, p, op.res_first, st);

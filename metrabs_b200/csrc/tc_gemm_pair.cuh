@@ -14,15 +14,19 @@
 // tile per k-block.  In a CTA pair each CTA stages only HALF of the B tile (the MMA reads the other half from the peer's
 // shared memory), so a stage is 16 + 14 KB (6 in flight in the same budget) and the B traffic per SM halves.
 //
-// Roles (192 threads per CTA):  warps 0-3 epilogue (TMEM lanes 32w..32w+31 = tile rows of THIS CTA, direct 64-byte row
+// Roles (320 threads per CTA):  warps 0-3 epilogue (TMEM lanes 32w..32w+31 = tile rows of THIS CTA, direct 64-byte row
 // stores) | warp 4 TMA producer (own A half + own B half; the transaction bytes of both CTAs land on the LEADER's full
-// barrier) | warp 5 TMEM allocation (both CTAs, cta_group::2) and, in the leader CTA only, the single-thread MMA issuer.
+// barrier) | warp 5 TMEM allocation (both CTAs, cta_group::2) and, in the leader CTA only, the single-thread MMA issuer |
+// warps 6-9 (SCALE variant, MTB_TC_PAIR_SCALE=1) squeeze-excitation scalers: each CTA multiplies ITS A tile in shared
+// memory by s[crop(row)][k] once it has landed (A then completes on a CTA-local barrier) and arrives on the leader's
+// `scaled` barrier; with 6 stages in flight the extra hand-off should no longer cost what the in-place se_scale_kernel
+// pass costs (2.4 ms per step) - in the single-CTA kernel it did.
 #pragma once
 #include "tc_gemm.cuh"
 
 namespace mtb {
 
-constexpr int TP_THREADS = 192;
+constexpr int TP_THREADS = 320;
 constexpr int TP_BM = 128;                  // rows per CTA (256 per pair)
 constexpr int TP_BK = 64;
 constexpr int TP_A_BYTES = TP_BM * TP_BK * 2;   // 16 KB
@@ -40,6 +44,8 @@ struct TcPairParams {
   int bn;         // N-tile stride (multiple of 32, <= 256); each CTA stages bn / 2 weight rows per k-block
   int n_tiles, m_pairs, kchunks;
   int nstages, stage_stride;
+  const float* a_scale;  // SCALE variant: squeeze-excitation scale [B][Cin] fp32
+  int a_scale_P;         // pixels per crop (row / P = crop index)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -85,7 +91,7 @@ __host__ __device__ inline uint32_t umma_idesc_bf16_m256(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
-template <int ACT, int RES>
+template <int ACT, int RES, bool SCALE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TP_THREADS, 1)
 tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcPairParams p) {
   extern __shared__ uint8_t tp_smem_raw[];
@@ -95,7 +101,9 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty = bars + TP_MAX_STAGES;              // [12] per CTA: the pair's MMAs have read this slot
   uint64_t* tmem_full = bars + 2 * TP_MAX_STAGES;      // [2]  per CTA: accumulator complete
   uint64_t* tmem_empty = tmem_full + 2;                // [2]  used in the leader: all 8 epilogue warps of the pair drained it
-  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  uint64_t* a_full = tmem_empty + 2;                   // [12] SCALE: per CTA, its own A tile has landed
+  uint64_t* scaled = a_full + TP_MAX_STAGES;           // [12] SCALE: used in the leader, all 8 scaler warps of the pair are done
+  uint32_t* tmem_slot = (uint32_t*)(scaled + TP_MAX_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -106,6 +114,8 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int i = 0; i < TP_MAX_STAGES; ++i) {
       mbar_init(&full[i], 1);    // the leader producer's arrive.expect_tx
       mbar_init(&empty[i], 1);   // tcgen05.commit (multicast to both CTAs)
+      mbar_init(&a_full[i], 1);  // SCALE: this CTA's producer
+      mbar_init(&scaled[i], 8);  // SCALE: 4 scaler warps x 2 CTAs
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -128,7 +138,9 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int pair_tiles = p.m_pairs * p.n_tiles;
   const int bnh = p.bn >> 1;                               // weight rows staged per CTA and k-block
   const uint32_t bh_bytes = (uint32_t)bnh * TP_BK * 2;
-  const uint32_t stage_tx = 2u * ((uint32_t)TP_A_BYTES + bh_bytes);   // both CTAs' loads of one stage
+  // bytes landing on the leader's full barrier per stage: both CTAs' loads (SCALE: only the weight halves; A completes locally)
+  const uint32_t stage_tx = SCALE ? 2u * bh_bytes : 2u * ((uint32_t)TP_A_BYTES + bh_bytes);
+  const uint32_t a_full0 = smem_u32(a_full), scaled0 = smem_u32(scaled);
   const int nstages = p.nstages;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
@@ -149,7 +161,12 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (elect_one()) {
           const uint32_t sa = smem_base + stage * p.stage_stride;
           if (leader) mbar_expect_tx_a(full0 + stage * 8, stage_tx);
-          tma_load_2d_2sm(sa, &tmA, full0 + stage * 8, kc * TP_BK, row0);
+          if constexpr (SCALE) {
+            mbar_expect_tx_a(a_full0 + stage * 8, (uint32_t)TP_A_BYTES);
+            tma_load_2d_a(sa, &tmA, a_full0 + stage * 8, kc * TP_BK, row0);
+          } else {
+            tma_load_2d_2sm(sa, &tmA, full0 + stage * 8, kc * TP_BK, row0);
+          }
           tma_load_2d_2sm(sa + TP_A_BYTES, &tmB, full0 + stage * 8, kc * TP_BK, brow);
         }
         __syncwarp();
@@ -171,6 +188,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
       for (int kb = 0; kb < p.kchunks; ++kb) {
         mbar_wait_a(full0 + stage * 8, phase);
+        if constexpr (SCALE) mbar_wait_a(scaled0 + stage * 8, phase);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a16 = base16 + stage * stride16;
@@ -248,6 +266,56 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
+  if constexpr (SCALE) {
+    if (warp >= 6) {
+      // ===== squeeze-excitation scalers (both CTAs): same mapping as tc_conv_kernel's - warp w owns rows [32w, 32w+32), a
+      // quarter-warp covers one 128-byte row (bank-conflict free); fp32 product rounded once to bf16 =====
+      const int sw = warp - 6;
+      const int sub = lane >> 3, pos = lane & 7;
+      uint32_t stage = 0, phase = 0;
+      for (int u = pair; u < pair_tiles; u += npairs) {
+        const int m_pair = u / p.n_tiles;
+        const int m0 = (m_pair * 2 + (int)rank) * TP_BM + sw * 32 + sub;
+        int soff[8];
+        uint32_t rok = 0;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = m0 + it * 4;
+          const bool ok = m < p.M;
+          rok |= ok ? (1u << it) : 0u;
+          soff[it] = (ok ? m / p.a_scale_P : 0) * p.Cin;
+        }
+#pragma unroll 1
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait_a(a_full0 + stage * 8, phase);
+          uint8_t* sa = smem + stage * p.stage_stride + (sw * 32 + sub) * 128 + pos * 16;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int k = kc * 64 + ((pos ^ (((it & 1) << 2) | sub)) << 3);  // 128B swizzle: logical chunk at position pos
+            if (!((rok >> it) & 1u) || k >= p.Cin) continue;
+            uint4* ptr = reinterpret_cast<uint4*>(sa + it * 512);
+            uint4 v = *ptr;
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.a_scale + soff[it] + k));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.a_scale + soff[it] + k + 4));
+            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            unsigned wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float lo = __uint_as_float(wd[i] << 16) * sc[2 * i];
+              const float hi = __uint_as_float(wd[i] & 0xffff0000u) * sc[2 * i + 1];
+              __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+              wd[i] = *reinterpret_cast<unsigned*>(&pk);
+            }
+            *ptr = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+          }
+          fence_proxy_async();  // generic-proxy writes -> visible to the tensor cores (async proxy) of the pair
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(scaled0 + stage * 8);
+          if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  }
   tc_fence_before();
   cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still address its shared memory / barriers
   if (warp == 5) {
@@ -276,17 +344,26 @@ inline bool tc_pair_eligible(const ConvParams& p) {
          (long)p.B * p.Hout * p.Wout >= 256;
 }
 
-template <int ACT, int RES>
-inline const char* tc_pair_launch_t(int grid, const CUtensorMap& a, const CUtensorMap& b, const TcPairParams& q, cudaStream_t st) {
+template <int ACT, int RES, bool SCALE>
+inline const char* tc_pair_launch_k(int grid, const CUtensorMap& a, const CUtensorMap& b, const TcPairParams& q, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_gemm_pair_kernel<ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_gemm_pair_kernel<ACT, RES, SCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM_BYTES) !=
+        cudaSuccess)
       return "cannot raise dynamic shared memory for tc_gemm_pair_kernel";
     attr_set = true;
   }
-  launch_k(tc_gemm_pair_kernel<ACT, RES>, dim3(grid), dim3(TP_THREADS), TP_SMEM_BYTES, st, a, b, q);
+  launch_k(tc_gemm_pair_kernel<ACT, RES, SCALE>, dim3(grid), dim3(TP_THREADS), TP_SMEM_BYTES, st, a, b, q);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+template <int ACT, int RES>
+inline const char* tc_pair_launch_t(int grid, const CUtensorMap& a, const CUtensorMap& b, const TcPairParams& q, cudaStream_t st) {
+  if constexpr (ACT == ACT_NONE) {  // the scaled GEMMs are the MBConv projections: no activation
+    if (q.a_scale) return tc_pair_launch_k<ACT, RES, true>(grid, a, b, q, st);
+  }
+  if (q.a_scale) return "fused SE scale in the pair GEMM is only built for activation-free projections";
+  return tc_pair_launch_k<ACT, RES, false>(grid, a, b, q, st);
 }
 template <int ACT>
 inline const char* tc_pair_launch_res(int res_mode, int grid, const CUtensorMap& a, const CUtensorMap& b, const TcPairParams& q,
@@ -299,8 +376,24 @@ inline const char* tc_pair_launch_res(int res_mode, int grid, const CUtensorMap&
 }
 
 // w: the op's tensor-core weights ([Cout][Cin] bf16 K-major + fp32 bias); maps cached per (input pointer, batch)
-inline const char* tc_pair_launch(const TcWeights& w, TcPairMaps& maps, const ConvParams& p, bool res_first, cudaStream_t st) {
+inline bool tc_pair_scale_enabled() {  // MTB_TC_PAIR_SCALE=1 (with MTB_TC_PAIR=1): SE scale fused into the pair GEMM
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTB_TC_PAIR_SCALE");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+// the projection behind a squeeze-excitation runs as a pair GEMM that applies the scale itself (no se_scale_kernel pass)
+inline bool tc_pair_fuses_scale(const ConvParams& p, bool has_scale) {
+  return has_scale && tc_pair_scale_enabled() && tc_pair_eligible(p) && p.act == ACT_NONE;
+}
+
+inline const char* tc_pair_launch(const TcWeights& w, TcPairMaps& maps, const ConvParams& p, bool res_first, bool fuse_scale,
+                                  cudaStream_t st) {
   TcPairParams q;
+  q.a_scale = fuse_scale ? p.a_scale : nullptr;
+  q.a_scale_P = p.Hin * p.Win;
   q.res = p.res; q.bias = w.d_bias; q.out = (__nv_bfloat16*)p.out;
   q.M = p.B * p.Hout * p.Wout; q.Cout = p.Cout; q.Cin = p.Cin;
   const int nt = (p.Cout + 255) / 256;

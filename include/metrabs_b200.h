@@ -193,6 +193,10 @@ const char* mtb_kernel_class_name(int cls);
 /* Number of kernels the last mtb_forward / mtb_backbone_forward / ... call on this handle launched. */
 int64_t mtb_last_launch_count(const mtb_handle* h);
 double mtb_backbone_flops_per_crop(const mtb_handle* h);
+/* Host-side tiling plan of the TMA-staged depthwise 3x3 kernel for an HxW map (no device needed): crops per item, output
+ * rows per item, row bands per crop (= SE pooling slices) and bytes of one shared-memory stage; all 0 when the shape falls
+ * back to the strip kernel. */
+int mtb_debug_dw_plan(int height, int width, int* crops_per_item, int* rows_per_item, int* row_bands, int* stage_bytes);
 
 #ifdef __cplusplus
 }

@@ -77,6 +77,8 @@ _SIGNATURES = {
     'mtb_kernel_class_name': (C.c_char_p, [C.c_int]),
     'mtb_last_launch_count': (C.c_int64, [C.c_void_p]),
     'mtb_backbone_flops_per_crop': (C.c_double, [C.c_void_p]),
+    'mtb_debug_dw_plan': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int)]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -1748,4 +1748,16 @@ int mtb_debug_run_op(mtb_handle* h, int op_index, const float* in, const float* 
 int64_t mtb_last_launch_count(const mtb_handle* h) { return h ? h->launches : 0; }
 double mtb_backbone_flops_per_crop(const mtb_handle* h) { return h ? h->flops_per_crop : 0.0; }
 
+int mtb_debug_dw_plan(int height, int width, int* crops_per_item, int* rows_per_item, int* row_bands, int* stage_bytes) {
+  if (height <= 0 || width <= 0 || !crops_per_item || !rows_per_item || !row_bands || !stage_bytes)
+    return fail(nullptr, MTB_ERR_INVALID_ARG, "invalid arguments");
+  const DwTmaPlan pl = dw_tma_plan(height, width);
+  if (!pl.ok) { *crops_per_item = *rows_per_item = *row_bands = *stage_bytes = 0; return MTB_OK; }
+  *crops_per_item = pl.G;
+  *rows_per_item = pl.BH;
+  *row_bands = pl.n_rb;
+  *stage_bytes = 128 * (width + 2) * (pl.BH + 2) * pl.G;
+  return MTB_OK;
+}
+
 }  // extern "C"

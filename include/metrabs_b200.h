@@ -188,6 +188,9 @@ int mtb_profile_end(mtb_handle* h, double* ms, double* flops, double* bytes, int
 /* Per-op view of the last profiling window: device ms per backbone op, its algorithmic FLOPs and bytes per crop and
  * its kernel class; arrays hold mtb_num_ops() entries. */
 int mtb_profile_op_times(const mtb_handle* h, double* ms, double* flops_per_crop, double* bytes_per_crop, int* cls, int n);
+/* Weight bytes the op reads once per launch (bf16 on the tensor-core path, fp32 otherwise); `bytes_per_crop` above counts
+ * activations (input + output + residual) only, so a launch on B crops moves B * bytes_per_crop + weight bytes. */
+double mtb_op_weight_bytes(const mtb_handle* h, int op);
 int mtb_num_kernel_classes(void);
 const char* mtb_kernel_class_name(int cls);
 /* Number of kernels the last mtb_forward / mtb_backbone_forward / ... call on this handle launched. */

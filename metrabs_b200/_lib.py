@@ -73,6 +73,7 @@ _SIGNATURES = {
                                   C.POINTER(C.c_int64)]),
     'mtb_profile_op_times': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_int), C.c_int]),
+    'mtb_op_weight_bytes': (C.c_double, [C.c_void_p, C.c_int]),
     'mtb_num_kernel_classes': (C.c_int, []),
     'mtb_kernel_class_name': (C.c_char_p, [C.c_int]),
     'mtb_last_launch_count': (C.c_int64, [C.c_void_p]),

@@ -19,6 +19,7 @@
 #include "tc_gemm.cuh"
 #include "dw_tma.cuh"
 #include "tc_gemm_pair.cuh"
+#include "tc_gemm_bres.cuh"
 #include "se_cluster.cuh"
 
 using namespace mtb;
@@ -72,6 +73,7 @@ struct Op {
   TcWeights tc;             // bf16 K-major copy + TMA descriptor state for the tcgen05 path
   mutable DwTmaCache dw_cache;  // input tensor map of the TMA-staged depthwise kernel
   mutable TcPairMaps pair_maps; // tensor maps of the (opt-in, MTB_TC_PAIR=1) cta_group::2 GEMM
+  mutable TcBresMaps bres_maps; // tensor maps of the (opt-in, MTB_TC_BRES=1) resident-weight-panel GEMM
   double flops = 0;         // 2*MACs per crop
   int stage = 0;            // EfficientNet stage (1-based; 0 = stem / last conv / other backbones)
 };
@@ -726,6 +728,11 @@ int op_class(const Op& op) {
   return KC_IGEMM_SIMT;
 }
 
+double op_weight_bytes(const Op& op) {
+  if (op.type == OP_POOL || op.type == OP_MAXPOOL) return 0.0;
+  return (double)op.R * op.S * (op.depthwise ? 1 : op.Cin) * op.Cout * (op.tc.ready ? 2.0 : 4.0);
+}
+
 double op_bytes(const mtb_handle* h, const Op& op, int B) {
   const double es = op.small_io ? 4.0 : (double)elem_size(h);
   double in = (double)B * op.Hin * op.Win * op.Cin * (op.type == OP_STEM ? 4.0 : es);
@@ -901,6 +908,10 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
           e = cudaGetLastError();
         }
         if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "launch %s: %s", op.name.c_str(), cudaGetErrorString(e));
+      } else if (op.tc.ready && tc_bres_eligible(p) && !op_pair_fuses_scale(op, B) &&
+                 !(op.scale_buf != BUF_NONE && tc_can_fuse_se(op.R, op.stride, op.Cin))) {
+        const char* e = tc_bres_launch(op.tc, op.bres_maps, p, op.res_first, st);  // opt-in short-K GEMM (never run yet)
+        if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 resident-panel launch %s: %s", op.name.c_str(), e);
       } else if (op.tc.ready && tc_pair_eligible(p) && !(op.scale_buf != BUF_NONE && tc_can_fuse_se(op.R, op.stride, op.Cin))) {
         const char* e = tc_pair_launch(op.tc, op.pair_maps, p, op.res_first, op_pair_fuses_scale(op, B), st);  // opt-in, never run yet
         if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 pair launch %s: %s", op.name.c_str(), e);
@@ -1678,10 +1689,15 @@ int mtb_profile_op_times(const mtb_handle* h, double* ms, double* flops_per_crop
   for (size_t i = 0; i < h->ops.size(); ++i) {
     ms[i] = i < h->prof_op_ms.size() ? h->prof_op_ms[i] : 0.0;
     if (flops_per_crop) flops_per_crop[i] = h->ops[i].flops;
-    if (bytes_per_crop) bytes_per_crop[i] = op_bytes(h, h->ops[i], 1);
+    if (bytes_per_crop) bytes_per_crop[i] = op_bytes(h, h->ops[i], 1) - op_weight_bytes(h->ops[i]);  // activations only
     if (cls) cls[i] = op_class(h->ops[i]);
   }
   return MTB_OK;
+}
+
+double mtb_op_weight_bytes(const mtb_handle* h, int op) {
+  if (!h || op < 0 || op >= (int)h->ops.size()) return 0.0;
+  return op_weight_bytes(h->ops[op]);
 }
 
 int mtb_num_kernel_classes(void) { return KC_COUNT; }
@@ -1735,6 +1751,7 @@ int mtb_debug_run_op(mtb_handle* h, int op_index, const float* in, const float* 
   o.tc.map_sets.clear();
   o.dw_cache = DwTmaCache();
   o.pair_maps = TcPairMaps();
+  o.bres_maps = TcBresMaps();
   o.fused_pool = false;      // in isolation a depthwise op does not pool and a pool op runs its own kernel
   o.se_fused = o.se_skip = false;
   rc = run_op(h, o, crops, batch, ws, nullptr, st);

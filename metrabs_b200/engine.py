@@ -272,13 +272,14 @@ class Engine:
                 for i in range(n) if la[i] > 0}
 
     def profile_op_times(self):
-        """After profile_end(): [(op name, kernel class, ms, flops_per_crop, bytes_per_crop)] per backbone op."""
+        """After profile_end(): [(op name, kernel class, ms, flops_per_crop, activation_bytes_per_crop, weight_bytes)] per op."""
         n = lib().mtb_num_ops(self._h)
         ms, fl, by = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
         cl = (C.c_int * n)()
         check(lib().mtb_profile_op_times(self._h, ms, fl, by, cl, n), self._h)
         names = self.op_names()
-        return [(names[i], lib().mtb_kernel_class_name(cl[i]).decode(), ms[i], fl[i], by[i]) for i in range(n)]
+        return [(names[i], lib().mtb_kernel_class_name(cl[i]).decode(), ms[i], fl[i], by[i],
+                 float(lib().mtb_op_weight_bytes(self._h, i))) for i in range(n)]
 
     @property
     def last_launch_count(self):

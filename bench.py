@@ -38,7 +38,7 @@ def parse():
     ap.add_argument('--depth', type=int, default=8, help='heatmap depth D (config c2: 32)')
     ap.add_argument('--joints', type=int, default=24)
     ap.add_argument('--batch', type=int, default=256, help='crops per GPU per step (weak scaling)')
-    ap.add_argument('--precision', default=os.environ.get('MTB_BENCH_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
+    ap.add_argument('--precision', default=os.environ.get('MTB_BENCH_PRECISION', 'bf16'), choices=['fp32', 'bf16', 'tf32x3'])
     ap.add_argument('--cpu-sample', type=int, default=8, help='crops per CPU-baseline forward')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--graph', type=int, default=int(os.environ.get('MTB_BENCH_GRAPH', '0')),
@@ -422,7 +422,7 @@ def run_b200(args):
     line = {
         'metric': METRIC, 'value': value, 'unit': 'crops/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+        'vs_baseline': None, 'dtype': {'bf16': 'bf16', 'fp32': 'f32', 'tf32x3': 'tf32x3'}[args.precision], 'data': 'synthetic',
         'config': {'workload': workload_name(args), 'global_batch': world * B, 'parallelism': f'dp{world}',
                    'precision_mode': args.precision, 'weights': 'conditioned random init (metrabs_b200/init.py)',
                    'l2_policy': f'inputs larger than L2: {B * 3 * S * S * 4 / 1e6:.0f} MB of crops per step',

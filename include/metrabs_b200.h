@@ -53,7 +53,11 @@ typedef enum { MTB_ARCH_EFFNET = 0, MTB_ARCH_RESNET50 = 1, MTB_ARCH_MOBILENETV3_
 typedef enum { MTB_PRECISION_FP32 = 0, MTB_PRECISION_BF16_TC = 1,
                /* verification mode: same bf16 storage and bf16-rounded weights as BF16_TC, but every conv on CUDA
                 * cores (fp32 FMA) - lets tests separate tensor-core kernel bugs from bf16 rounding effects */
-               MTB_PRECISION_BF16_SIMT = 2 } mtb_precision;
+               MTB_PRECISION_BF16_SIMT = 2,
+               /* the 1e-3 parity mode ON TENSOR CORES: fp32 storage, every conv/GEMM as three tcgen05 kind::tf32
+                * products of hi/lo-split operands (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo) with fp32 accumulation in TMEM;
+                * conv outputs agree with the fp32 FMA chain to ~1e-6 */
+               MTB_PRECISION_TF32X3 = 3 } mtb_precision;
 
 /* Layout of a logits tensor handed to the standalone soft-argmax. */
 typedef enum {

@@ -7,7 +7,7 @@ MTB_ABI_VERSION = 1
 MTB_MAX_STAGES = 16
 
 ARCH_EFFNET, ARCH_RESNET50, ARCH_MOBILENETV3_SMALL, ARCH_HEAD_ONLY = 0, 1, 2, 3
-PRECISION_FP32, PRECISION_BF16_TC, PRECISION_BF16_SIMT = 0, 1, 2
+PRECISION_FP32, PRECISION_BF16_TC, PRECISION_BF16_SIMT, PRECISION_TF32X3 = 0, 1, 2, 3
 DTYPE_F32, DTYPE_BF16, DTYPE_F16, DTYPE_I64 = 0, 1, 2, 3
 LAYOUT_BDJHW, LAYOUT_BHWN = 0, 1
 

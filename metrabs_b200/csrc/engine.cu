@@ -17,6 +17,7 @@
 #include "conv_simt.cuh"
 #include "decode.cuh"
 #include "tc_gemm.cuh"
+#include "tc_tf32.cuh"
 #include "dw_tma.cuh"
 #include "tc_gemm_pair.cuh"
 #include "tc_gemm_bres.cuh"
@@ -31,11 +32,12 @@ std::string g_error;
 enum OpType { OP_STEM = 0, OP_CONV = 1, OP_DW = 2, OP_POOL = 3, OP_MAXPOOL = 4 };
 // kernel classes for the CUDA-event profiler (mtb_profile_begin / mtb_profile_end)
 enum KClass { KC_STEM = 0, KC_IGEMM_SIMT = 1, KC_DWCONV = 2, KC_POOL = 3, KC_SE_FC = 4, KC_TC_GEMM = 5, KC_TC_CONV3 = 6,
-              KC_HEAD_FUSED = 7, KC_HEAD_CONV_SIMT = 8, KC_SOFTARGMAX = 9, KC_RECON = 10, KC_OTHER = 11, KC_SE_SCALE = 12, KC_COUNT = 13 };
+              KC_HEAD_FUSED = 7, KC_HEAD_CONV_SIMT = 8, KC_SOFTARGMAX = 9, KC_RECON = 10, KC_OTHER = 11, KC_SE_SCALE = 12, KC_TC32 = 13,
+              KC_COUNT = 14 };
 const char* kKClassNames[KC_COUNT] = {"stem_conv_kernel", "conv_igemm_kernel", "dwconv_kernel", "pool_mean_kernel",
                                       "se_fc(conv_igemm_kernel)", "tc_conv_kernel", "tc_conv_kernel(unused)",
                                       "tc_head_softargmax_kernel", "head_conv(conv_igemm_kernel)",
-                                      "softargmax_bhwn_kernel", "recon_pass1+2_kernel", "other", "se_scale_kernel"};
+                                      "softargmax_bhwn_kernel", "recon_pass1+2_kernel", "other", "se_scale_kernel", "tc32_conv_kernel"};
 enum { BUF_FEATURES = -2, BUF_NONE = -1, BUF_SMALL0 = 4 };  // 0..3 big activation buffers, 4..6 small [B,C]
 constexpr int kNumBig = 4, kNumSmall = 3;
 constexpr int kPoolSlices = 8;  // the fused depthwise+pool kernel leaves up to 8 partial slices [slice][B][C]
@@ -71,6 +73,7 @@ struct Op {
   float* d_w = nullptr;     // fp32 [R*S*Cin][Cout]  (dw: [R*S][C])
   float* d_bias = nullptr;  // fp32 [Cout]
   TcWeights tc;             // bf16 K-major copy + TMA descriptor state for the tcgen05 path
+  Tc32Weights tc32;         // fp32 K-major copy + TMA descriptor state for the 3xTF32 tcgen05 path (MTB_PRECISION_TF32X3)
   mutable DwTmaCache dw_cache;  // input tensor map of the TMA-staged depthwise kernel
   mutable TcPairMaps pair_maps; // tensor maps of the (opt-in, MTB_TC_PAIR=1) cta_group::2 GEMM
   mutable TcBresMaps bres_maps; // tensor maps of the (opt-in, MTB_TC_BRES=1) resident-weight-panel GEMM
@@ -96,7 +99,7 @@ struct mtb_handle {
   double flops_per_crop = 0;
   // host-path staging
   void* stage = nullptr;
-  size_t stage_bytes = 0;
+  size_t stage_bytes = 0, stage_ws_bytes = 0;
   int stage_batch = 0;
   // pipelined host path (mtb_forward_host_submit / _wait): two input/output slots, one shared workspace, a copy stream
   struct HostSlot {
@@ -155,7 +158,7 @@ int fail(const mtb_handle* h, int code, const char* fmt, ...) {
   } while (0)
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-inline bool is_bf16(const mtb_handle* h) { return h->cfg.precision != MTB_PRECISION_FP32; }
+inline bool is_bf16(const mtb_handle* h) { return h->cfg.precision == MTB_PRECISION_BF16_TC || h->cfg.precision == MTB_PRECISION_BF16_SIMT; }
 inline size_t elem_size(const mtb_handle* h) { return is_bf16(h) ? 2 : 4; }
 
 // ------------------------------------------------------------------------------------------- plan building
@@ -559,7 +562,11 @@ int prepare_op_weights(mtb_handle* h, Op& op) {
     const HostTensor *g = find(h, op.bnkey + ".weight"), *b = find(h, op.bnkey + ".bias"),
                      *m = find(h, op.bnkey + ".running_mean"), *v = find(h, op.bnkey + ".running_var");
     if (!g || !b || !m || !v) return fail(h, MTB_ERR_MISSING_WEIGHT, "missing batch-norm tensors '%s.*'", op.bnkey.c_str());
-    for (int n = 0; n < op.Cout; ++n) {
+    for (const HostTensor* t : {g, b, m, v})
+      if ((int)t->data.size() != n_real)
+        return fail(h, MTB_ERR_INVALID_ARG, "batch-norm tensors '%s.*' must have %d elements (got %zu)", op.bnkey.c_str(), n_real,
+                    t->data.size());
+    for (int n = 0; n < n_real; ++n) {
       double s = (double)g->data[n] / std::sqrt((double)v->data[n] + (double)op.bn_eps);
       scale[n] = s;
       shift[n] = (shift[n] - (double)m->data[n]) * s + (double)b->data[n];
@@ -586,6 +593,11 @@ int prepare_op_weights(mtb_handle* h, Op& op) {
   if (h->cfg.precision == MTB_PRECISION_BF16_TC && tc_like && !tc_disabled()) {
     const char* e = tc_prepare_weights(op.tc, wk.data(), bias.data(), K, op.Cout, op.R, op.S, op.Cin, h->dev_allocs);
     if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 weight prep for '%s': %s", op.name.c_str(), e);
+  }
+  if (h->cfg.precision == MTB_PRECISION_TF32X3 && !tc_disabled() &&
+      tc32_eligible(op.type == OP_CONV, op.depthwise, op.small_io, op.R, op.stride, op.Cin, op.Cout)) {
+    const char* e = tc32_prepare_weights(op.tc32, wk.data(), bias.data(), K, op.Cout, op.R, op.S, op.Cin, h->dev_allocs);
+    if (e) return fail(h, MTB_ERR_CUDA, "3xTF32 weight prep for '%s': %s", op.name.c_str(), e);
   }
   return MTB_OK;
 }
@@ -629,7 +641,7 @@ void* buf_ptr(const Workspace& w, int id, void* features) {
 void* act_ptr(const mtb_handle* h, const Workspace& w, int id, void* features, int hh, int ww, int cc) {
   char* base = (char*)buf_ptr(w, id, features);
   if (!base || id >= kNumBig) return base;
-  return base + (size_t)w.b0 * hh * ww * cc * (h->cfg.precision != MTB_PRECISION_FP32 ? 2 : 4);
+  return base + (size_t)w.b0 * hh * ww * cc * elem_size(h);
 }
 
 // ---------------------------------------------------------------------------------------------- profiler
@@ -725,6 +737,7 @@ int op_class(const Op& op) {
   }
   if (op.small_io) return KC_SE_FC;
   if (op.tc.ready) return KC_TC_GEMM;  // one class per kernel: every tensor-core conv/GEMM launch is tc_conv_kernel
+  if (op.tc32.ready) return KC_TC32;
   return KC_IGEMM_SIMT;
 }
 
@@ -918,6 +931,9 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
       } else if (op.tc.ready) {
         const char* e = tc_conv_launch(op.tc, p, op.res_first, st);
         if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 launch %s: %s", op.name.c_str(), e);
+      } else if (op.tc32.ready) {
+        const char* e = tc32_conv_launch(op.tc32, p, op.res_first, st);  // SE scale (p.a_scale) applied by the splitter warps
+        if (e) return fail(h, MTB_ERR_CUDA, "3xTF32 launch %s: %s", op.name.c_str(), e);
       } else {
         cudaError_t e = launch_conv_igemm<T, T>(p, st);
         if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "launch %s: %s", op.name.c_str(), cudaGetErrorString(e));
@@ -1021,7 +1037,12 @@ int head_decode_impl(mtb_handle* h, const void* features, int B, float* c2d, flo
   p.R = p.S = 1; p.stride = 1; p.dil = 1; p.pad_t = p.pad_l = 0; p.act = ACT_NONE;
   const double logit_bytes = (double)B * P * op.Cout * 4;
   cudaError_t e;
-  {
+  if (op.tc32.ready) {  // 3xTF32 GEMM -> fp32 NHWC logits
+    ProfScope prof(h, KC_TC32, op.flops * B, feat_bytes + (double)op.Cin * op.Cout * 4 + logit_bytes, st);
+    const char* te = tc32_conv_launch(op.tc32, p, false, st);
+    if (te) return fail(h, MTB_ERR_CUDA, "3xTF32 head conv: %s", te);
+    e = cudaSuccess;
+  } else {
     ProfScope prof(h, KC_HEAD_CONV_SIMT, op.flops * B, feat_bytes + (double)op.Cin * op.Cout * 4 + logit_bytes, st);
     e = is_bf16(h) ? launch_conv_igemm<__nv_bfloat16, float>(p, st)
                                              : launch_conv_igemm<float, float>(p, st);
@@ -1100,7 +1121,7 @@ int mtb_create(const mtb_config* cfg, mtb_handle** out) {
                 cfg->depth, cfg->proc_side, cfg->stride_test);
   if (cfg->arch == MTB_ARCH_EFFNET && (cfg->n_stages <= 0 || cfg->n_stages > MTB_MAX_STAGES))
     return fail(nullptr, MTB_ERR_INVALID_ARG, "n_stages out of range");
-  if (cfg->precision < MTB_PRECISION_FP32 || cfg->precision > MTB_PRECISION_BF16_SIMT)
+  if (cfg->precision < MTB_PRECISION_FP32 || cfg->precision > MTB_PRECISION_TF32X3)
     return fail(nullptr, MTB_ERR_INVALID_ARG, "unknown precision %d", cfg->precision);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -1394,6 +1415,18 @@ static int forward_body(mtb_handle* h, const float* crops, const float* intrinsi
 // time it sees the same (buffers, batch, stream) and replays that graph from then on - the 465 launches of a step were
 // 8-9 % faster as one graph launch than as stream submissions (bench.py --graph 1).  A profiling window bypasses it
 // (events cannot be timed inside a graph), any capture failure falls back to plain launches for that key.
+// destroys and forgets the captured forwards whose workspace is `ws` (nullptr: all of them)
+static void drop_graphs_on(mtb_handle* h, const void* ws) {
+  for (size_t i = 0; i < h->graphs.size();) {
+    if (ws == nullptr || h->graphs[i].ws == ws) {
+      if (h->graphs[i].exec) cudaGraphExecDestroy(h->graphs[i].exec);
+      h->graphs.erase(h->graphs.begin() + (long)i);
+    } else {
+      ++i;
+    }
+  }
+}
+
 static bool graph_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -1441,11 +1474,7 @@ int mtb_forward(mtb_handle* h, const float* crops, const float* intrinsics, int 
         }
         ent->failed = true;  // plain launches for this key from now on
       } else if (!ent) {
-        if (h->graphs.size() >= 8) {  // a caller cycling through many buffers gets no graphs rather than unbounded state
-          for (auto& e : h->graphs)
-            if (e.exec) cudaGraphExecDestroy(e.exec);
-          h->graphs.clear();
-        }
+        if (h->graphs.size() >= 8) drop_graphs_on(h, nullptr);  // a caller cycling through many buffers: bounded state
         mtb_handle::GraphEntry e;
         e.crops = crops; e.k = intrinsics; e.out = coords3d_abs; e.ws = workspace; e.batch = batch; e.st = st;
         h->graphs.push_back(e);
@@ -1469,11 +1498,13 @@ int mtb_forward_host(mtb_handle* h, const float* host_crops, const float* host_i
   const size_t need = crops_b + k_b + out_b + ws_b;
   if (need > h->stage_bytes) {  // grows only when a larger batch than ever before arrives
     CUDA_TRY(h, cudaStreamSynchronize(st));
+    if (h->stage) drop_graphs_on(h, (char*)h->stage + (h->stage_bytes - h->stage_ws_bytes));
     if (h->stage) cudaFree(h->stage);
     h->stage = nullptr;
     h->stage_bytes = 0;
     CUDA_TRY(h, cudaMalloc(&h->stage, need));
     h->stage_bytes = need;
+    h->stage_ws_bytes = ws_b;
   }
   char* base = (char*)h->stage;
   float* d_crops = (float*)base;
@@ -1516,9 +1547,8 @@ int mtb_forward_host_submit(mtb_handle* h, const float* host_crops, const float*
       sl.bytes = crops_b + k_b + out_b;
     }
     if (ws_b > h->pipe_ws_bytes) {
-      for (auto& e : h->graphs)
-      if (e.exec) cudaGraphExecDestroy(e.exec);
-    if (h->pipe_ws) cudaFree(h->pipe_ws);
+      drop_graphs_on(h, h->pipe_ws);  // captured forwards that write into the old pipeline workspace
+      if (h->pipe_ws) cudaFree(h->pipe_ws);
       h->pipe_ws = nullptr; h->pipe_ws_bytes = 0;
       CUDA_TRY(h, cudaMalloc(&h->pipe_ws, ws_b));
       h->pipe_ws_bytes = ws_b;
@@ -1749,6 +1779,7 @@ int mtb_debug_run_op(mtb_handle* h, int op_index, const float* in, const float* 
   o.out_buf = (o.type == OP_POOL || o.small_io) ? BUF_SMALL0 + 1 : 2;
   o.tc.cached_in = nullptr;  // the copy must not reuse a tensor map encoded for other buffers
   o.tc.map_sets.clear();
+  o.tc32.map_sets.clear();
   o.dw_cache = DwTmaCache();
   o.pair_maps = TcPairMaps();
   o.bres_maps = TcBresMaps();

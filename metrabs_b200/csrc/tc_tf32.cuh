@@ -1,0 +1,540 @@
+// 3xTF32 tensor-core path (sm_100a): the PARITY mode on tcgen05.  fp32 NHWC activations and fp32 weights are staged by
+// TMA exactly as they sit in HBM; "splitter" warps rewrite every landed operand tile in shared memory as
+//     x_hi = tf32(x)  (round to nearest, low 13 mantissa bits zero)      x_lo = x - x_hi  (exact in fp32)
+// and the MMA warp issues, per K step of 8,
+//     D += A_hi * B_hi        D += A_lo * B_hi        D += A_hi * B_lo              (tcgen05.mma kind::tf32, fp32 in TMEM)
+// i.e. the product of two 21-bit-mantissa operands with fp32 accumulation: the dropped terms (a_lo*b_lo and the bits of
+// x_lo below tf32) are ~2^-21 relative, so conv outputs agree with an fp32 FMA chain to ~1e-6 and the joints meet the 1e-3
+// bar of BASELINE.json (measured in tests/test_gpu_tf32.py) - on tensor cores instead of the CUDA-core conv_igemm_kernel.
+//
+//   mode 0   1x1 stride-1 conv == GEMM  D[pixels, Cout] = A[pixels, Cin] * W[Cout, Cin]^T (2D TMA); the squeeze-excitation
+//            scale of an MBConv projection (backbones/efficientnet.py:110-173, `scale * x`) is applied by the splitter
+//            warps to the A tile before the split: the separate scaling pass of the bf16 mode does not exist here
+//   mode 1   RxS conv (stride 1/2, dilation) as implicit GEMM: per tap the A tile is a shifted [8 x 16] pixel box of the
+//            NHWC input fetched by a 4D TMA; out-of-bounds = the reference's explicit zero padding (efficientnet.py:1127-1161)
+//   epilogue TMEM -> registers, + folded-BN bias, exact activation (expf SiLU), + residual, fp32 NHWC store.
+//
+// Shared-memory stage: [A raw/hi 128 rows | B raw/hi b_rows rows | A lo | B lo], rows of RB bytes (RB = 128: 32 fp32,
+// 128B swizzle; RB = 64: 16 fp32, 64B swizzle - used with 256-wide N tiles so that four stages stay in flight).  The lo
+// tiles mirror the raw tiles byte for byte, so the splitters never need to undo the TMA swizzle.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace mtb {
+
+constexpr int T32_THREADS = 608;  // warps 0-7 epilogue, 8 A producer, 9 B producer, 10 MMA + TMEM, 11-18 splitters
+constexpr int T32_SPLIT_WARPS = 8;
+constexpr int T32_MAX_STAGES = 8;
+constexpr int T32_RING_BYTES = 216 * 1024;
+constexpr int T32_BAR_OFF = T32_RING_BYTES;
+constexpr int T32_SMEM_BYTES = T32_BAR_OFF + 512 + 1024 /*align slack*/;
+
+struct Tc32Params {
+  const float* res;
+  const float* bias;
+  float* out;
+  const float* a_scale;  // mode 0: squeeze-excitation scale [B][Cin] applied to A before the split (nullptr: none)
+  int a_scale_P;         // pixels per crop
+  int mode;              // 0 flat 1x1 stride 1; 1 spatial tiles (4D TMA per tap)
+  int Hin, Win;
+  int M;                 // mode 0: rows
+  int Cout, Cin;
+  int bn, b_rows;        // N-tile stride; rows of the weight TMA box
+  int n_tiles, m_tiles, kchunks, taps;
+  int nstages, stage_stride, lo_off;
+  int Hout, Wout, tiles_w, tiles_h, pad_t, pad_l, R, S, stride, dil;
+};
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::tf32 instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = n
+__host__ __device__ inline uint32_t umma_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// hi = x rounded to tf32 (nearest, ties away: integer add on the bit pattern, carries into the exponent correctly),
+// lo = x - hi (exact: hi and x agree in sign/exponent up to one binade, the difference has <= 13 significant bits)
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = x - hi;
+}
+
+template <int ACT, int RES, int RB>
+__global__ void __launch_bounds__(T32_THREADS, 1)
+tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Tc32Params p) {
+  constexpr int BK = RB / 4;       // fp32 elements per row
+  constexpr int KSTEPS = RB / 32;  // MMAs (K = 8 tf32 = 32 bytes) per stage and product term
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + T32_BAR_OFF);
+  uint64_t* full = bars;                          // [8]  TMA landed (A + B producers)
+  uint64_t* split = bars + T32_MAX_STAGES;        // [8]  hi/lo tiles written (8 splitter warps)
+  uint64_t* empty = bars + 2 * T32_MAX_STAGES;    // [8]  tcgen05.commit
+  uint64_t* tmem_full = bars + 3 * T32_MAX_STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;             // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 9 && lane == 0) {
+    for (int i = 0; i < T32_MAX_STAGES; ++i) {
+      mbar_init(&full[i], 2);
+      mbar_init(&split[i], T32_SPLIT_WARPS);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], TCV_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 10) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_trigger();
+  pdl_wait();
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const uint32_t a_bytes = (uint32_t)TC_BM * RB;
+  const uint32_t b_bytes = (uint32_t)p.b_rows * RB;
+  const int nstages = p.nstages;
+  const int num_kb = pin(p.taps * p.kchunks);
+  const uint32_t stage_stride = pin((uint32_t)p.stage_stride);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), split0 = smem_u32(split);
+
+  if (warp == 8) {
+    // ===== A-operand TMA producer =====
+    uint32_t stage = 0, phase = 0, sa = smem_base;
+    const int kchunks = pin(p.kchunks);
+    TileWalk tw_(blockIdx.x, gridDim.x, p.n_tiles);
+    if (p.mode == 0) {
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
+        const int row0 = tw_.m_blk * TC_BM;
+#pragma unroll 1
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx_a(full0 + stage * 8, a_bytes);
+            tma_load_2d_a(sa, &tmA, full0 + stage * 8, kc * BK, row0);
+          }
+          __syncwarp();
+          sa += stage_stride;
+          if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; sa = smem_base; }
+        }
+      }
+    } else {
+      const int S = pin(p.S), dil = pin(p.dil);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
+        const int m_blk = tw_.m_blk;
+        const int tw = m_blk % p.tiles_w;
+        const int th = (m_blk / p.tiles_w) % p.tiles_h;
+        const int b = m_blk / (p.tiles_w * p.tiles_h);
+        const int ih0 = th * TC_TILE_H * p.stride - p.pad_t;
+        const int iw0 = tw * TC_TILE_W * p.stride - p.pad_l;
+        int r = 0, s_ = 0, kc = 0;
+#pragma unroll 1
+        for (int i = 0; i < num_kb; ++i) {
+          mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx_a(full0 + stage * 8, a_bytes);
+            tma_load_4d_a(sa, &tmA, full0 + stage * 8, kc * BK, iw0 + s_ * dil, ih0 + r * dil, b);
+          }
+          __syncwarp();
+          if (++kc == kchunks) {
+            kc = 0;
+            if (++s_ == S) { s_ = 0; ++r; }
+          }
+          sa += stage_stride;
+          if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; sa = smem_base; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===== B-operand (weights) TMA producer =====
+    uint32_t stage = 0, phase = 0, sb = smem_base + a_bytes;
+    const int taps = pin(p.taps), kchunks = pin(p.kchunks), Cin = pin(p.Cin), bn = pin(p.bn);
+    TileWalk tw_(blockIdx.x, gridDim.x, p.n_tiles);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
+      const int nrow = tw_.n_blk * bn;
+      int tap = 0, kc = 0;
+#pragma unroll 1
+      for (int i = 0; i < num_kb; ++i) {
+        mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx_a(full0 + stage * 8, b_bytes);
+          tma_load_2d_a(sb, &tmB, full0 + stage * 8, tap * Cin + kc * BK, nrow);
+        }
+        __syncwarp();
+        if (++kc == kchunks) { kc = 0; if (++tap == taps) tap = 0; }
+        sb += stage_stride;
+        if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; sb = smem_base + a_bytes; }
+      }
+    }
+  } else if (warp == 10) {
+    // ===== MMA issuer: three tf32 products per K step into one fp32 accumulator =====
+    uint32_t acc = 0, acc_phase = 0;
+    constexpr uint32_t hi_sw = (uint32_t)((8 * RB) >> 4) | (1u << 14) | ((RB == 128 ? 2u : 4u) << 29);
+    const uint32_t stride16 = stage_stride >> 4;
+    const uint32_t base16 = smem_base >> 4;
+    const uint32_t b_off16 = a_bytes >> 4;
+    const uint32_t lo16 = (uint32_t)p.lo_off >> 4;
+    const uint32_t tmem_full0 = smem_u32(tmem_full), tmem_empty0 = smem_u32(tmem_empty);
+    const int bn = pin(p.bn), Cout = pin(p.Cout);
+    TileWalk tw_(blockIdx.x, gridDim.x, p.n_tiles);
+    uint32_t stage = 0, phase = 0, a16 = base16;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
+      const int n_valid = min(bn, Cout - tw_.n_blk * bn);
+      const uint32_t idesc = umma_idesc_tf32((n_valid + 15) & ~15);
+      mbar_wait_a(tmem_empty0 + acc * 8, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * TC_MAX_BN;
+#pragma unroll 1
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait_a(split0 + stage * 8, phase);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < KSTEPS; ++k) {
+            const uint64_t a_hi = make_desc(a16 + 2 * k, hi_sw), b_hi = make_desc(a16 + b_off16 + 2 * k, hi_sw);
+            const uint64_t a_lo = make_desc(a16 + lo16 + 2 * k, hi_sw), b_lo = make_desc(a16 + lo16 + b_off16 + 2 * k, hi_sw);
+            umma_tf32(d_tmem, a_hi, b_hi, idesc, (uint32_t)(kb | k));
+            umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
+            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+          }
+          umma_commit_a(empty0 + stage * 8);
+          if (kb == num_kb - 1) umma_commit_a(tmem_full0 + acc * 8);
+        }
+        __syncwarp();
+        a16 += stride16;
+        if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; a16 = base16; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 11) {
+    // ===== splitters: raw fp32 tile -> (hi in place, lo in the mirror tile); optional SE scale on A (mode 0) =====
+    const int st = (warp - 11) * 32 + lane;            // 0..255
+    constexpr int CPR = RB / 16;                        // 16-byte chunks per row
+    const int a_chunks = TC_BM * CPR;
+    const int tot_chunks = (TC_BM + p.b_rows) * CPR;
+    const uint32_t lo_off = (uint32_t)p.lo_off;
+    const float* __restrict__ sc = p.a_scale;
+    const int kchunks = pin(p.kchunks), Cin = pin(p.Cin);
+    uint32_t stage = 0, phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m_blk = t / p.n_tiles;
+      int kc = 0;
+#pragma unroll 1
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait_a(full0 + stage * 8, phase);
+        uint8_t* base = smem + stage * stage_stride;
+#pragma unroll 2
+        for (int i = st; i < tot_chunks; i += T32_SPLIT_WARPS * 32) {
+          float4 v = *reinterpret_cast<const float4*>(base + i * 16);
+          if (sc != nullptr && i < a_chunks) {
+            // physical chunk j of row r holds logical chunk j ^ swz(r)  (128B swizzle: r & 7; 64B swizzle: (r >> 1) & 3)
+            const int r = i / CPR, j = i - r * CPR;
+            const int jl = RB == 128 ? (j ^ (r & 7)) : (j ^ ((r >> 1) & 3));
+            const int k = kc * BK + jl * 4;
+            const int m = m_blk * TC_BM + r;
+            if (m < p.M && k < Cin) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + (size_t)(m / p.a_scale_P) * Cin + k));
+              v.x *= s4.x; v.y *= s4.y; v.z *= s4.z; v.w *= s4.w;
+            }
+          }
+          float4 h, l;
+          split_tf32(v.x, h.x, l.x);
+          split_tf32(v.y, h.y, l.y);
+          split_tf32(v.z, h.z, l.z);
+          split_tf32(v.w, h.w, l.w);
+          *reinterpret_cast<float4*>(base + i * 16) = h;
+          *reinterpret_cast<float4*>(base + lo_off + i * 16) = l;
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split[stage]);
+        if (++kc == kchunks) kc = 0;
+        if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue (warps 0-7): warp w owns TMEM lanes / tile rows [32(w&3), +32) and the 32-column chunks c = (w>>2) mod 2 =====
+    const int q = warp & 3, par = warp >> 2;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const float* __restrict__ res = p.res;
+    float* __restrict__ out = p.out;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m_blk = t / p.n_tiles, n_blk = t - m_blk * p.n_tiles;
+      const int n0 = n_blk * p.bn;
+      const int n_valid = min(p.bn, p.Cout - n0);
+      bool valid;
+      size_t off;
+      if (p.mode == 0) {
+        const int m = m_blk * TC_BM + row;
+        valid = m < p.M;
+        off = (size_t)m * p.Cout;
+      } else {
+        const int tw = m_blk % p.tiles_w;
+        const int th = (m_blk / p.tiles_w) % p.tiles_h;
+        const int b = m_blk / (p.tiles_w * p.tiles_h);
+        const int oh = th * TC_TILE_H + (row >> 4), ow = tw * TC_TILE_W + (row & 15);
+        valid = oh < p.Hout && ow < p.Wout;
+        off = ((size_t)(b * p.Hout + oh) * p.Wout + ow) * p.Cout;
+      }
+      mbar_wait_a(smem_u32(&tmem_full[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_MAX_BN;
+      const int nchunks = (n_valid + 31) >> 5;
+      for (int ch = par; ch < nchunks; ch += 2) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int c0 = ch * 32 + hf * 16;
+          if (c0 >= n_valid) break;  // warp-uniform
+          float4 rv[4];
+          if constexpr (RES != 0) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              rv[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (valid && c0 + g * 4 < n_valid) rv[g] = *reinterpret_cast<const float4*>(res + off + n0 + c0 + g * 4);
+            }
+          }
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (c0 + g * 4 < n_valid) {  // Cout is a multiple of 4
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g * 4));
+              float o[4] = {v[g * 4 + 0] + b4.x, v[g * 4 + 1] + b4.y, v[g * 4 + 2] + b4.z, v[g * 4 + 3] + b4.w};
+              if constexpr (RES == 2) {
+                o[0] = act_t<ACT>(o[0] + rv[g].x); o[1] = act_t<ACT>(o[1] + rv[g].y);
+                o[2] = act_t<ACT>(o[2] + rv[g].z); o[3] = act_t<ACT>(o[3] + rv[g].w);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = act_t<ACT>(o[i]);
+                if constexpr (RES == 1) { o[0] += rv[g].x; o[1] += rv[g].y; o[2] += rv[g].z; o[3] += rv[g].w; }
+              }
+              if (valid) *reinterpret_cast<float4*>(out + off + n0 + c0 + g * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          }
+        }
+      }
+      // hand the accumulator back (every epilogue warp arrives once per tile, after its last TMEM read)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+// rank-2 fp32 tensor [rows][cols] (cols contiguous), box [box_rows][box_cols], swizzle = row bytes, OOB -> 0
+inline const char* make_tmap_2d_f32(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+  tmap_encode_fn enc = get_tmap_encode();
+  if (!enc) return "cuTensorMapEncodeTiled unavailable";
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 4};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(2d, f32) failed";
+}
+// rank-4 fp32 NHWC tensor; box = box_c channels x (16 x 8) pixels sampled every `stride` pixels
+inline const char* make_tmap_nhwc_f32(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t stride,
+                                      uint32_t box_c) {
+  tmap_encode_fn enc = get_tmap_encode();
+  if (!enc) return "cuTensorMapEncodeTiled unavailable";
+  cuuint64_t dims[4] = {C, W, H, B};
+  cuuint64_t strides[3] = {C * 4, W * C * 4, H * W * C * 4};
+  cuuint32_t box[4] = {box_c, TC_TILE_W * stride, TC_TILE_H * stride, 1};
+  cuuint32_t estr[4] = {1, stride, stride, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(4d, f32) failed";
+}
+
+struct Tc32Weights {
+  bool ready = false;
+  float* d_w = nullptr;     // fp32 [Cout][taps*Cin] K-major (BN folded)
+  float* d_bias = nullptr;  // [Cout]
+  int Cout = 0, Cin = 0, taps = 1, S = 1;
+  struct MapSet {
+    CUtensorMap a, b;
+    const void* in = nullptr;
+    int B = -1, bn = 0, rb = 0;
+  };
+  mutable std::vector<MapSet> map_sets;
+  mutable size_t map_rr = 0;
+};
+
+// wk: fp32 [K = taps*Cin][Cout] (BN folded) -> fp32 [Cout][K]
+inline const char* tc32_prepare_weights(Tc32Weights& w, const float* wk, const float* bias, int K, int cout, int R, int S, int cin,
+                                        std::vector<void*>& allocs) {
+  std::vector<float> t((size_t)K * cout);
+  for (int k = 0; k < K; ++k)
+    for (int n = 0; n < cout; ++n) t[(size_t)n * K + k] = wk[(size_t)k * cout + n];
+  if (cudaMalloc((void**)&w.d_w, t.size() * 4) != cudaSuccess) return "cudaMalloc failed";
+  allocs.push_back(w.d_w);
+  if (cudaMemcpy(w.d_w, t.data(), t.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return "cudaMemcpy failed";
+  if (cudaMalloc((void**)&w.d_bias, (size_t)cout * 4) != cudaSuccess) return "cudaMalloc failed";
+  allocs.push_back(w.d_bias);
+  if (cudaMemcpy(w.d_bias, bias, (size_t)cout * 4, cudaMemcpyHostToDevice) != cudaSuccess) return "cudaMemcpy failed";
+  w.Cout = cout; w.Cin = cin; w.taps = R * S; w.S = S;
+  w.ready = true;
+  w.map_sets.clear();
+  return nullptr;
+}
+
+// the 3xTF32 kernel takes what the bf16 tensor-core kernel takes, with fp32 alignment rules (16-byte TMA strides / stores)
+inline bool tc32_eligible(bool is_conv, bool depthwise, bool small_io, int k, int stride, int cin, int cout) {
+  if (!is_conv || depthwise || small_io) return false;
+  if (cin % 4 != 0 || cout % 4 != 0) return false;
+  return (stride == 1 || stride == 2) && (k == 1 || k == 3);
+}
+
+// N-tile stride and row bytes.  Per-stage MMA time (cycles) = 3 products x (RB/32) K steps x N/2; a stage of 256-wide
+// tiles with 128-byte rows is 96 KB (two stages in flight: TMA + split + MMA serialise), so those use 64-byte rows
+// (48 KB stages, four in flight).
+inline void tc32_pick_tile(int cout, int m_tiles, int num_kb32, int* bn_out, int* rb_out) {
+  int best = 64, best_rb = 128;
+  double best_cost = 1e30;
+  for (int bn = 256; bn >= 64; bn -= 64) {
+    const int nt = (cout + bn - 1) / bn;
+    const long tiles = (long)m_tiles * nt;
+    const long waves = (tiles + 147) / 148;
+    const int last = cout - (nt - 1) * bn;
+    const double avg_n = ((double)(nt - 1) * bn + ((last + 15) & ~15)) / nt;
+    const int rb = bn > 128 ? 64 : 128;
+    const int kb = rb == 128 ? num_kb32 : 2 * num_kb32;
+    const double mma_kb = 3.0 * (rb / 32) * avg_n / 2.0;
+    // L2 -> SM operand bytes per k-block at ~40 B/clk, and the fixed per-k-block issue cost
+    const double fill_kb = (128.0 + (nt == 1 ? ((cout + 15) & ~15) : bn)) * rb / 40.0;
+    double per_kb = mma_kb;
+    if (fill_kb > per_kb) per_kb = fill_kb;
+    if (per_kb < 350.0) per_kb = 350.0;
+    const double cost = (double)waves * (kb * per_kb + 600.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; best_rb = rb; }
+  }
+  *bn_out = best;
+  *rb_out = best_rb;
+}
+
+template <int ACT, int RES, int RB>
+inline const char* tc32_launch_k(int grid, const CUtensorMap& a, const CUtensorMap& b, const Tc32Params& q, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc32_conv_kernel<ACT, RES, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, T32_SMEM_BYTES) != cudaSuccess)
+      return "cannot raise dynamic shared memory for tc32_conv_kernel";
+    attr_set = true;
+  }
+  launch_k(tc32_conv_kernel<ACT, RES, RB>, dim3(grid), dim3(T32_THREADS), T32_SMEM_BYTES, st, a, b, q);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+template <int ACT>
+inline const char* tc32_dispatch_res(int res_mode, int rb, int grid, const CUtensorMap& a, const CUtensorMap& b, const Tc32Params& q,
+                                     cudaStream_t st) {
+  if (rb == 128) {
+    switch (res_mode) {
+      case 0: return tc32_launch_k<ACT, 0, 128>(grid, a, b, q, st);
+      case 1: return tc32_launch_k<ACT, 1, 128>(grid, a, b, q, st);
+      default: return tc32_launch_k<ACT, 2, 128>(grid, a, b, q, st);
+    }
+  }
+  switch (res_mode) {
+    case 0: return tc32_launch_k<ACT, 0, 64>(grid, a, b, q, st);
+    case 1: return tc32_launch_k<ACT, 1, 64>(grid, a, b, q, st);
+    default: return tc32_launch_k<ACT, 2, 64>(grid, a, b, q, st);
+  }
+}
+
+inline const char* tc32_conv_launch(const Tc32Weights& w, const ConvParams& p, bool res_first, cudaStream_t st) {
+  Tc32Params q;
+  q.res = (const float*)p.res; q.bias = w.d_bias; q.out = (float*)p.out;
+  q.mode = (p.R == 1 && p.stride == 1) ? 0 : 1;
+  q.a_scale = q.mode == 0 ? p.a_scale : nullptr;
+  if (p.a_scale && q.mode != 0) return "squeeze-excitation scale on a spatial conv is not supported by the 3xTF32 kernel";
+  q.a_scale_P = p.Hin * p.Win;
+  q.Hin = p.Hin; q.Win = p.Win;
+  q.Cout = p.Cout; q.Cin = p.Cin;
+  q.taps = w.taps; q.R = p.R; q.S = w.S; q.stride = p.stride; q.dil = p.dil;
+  q.Hout = p.Hout; q.Wout = p.Wout; q.pad_t = p.pad_t; q.pad_l = p.pad_l;
+  q.tiles_w = (p.Wout + TC_TILE_W - 1) / TC_TILE_W;
+  q.tiles_h = (p.Hout + TC_TILE_H - 1) / TC_TILE_H;
+  q.M = p.B * p.Hout * p.Wout;
+  q.m_tiles = q.mode == 0 ? (q.M + TC_BM - 1) / TC_BM : p.B * q.tiles_w * q.tiles_h;
+  int bn = 64, rb = 128;
+  tc32_pick_tile(p.Cout, q.m_tiles, q.taps * ((p.Cin + 31) / 32), &bn, &rb);
+  {
+    static int rb_env = -1, bn_env = -1;  // A/B switches: MTB_T32_RB = 64 | 128, MTB_T32_BN = 64..256
+    if (rb_env < 0) { const char* e = getenv("MTB_T32_RB"); rb_env = e ? atoi(e) : 0; }
+    if (bn_env < 0) { const char* e = getenv("MTB_T32_BN"); bn_env = e ? atoi(e) : 0; }
+    if (rb_env == 64 || rb_env == 128) rb = rb_env;
+    if (bn_env >= 64 && bn_env <= 256 && bn_env % 64 == 0) bn = bn_env;
+  }
+  const int bk = rb / 4;
+  q.bn = bn;
+  q.n_tiles = (p.Cout + bn - 1) / bn;
+  q.kchunks = (p.Cin + bk - 1) / bk;
+  q.b_rows = q.n_tiles == 1 ? (p.Cout + 15) / 16 * 16 : bn;
+  q.lo_off = (TC_BM + q.b_rows) * rb;
+  q.stage_stride = (2 * q.lo_off + 1023) / 1024 * 1024;
+  q.nstages = T32_RING_BYTES / q.stage_stride;
+  if (q.nstages > T32_MAX_STAGES) q.nstages = T32_MAX_STAGES;
+  if (q.nstages < 2) return "operand ring too small for this tile";
+  const Tc32Weights::MapSet* ms = nullptr;
+  for (const Tc32Weights::MapSet& c : w.map_sets)
+    if (c.in == p.in && c.B == p.B && c.bn == bn && c.rb == rb) { ms = &c; break; }
+  if (!ms) {
+    Tc32Weights::MapSet c;
+    const char* e = q.mode == 0 ? make_tmap_2d_f32(&c.a, p.in, (uint64_t)q.M, (uint64_t)p.Cin, TC_BM, (uint32_t)bk)
+                                : make_tmap_nhwc_f32(&c.a, p.in, p.B, p.Hin, p.Win, p.Cin, (uint32_t)p.stride, (uint32_t)bk);
+    if (e) return e;
+    e = make_tmap_2d_f32(&c.b, w.d_w, (uint64_t)p.Cout, (uint64_t)w.taps * p.Cin, (uint32_t)q.b_rows, (uint32_t)bk);
+    if (e) return e;
+    c.in = p.in; c.B = p.B; c.bn = bn; c.rb = rb;
+    if (w.map_sets.size() < 16) {
+      w.map_sets.push_back(c);
+      ms = &w.map_sets.back();
+    } else {
+      w.map_sets[w.map_rr % 16] = c;
+      ms = &w.map_sets[w.map_rr % 16];
+      ++w.map_rr;
+    }
+  }
+  const int total = q.m_tiles * q.n_tiles;
+  const int grid = total < 148 ? total : 148;
+  const int res_mode = p.res ? (res_first ? 2 : 1) : 0;
+  switch (p.act) {
+    case ACT_NONE: return tc32_dispatch_res<ACT_NONE>(res_mode, rb, grid, ms->a, ms->b, q, st);
+    case ACT_SILU: return tc32_dispatch_res<ACT_SILU>(res_mode, rb, grid, ms->a, ms->b, q, st);
+    case ACT_RELU: return tc32_dispatch_res<ACT_RELU>(res_mode, rb, grid, ms->a, ms->b, q, st);
+    case ACT_HSWISH: return tc32_dispatch_res<ACT_HSWISH>(res_mode, rb, grid, ms->a, ms->b, q, st);
+    default: return "unsupported activation in the 3xTF32 epilogue";
+  }
+}
+
+}  // namespace mtb

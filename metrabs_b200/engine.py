@@ -23,7 +23,7 @@ def make_config(cfg, n_joints, stages=None, last_channel=0, arch=_lib.ARCH_EFFNE
     c.abi_version = _lib.MTB_ABI_VERSION
     c.arch = arch
     c.precision = {'fp32': _lib.PRECISION_FP32, 'bf16': _lib.PRECISION_BF16_TC,
-                   'bf16_simt': _lib.PRECISION_BF16_SIMT}[cfg.precision]
+                   'bf16_simt': _lib.PRECISION_BF16_SIMT, 'tf32x3': _lib.PRECISION_TF32X3}[cfg.precision]
     c.device = device
     c.proc_side = int(cfg.proc_side)
     c.stride_train = int(cfg.stride_train)
@@ -69,7 +69,8 @@ class Engine:
         check(lib().mtb_feature_shape(self._h, C.byref(hw), C.byref(ch)), self._h)
         self.feature_side, self.feature_channels = hw.value, ch.value
         self.n_joints, self.depth = mtb_config.n_joints, mtb_config.depth
-        self.feature_dtype = torch.float32 if mtb_config.precision == _lib.PRECISION_FP32 else torch.bfloat16
+        self.feature_dtype = (torch.float32 if mtb_config.precision in (_lib.PRECISION_FP32, _lib.PRECISION_TF32X3)
+                              else torch.bfloat16)
 
     def close(self):
         if getattr(self, '_h', None):

@@ -153,14 +153,18 @@ def test_tiny_model_golden(H, golden_dir, fname):
     assert torch.equal(outs[0], out_h)
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
 @pytest.mark.parametrize('name,side,j,batch,fname', [
     ('efficientnetv2-s', 256, 24, 3, 'effnetv2s_s256_j24.npz'),
     ('efficientnetv2-s', 256, 122, 2, 'effnetv2s_s256_j122.npz'),
     ('efficientnetv2-l', 256, 24, 2, 'effnetv2l_s256_j24.npz'),
     ('efficientnetv2-l', 384, 24, 1, 'effnetv2l_s384_j24.npz'),
 ])
-def test_full_models_fp32(H, golden_dir, name, side, j, batch, fname):
-    """fp32 parity mode: device vs the oracle port on the same weights/inputs, and vs the reference's goldens."""
+def test_full_models_parity_modes(H, golden_dir, name, side, j, batch, fname, precision):
+    """The two modes that must meet BASELINE.json's 1e-3 bar - 'fp32' (CUDA-core FMA) and 'tf32x3' (tcgen05 kind::tf32, three
+    split products, fp32 accumulate) - against the oracle port on the same weights/inputs AND against the goldens the
+    unmodified reference produced (/root/reference/metrabs_pytorch/models/metrabs.py:47-64), the latter at the golden's
+    own batch size (reconstruct_ref_fullpersp normalises with batch-global RMS, ptu3d.py:71-74)."""
     g = _golden(golden_dir, fname)
     pcfg = port.PathConfig(proc_side=side)
     spec = port.effnet_spec(name)
@@ -169,19 +173,23 @@ def test_full_models_fp32(H, golden_dir, name, side, j, batch, fname):
     stages = {}
     with torch.inference_mode():
         ref = port.metrabs_forward(sd, spec, pcfg, j, crops, k, stages=stages)
-    m = H.device_model(name, pcfg, j, sd)
+    m = H.device_model(name, pcfg, j, sd, precision=precision)
     eng = m.engine()
     feats = eng.backbone(crops.cuda())
     e_feat = H.rel_err(feats.permute(0, 3, 1, 2), stages['features'])
     out = m((crops.cuda(), k.cuda()))
     e_out = H.rel_err(out, ref)
-    print(f'{name}@{side} J={j}: features {e_feat:.2e}, joints {e_out:.2e}')
     assert e_feat < 1e-3
     assert e_out < 1e-3
     gb = int(g['batch'])
-    assert H.rel_err(out[:gb], g['coords3d_abs']) < 2e-3 or batch != gb  # golden batch may differ (batch-global RMS)
-    if batch == gb:
-        assert H.rel_err(out, g['coords3d_abs']) < 1e-3
+    gcrops, gk = port.synthetic_inputs(gb, side, seed=int(g['seed']))
+    gout = m((gcrops.cuda(), gk.cuda()))
+    e_gold = H.rel_err(gout, g['coords3d_abs'])
+    e_gfeat = H.rel_err(eng.backbone(gcrops.cuda()).permute(0, 3, 1, 2).reshape(gb, -1)[:, ::int(g['feature_stride'])], g['features'])
+    print(f'{name}@{side} J={j} [{precision}]: vs oracle features {e_feat:.2e} joints {e_out:.2e}; vs reference goldens '
+          f'features {e_gfeat:.2e} joints {e_gold:.2e}; launches {eng.last_launch_count}')
+    assert e_gfeat < 1e-3
+    assert e_gold < 1e-3
 
 
 @pytest.mark.parametrize('kind,cfgkw,j,batch', [

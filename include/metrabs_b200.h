@@ -168,6 +168,95 @@ int mtb_comm_unique_id(void* id128 /* host, 128 bytes */);
 int mtb_comm_init(mtb_handle* h, const void* id128, int rank, int world_size);
 int mtb_allgather_joints(mtb_handle* h, const float* local, int floats_per_rank, float* all, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * The callers either side of the crop model (/root/reference/metrabs_pytorch/multiperson/).  Handle-free
+ * device functions: every pointer is a DEVICE pointer, work is enqueued on `stream`, nothing is allocated or synchronised.
+ * Crop order: flat index = aug * n_boxes + box (multiperson_model.py:236-239).
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* Gamma decoding `(images / 255) ** 2.2` (multiperson_model.py:200) + the box-filter pyramid of warp_images_with_pyramid
+ * (warping.py:9-13).  images: u8 NCHW [n,3,H,W].  level1 [n,3,H/2,W/2] and level2 [n,3,H/4,W/4] are fp32 (floor sizes);
+ * level 0 is decoded on the fly by mtb_warp_crops. */
+int mtb_image_pyramid(const uint8_t* images, int n_images, int height, int width, float* level1, float* level2,
+                      void* stream);
+
+/* _get_new_rotation_and_scale (multiperson_model.py:321-355) + the per-crop matrices of _get_crops (:264-293) + the
+ * pyramid level choice (warping.py:20-21). */
+typedef struct {
+  const float* boxes;            /* [n_boxes, box_stride]: x, y, w, h(, score) in image pixels */
+  int32_t box_stride;
+  const float* intrinsics;       /* [n_boxes,3,3] of the image each box lives in */
+  const float* distortion;       /* [n_boxes, n_dist] OpenCV order (k1,k2,p1,p2,k3,k4,k5,k6,s1..s4), zero padded */
+  int32_t n_dist;                /* 0..12 */
+  const float* camspace_up;      /* [n_boxes,3] */
+  const float* aug_rotflipmat;   /* [num_aug,3,3] */
+  const float* aug_scales;       /* [num_aug] */
+  int32_t n_boxes, num_aug, resolution, antialias_factor;
+  float* new_intrinsics;         /* out [num_aug*n_boxes,3,3] (the intrinsics mtb_forward takes) */
+  float* rotations;              /* out [num_aug*n_boxes,3,3] R = aug_rotflipmat @ R_noaug */
+  float* inv_projections;        /* out [num_aug*n_boxes,3,3] inv(new_intrinsics @ R) (@ antialias scaling) */
+  int32_t* pyramid_levels;       /* out [num_aug*n_boxes] */
+} mtb_crop_setup_args;
+int mtb_crop_setup(const mtb_crop_setup_args* args, void* stream);
+
+/* warp_images_with_pyramid + the gamma of _get_crops (warping.py:6-52, multiperson_model.py:295-319): every crop of the
+ * batch in ONE launch, written as the fp32 NCHW [num_aug*n_boxes,3,res,res] tensor mtb_forward reads.  antialias_factor
+ * 1, 2 or 4 (rendered by supersampling = the reference's larger render followed by avg_pool2d). */
+typedef struct {
+  const uint8_t* images;         /* [n_images,3,H,W] u8 */
+  const float* level1;           /* from mtb_image_pyramid */
+  const float* level2;
+  int32_t n_images, height, width;
+  const float* intrinsics;       /* [n_boxes,3,3] */
+  const float* distortion;       /* [n_boxes, n_dist] */
+  int32_t n_dist;
+  const int32_t* image_ids;      /* [n_boxes] */
+  const float* inv_projections;  /* [num_aug*n_boxes,3,3] */
+  const int32_t* pyramid_levels; /* [num_aug*n_boxes] */
+  const float* gamma_exponents;  /* [num_aug] = aug_gammas / 2.2 */
+  int32_t n_boxes, num_aug, resolution, antialias_factor;
+  float* crops;                  /* out [num_aug*n_boxes,3,res,res] */
+} mtb_warp_args;
+int mtb_warp_crops(const mtb_warp_args* args, void* stream);
+
+/* The epilogue of _predict_single_batch (mirror swap, poses @ R; multiperson_model.py:246-259) and of
+ * _estimate_poses_batched (joint transform, 2D projection with distortion + intrinsics, inverse extrinsics, skeleton
+ * gather, mean over augmentations; :143-182). */
+typedef struct {
+  const float* poses;            /* [num_aug*n_boxes, J, 3] crop-model output */
+  const float* rotations;        /* [num_aug*n_boxes,3,3] */
+  const uint8_t* aug_should_flip;/* [num_aug] */
+  const int32_t* mirror_mapping; /* [J] */
+  const float* joint_transform;  /* [J, J2] or NULL (J2 = J) */
+  const int32_t* skeleton;       /* [Js] indices into J2, or NULL (Js = J2) */
+  const float* intrinsics;       /* [n_boxes,3,3] */
+  const float* distortion;       /* [n_boxes, n_dist] */
+  int32_t n_dist;
+  const float* extrinsics_inv;   /* [n_boxes,4,4] inverse extrinsic matrix of the box's image */
+  int32_t n_boxes, num_aug, n_joints, n_joints_transformed, n_skeleton, average_aug;
+  float* poses3d;                /* out [n_boxes,(num_aug,)Js,3] */
+  float* poses2d;                /* out [n_boxes,(num_aug,)Js,2] */
+} mtb_tta_args;
+int mtb_tta_merge(const mtb_tta_args* args, void* stream);
+
+/* plausibility_check.py:8-119: is_pose_plausible, are_augmentation_results_consistent, is_pose_consistent_with_box and
+ * pose_non_max_suppression (similarity threshold 0.4) per image.  At most 128 boxes per image, num_aug <= 16. */
+typedef struct {
+  const float* poses3d;          /* [n_boxes, num_aug, J, 3] camera space */
+  const float* poses2d;          /* [n_boxes, num_aug, J, 2] */
+  const float* boxes;            /* [n_boxes, box_stride] x, y, w, h, score */
+  int32_t box_stride;
+  const int32_t* bones;          /* [n_bones,2] joint pairs (rows of joint2bone_mat) */
+  const float* mean_bones;       /* [n_bones] mm */
+  int32_t n_bones;
+  const int32_t* image_start;    /* [n_images+1] box range of each image */
+  int32_t n_images, n_boxes, num_aug, n_joints;
+  uint8_t* plausible;            /* out [n_boxes] */
+  uint8_t* keep;                 /* out [n_boxes]: plausible and not suppressed */
+  float* scratch;                /* [n_boxes, J, 3] */
+} mtb_filter_args;
+int mtb_filter_poses(const mtb_filter_args* args, void* stream);
+
 /* Introspection for tests / profiling. */
 int mtb_num_ops(const mtb_handle* h);
 const char* mtb_op_name(const mtb_handle* h, int op);

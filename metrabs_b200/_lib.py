@@ -28,6 +28,38 @@ class MtbConfig(C.Structure):
                 ('n_stages', C.c_int32), ('last_channel', C.c_int32), ('stages', MtbStage * MTB_MAX_STAGES)]
 
 
+class MtbCropSetupArgs(C.Structure):
+    _fields_ = [('boxes', C.c_void_p), ('box_stride', C.c_int32), ('intrinsics', C.c_void_p), ('distortion', C.c_void_p),
+                ('n_dist', C.c_int32), ('camspace_up', C.c_void_p), ('aug_rotflipmat', C.c_void_p), ('aug_scales', C.c_void_p),
+                ('n_boxes', C.c_int32), ('num_aug', C.c_int32), ('resolution', C.c_int32), ('antialias_factor', C.c_int32),
+                ('new_intrinsics', C.c_void_p), ('rotations', C.c_void_p), ('inv_projections', C.c_void_p),
+                ('pyramid_levels', C.c_void_p)]
+
+
+class MtbWarpArgs(C.Structure):
+    _fields_ = [('images', C.c_void_p), ('level1', C.c_void_p), ('level2', C.c_void_p), ('n_images', C.c_int32),
+                ('height', C.c_int32), ('width', C.c_int32), ('intrinsics', C.c_void_p), ('distortion', C.c_void_p),
+                ('n_dist', C.c_int32), ('image_ids', C.c_void_p), ('inv_projections', C.c_void_p),
+                ('pyramid_levels', C.c_void_p), ('gamma_exponents', C.c_void_p), ('n_boxes', C.c_int32),
+                ('num_aug', C.c_int32), ('resolution', C.c_int32), ('antialias_factor', C.c_int32), ('crops', C.c_void_p)]
+
+
+class MtbTtaArgs(C.Structure):
+    _fields_ = [('poses', C.c_void_p), ('rotations', C.c_void_p), ('aug_should_flip', C.c_void_p),
+                ('mirror_mapping', C.c_void_p), ('joint_transform', C.c_void_p), ('skeleton', C.c_void_p),
+                ('intrinsics', C.c_void_p), ('distortion', C.c_void_p), ('n_dist', C.c_int32),
+                ('extrinsics_inv', C.c_void_p), ('n_boxes', C.c_int32), ('num_aug', C.c_int32), ('n_joints', C.c_int32),
+                ('n_joints_transformed', C.c_int32), ('n_skeleton', C.c_int32), ('average_aug', C.c_int32),
+                ('poses3d', C.c_void_p), ('poses2d', C.c_void_p)]
+
+
+class MtbFilterArgs(C.Structure):
+    _fields_ = [('poses3d', C.c_void_p), ('poses2d', C.c_void_p), ('boxes', C.c_void_p), ('box_stride', C.c_int32),
+                ('bones', C.c_void_p), ('mean_bones', C.c_void_p), ('n_bones', C.c_int32), ('image_start', C.c_void_p),
+                ('n_images', C.c_int32), ('n_boxes', C.c_int32), ('num_aug', C.c_int32), ('n_joints', C.c_int32),
+                ('plausible', C.c_void_p), ('keep', C.c_void_p), ('scratch', C.c_void_p)]
+
+
 class MetrabsB200Error(RuntimeError):
     pass
 
@@ -58,6 +90,11 @@ _SIGNATURES = {
     'mtb_comm_unique_id': (C.c_int, [C.c_void_p]),
     'mtb_comm_init': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     'mtb_allgather_joints': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    'mtb_image_pyramid': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'mtb_crop_setup': (C.c_int, [C.POINTER(MtbCropSetupArgs), C.c_void_p]),
+    'mtb_warp_crops': (C.c_int, [C.POINTER(MtbWarpArgs), C.c_void_p]),
+    'mtb_tta_merge': (C.c_int, [C.POINTER(MtbTtaArgs), C.c_void_p]),
+    'mtb_filter_poses': (C.c_int, [C.POINTER(MtbFilterArgs), C.c_void_p]),
     'mtb_num_ops': (C.c_int, [C.c_void_p]),
     'mtb_op_name': (C.c_char_p, [C.c_void_p, C.c_int]),
     'mtb_debug_run_ops': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,

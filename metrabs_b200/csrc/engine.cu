@@ -22,6 +22,7 @@
 #include "tc_gemm_pair.cuh"
 #include "tc_gemm_bres.cuh"
 #include "se_cluster.cuh"
+#include "multiperson.cuh"
 
 using namespace mtb;
 
@@ -122,6 +123,8 @@ struct mtb_handle {
   void* pipe_ws = nullptr;
   size_t pipe_ws_bytes = 0;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t graph_stream = nullptr;  // MTB_GRAPH=1 with the legacy default stream: captured forwards run here
+  cudaEvent_t graph_in = nullptr, graph_out = nullptr;
   // profiler
   unsigned prof_mask = 0;
   std::vector<cudaEvent_t> prof_events;  // pairs
@@ -1164,6 +1167,9 @@ int mtb_destroy(mtb_handle* h) {
       if (e.exec) cudaGraphExecDestroy(e.exec);
     if (h->pipe_ws) cudaFree(h->pipe_ws);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->graph_stream) cudaStreamDestroy(h->graph_stream);
+    if (h->graph_in) cudaEventDestroy(h->graph_in);
+    if (h->graph_out) cudaEventDestroy(h->graph_out);
     cudaGetLastError();
     for (size_t i = 0; i < h->prof_events.size(); ++i) {
       cudaError_t e = cudaEventDestroy(h->prof_events[i]);
@@ -1448,30 +1454,55 @@ int mtb_forward(mtb_handle* h, const float* crops, const float* intrinsics, int 
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cs);
     if (cs == cudaStreamCaptureStatusNone) {  // (a caller capturing this stream itself just records our launches)
+      // the legacy default stream cannot be captured: fork to an internal stream and join back with events
+      const bool side = st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread;
+      cudaStream_t gs = st;
+      if (side) {
+        if (!h->graph_stream) {
+          CUDA_TRY(h, cudaStreamCreateWithFlags(&h->graph_stream, cudaStreamNonBlocking));
+          CUDA_TRY(h, cudaEventCreateWithFlags(&h->graph_in, cudaEventDisableTiming));
+          CUDA_TRY(h, cudaEventCreateWithFlags(&h->graph_out, cudaEventDisableTiming));
+        }
+        gs = h->graph_stream;
+      }
+      auto launch = [&](cudaGraphExec_t ex) -> cudaError_t {
+        cudaError_t e = cudaSuccess;
+        if (side) {
+          if ((e = cudaEventRecord(h->graph_in, st)) != cudaSuccess) return e;
+          if ((e = cudaStreamWaitEvent(gs, h->graph_in, 0)) != cudaSuccess) return e;
+        }
+        if ((e = cudaGraphLaunch(ex, gs)) != cudaSuccess) return e;
+        if (side) {
+          if ((e = cudaEventRecord(h->graph_out, gs)) != cudaSuccess) return e;
+          if ((e = cudaStreamWaitEvent(st, h->graph_out, 0)) != cudaSuccess) return e;
+        }
+        return e;
+      };
       mtb_handle::GraphEntry* ent = nullptr;
       for (auto& e : h->graphs)
         if (e.crops == crops && e.k == intrinsics && e.out == coords3d_abs && e.ws == workspace && e.batch == batch && e.st == st) ent = &e;
       if (ent && ent->exec) {
-        CUDA_TRY(h, cudaGraphLaunch(ent->exec, st));
+        CUDA_TRY(h, launch(ent->exec));
         h->launches = ent->launches;
         return MTB_OK;
       }
       if (ent && !ent->failed) {  // second sighting of this key: capture
-        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
-          rc = forward_body(h, crops, intrinsics, batch, coords3d_abs, workspace, st);
+        if (side) cudaStreamSynchronize(st);  // (once per key) everything the capture stream must see has completed
+        if (cudaStreamBeginCapture(gs, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+          rc = forward_body(h, crops, intrinsics, batch, coords3d_abs, workspace, gs);
           cudaGraph_t gr = nullptr;
-          cudaError_t ce = cudaStreamEndCapture(st, &gr);
+          cudaError_t ce = cudaStreamEndCapture(gs, &gr);
           cudaGraphExec_t ex = nullptr;
           if (rc == MTB_OK && ce == cudaSuccess && gr && cudaGraphInstantiate(&ex, gr, 0) == cudaSuccess) {
             cudaGraphDestroy(gr);
             ent->exec = ex;
             ent->launches = h->launches;
-            CUDA_TRY(h, cudaGraphLaunch(ent->exec, st));
+            CUDA_TRY(h, launch(ent->exec));
             return MTB_OK;
           }
           if (gr) cudaGraphDestroy(gr);
-          cudaGetLastError();
         }
+        cudaGetLastError();  // a refused capture leaves a sticky error behind: clear it before the plain launches
         ent->failed = true;  // plain launches for this key from now on
       } else if (!ent) {
         if (h->graphs.size() >= 8) drop_graphs_on(h, nullptr);  // a caller cycling through many buffers: bounded state
@@ -1630,6 +1661,99 @@ int mtb_allgather_joints(mtb_handle* h, const float* local, int floats_per_rank,
   if (!f) return fail(h, MTB_ERR_NCCL, "ncclAllGather not found");
   int rc = f(local, all, (size_t)floats_per_rank, /*ncclFloat32*/ 7, h->nccl_comm, (cudaStream_t)stream);
   if (rc) return fail(h, MTB_ERR_NCCL, "ncclAllGather failed (%d)", rc);
+  return MTB_OK;
+}
+
+// ------------------------------------------------------------------------------------ multiperson
+int mtb_image_pyramid(const uint8_t* images, int n_images, int height, int width, float* level1, float* level2, void* stream) {
+  if (!images || !level1 || !level2 || n_images <= 0 || height < 4 || width < 4)
+    return fail(nullptr, MTB_ERR_INVALID_ARG, "invalid pyramid arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int planes = n_images * 3;
+  const size_t t1 = (size_t)planes * (height / 2) * (width / 2), t2 = (size_t)planes * (height / 4) * (width / 4);
+  launch_k(pyramid_level1_kernel, dim3(grid_for(t1, 256)), dim3(256), 0, st, images, level1, planes, height, width);
+  launch_k(pyramid_down_kernel, dim3(grid_for(t2, 256)), dim3(256), 0, st, (const float*)level1, level2, planes, height / 2, width / 2);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(nullptr, MTB_ERR_CUDA, "pyramid launch: %s", cudaGetErrorString(e));
+  return MTB_OK;
+}
+
+int mtb_crop_setup(const mtb_crop_setup_args* a, void* stream) {
+  if (!a || !a->boxes || !a->intrinsics || !a->camspace_up || !a->aug_rotflipmat || !a->aug_scales || !a->new_intrinsics ||
+      !a->rotations || !a->inv_projections || !a->pyramid_levels || (a->n_dist > 0 && !a->distortion))
+    return fail(nullptr, MTB_ERR_INVALID_ARG, "null crop-setup argument");
+  if (a->n_boxes <= 0 || a->num_aug <= 0 || a->num_aug > MP_MAX_AUG || a->box_stride < 4 || a->n_dist < 0 || a->n_dist > MP_NDIST ||
+      a->resolution <= 0)
+    return fail(nullptr, MTB_ERR_INVALID_ARG, "invalid crop-setup sizes (n_boxes=%d num_aug=%d n_dist=%d)", a->n_boxes, a->num_aug, a->n_dist);
+  if (a->antialias_factor != 1 && a->antialias_factor != 2 && a->antialias_factor != 4)
+    return fail(nullptr, MTB_ERR_UNSUPPORTED, "antialias_factor must be 1, 2 or 4 (got %d)", a->antialias_factor);
+  CropSetupParams p;
+  p.boxes = a->boxes; p.box_stride = a->box_stride; p.K = a->intrinsics; p.dist = a->distortion; p.ncoef = a->n_dist;
+  p.up = a->camspace_up; p.rotflip = a->aug_rotflipmat; p.aug_scales = a->aug_scales;
+  p.n_box = a->n_boxes; p.num_aug = a->num_aug; p.res = a->resolution; p.antialias = a->antialias_factor;
+  p.new_K = a->new_intrinsics; p.R = a->rotations; p.invproj = a->inv_projections; p.level = a->pyramid_levels;
+  launch_k(crop_setup_kernel, dim3((a->n_boxes + 127) / 128), dim3(128), 0, (cudaStream_t)stream, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(nullptr, MTB_ERR_CUDA, "crop setup launch: %s", cudaGetErrorString(e));
+  return MTB_OK;
+}
+
+int mtb_warp_crops(const mtb_warp_args* a, void* stream) {
+  if (!a || !a->images || !a->level1 || !a->level2 || !a->intrinsics || !a->image_ids || !a->inv_projections ||
+      !a->pyramid_levels || !a->gamma_exponents || !a->crops || (a->n_dist > 0 && !a->distortion))
+    return fail(nullptr, MTB_ERR_INVALID_ARG, "null warp argument");
+  if (a->n_boxes <= 0 || a->num_aug <= 0 || a->num_aug > MP_MAX_AUG || a->n_dist < 0 || a->n_dist > MP_NDIST || a->resolution <= 0 ||
+      a->height < 4 || a->width < 4 || a->n_images <= 0)
+    return fail(nullptr, MTB_ERR_INVALID_ARG, "invalid warp sizes");
+  if (a->antialias_factor != 1 && a->antialias_factor != 2 && a->antialias_factor != 4)
+    return fail(nullptr, MTB_ERR_UNSUPPORTED, "antialias_factor must be 1, 2 or 4 (got %d)", a->antialias_factor);
+  if ((long long)a->n_boxes * a->num_aug > 65535) return fail(nullptr, MTB_ERR_UNSUPPORTED, "more than 65535 crops per call");
+  WarpParams p;
+  p.img = a->images; p.l1 = a->level1; p.l2 = a->level2; p.N = a->n_images; p.H = a->height; p.W = a->width;
+  p.K = a->intrinsics; p.dist = a->distortion; p.ncoef = a->n_dist; p.image_ids = a->image_ids; p.invproj = a->inv_projections;
+  p.level = a->pyramid_levels; p.gamma_exp = a->gamma_exponents; p.n_box = a->n_boxes; p.num_aug = a->num_aug;
+  p.res = a->resolution; p.antialias = a->antialias_factor; p.crops = a->crops;
+  const int npix = a->resolution * a->resolution;
+  launch_k(warp_crops_kernel, dim3((npix + 255) / 256, a->n_boxes * a->num_aug), dim3(256), 0, (cudaStream_t)stream, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(nullptr, MTB_ERR_CUDA, "warp launch: %s", cudaGetErrorString(e));
+  return MTB_OK;
+}
+
+int mtb_tta_merge(const mtb_tta_args* a, void* stream) {
+  if (!a || !a->poses || !a->rotations || !a->aug_should_flip || !a->mirror_mapping || !a->intrinsics || !a->extrinsics_inv ||
+      !a->poses3d || !a->poses2d || (a->n_dist > 0 && !a->distortion))
+    return fail(nullptr, MTB_ERR_INVALID_ARG, "null TTA-merge argument");
+  if (a->n_boxes <= 0 || a->num_aug <= 0 || a->n_joints <= 0 || a->n_dist < 0 || a->n_dist > MP_NDIST)
+    return fail(nullptr, MTB_ERR_INVALID_ARG, "invalid TTA-merge sizes");
+  TtaParams p;
+  p.poses = a->poses; p.R = a->rotations; p.flip = a->aug_should_flip; p.mirror = a->mirror_mapping; p.jt = a->joint_transform;
+  p.skel = a->skeleton; p.K = a->intrinsics; p.dist = a->distortion; p.ncoef = a->n_dist; p.ext_inv = a->extrinsics_inv;
+  p.n_box = a->n_boxes; p.num_aug = a->num_aug; p.J = a->n_joints;
+  p.J2 = a->joint_transform ? a->n_joints_transformed : a->n_joints;
+  p.Js = a->skeleton ? a->n_skeleton : p.J2;
+  p.average = a->average_aug ? 1 : 0;
+  p.poses3d = a->poses3d; p.poses2d = a->poses2d;
+  if (p.J2 <= 0 || p.Js <= 0) return fail(nullptr, MTB_ERR_INVALID_ARG, "invalid joint counts");
+  launch_k(tta_merge_kernel, dim3(a->n_boxes), dim3(128), 0, (cudaStream_t)stream, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(nullptr, MTB_ERR_CUDA, "TTA merge launch: %s", cudaGetErrorString(e));
+  return MTB_OK;
+}
+
+int mtb_filter_poses(const mtb_filter_args* a, void* stream) {
+  if (!a || !a->poses3d || !a->poses2d || !a->boxes || !a->image_start || !a->plausible || !a->keep || !a->scratch ||
+      (a->n_bones > 0 && (!a->bones || !a->mean_bones)))
+    return fail(nullptr, MTB_ERR_INVALID_ARG, "null pose-filter argument");
+  if (a->n_images <= 0 || a->n_boxes <= 0 || a->num_aug < 2 || a->num_aug > MP_MAX_AUG || a->n_joints < 4 || a->box_stride < 5)
+    return fail(nullptr, MTB_ERR_INVALID_ARG, "invalid pose-filter sizes (num_aug must be 2..16, boxes need a score column)");
+  FilterParams p;
+  p.poses3d = a->poses3d; p.poses2d = a->poses2d; p.boxes = a->boxes; p.box_stride = a->box_stride; p.bones = a->bones;
+  p.mean_bones = a->mean_bones; p.n_bones = a->n_bones; p.image_start = a->image_start; p.num_aug = a->num_aug; p.J = a->n_joints;
+  p.plausible = a->plausible; p.keep = a->keep; p.scratch = a->scratch;
+  launch_k(pose_filter_kernel, dim3(a->n_images), dim3(128), 0, (cudaStream_t)stream, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(nullptr, MTB_ERR_CUDA, "pose filter launch: %s", cudaGetErrorString(e));
   return MTB_OK;
 }
 

@@ -1,33 +1,41 @@
 // 3xTF32 tensor-core path (sm_100a): the PARITY mode on tcgen05.  fp32 NHWC activations and fp32 weights are staged by
 // TMA exactly as they sit in HBM; "splitter" warps rewrite every landed operand tile in shared memory as
 //     x_hi = tf32(x)  (round to nearest, low 13 mantissa bits zero)      x_lo = x - x_hi  (exact in fp32)
-// and the MMA warp issues, per K step of 8,
-//     D += A_hi * B_hi        D += A_lo * B_hi        D += A_hi * B_lo              (tcgen05.mma kind::tf32, fp32 in TMEM)
-// i.e. the product of two 21-bit-mantissa operands with fp32 accumulation: the dropped terms (a_lo*b_lo and the bits of
-// x_lo below tf32) are ~2^-21 relative, so conv outputs agree with an fp32 FMA chain to ~1e-6 and the joints meet the 1e-3
-// bar of BASELINE.json (measured in tests/test_gpu_tf32.py) - on tensor cores instead of the CUDA-core conv_igemm_kernel.
+// and the MMA warp issues, per K step of 8, three tcgen05.mma kind::tf32 products:
+//     P += A_hi * B_hi          S += A_lo * B_hi          S += A_hi * B_lo
+// into TWO kinds of TMEM accumulators.  Why two (measured, round 2): the tensor core's fp32 accumulate TRUNCATES (round
+// toward zero, as on every generation since Volta), so a long accumulation chain carries a bias that grows linearly with
+// K - one accumulator for everything gave 2e-6 ... 2e-5 per conv (K = 288 ... 3840) and 1.6e-3 on EfficientNetV2-S features,
+// above the 1e-3 bar.  The cure is the one of Ootomo & Yokota (2022, "Recovering single precision accuracy from Tensor
+// Cores"): accumulate OUTSIDE the tensor core.  The main term runs in short chains of `chain` k-blocks (default 2 = 8 MMAs)
+// into a partial buffer P that the accumulator warps drain (tcgen05.ld) and add to fp32 REGISTER accumulators with
+// round-to-nearest FADDs; the correction terms are 2^-11 of the main term, so their truncation error is negligible and
+// they keep one TMEM accumulator S for the whole tile.
 //
 //   mode 0   1x1 stride-1 conv == GEMM  D[pixels, Cout] = A[pixels, Cin] * W[Cout, Cin]^T (2D TMA); the squeeze-excitation
 //            scale of an MBConv projection (backbones/efficientnet.py:110-173, `scale * x`) is applied by the splitter
 //            warps to the A tile before the split: the separate scaling pass of the bf16 mode does not exist here
 //   mode 1   RxS conv (stride 1/2, dilation) as implicit GEMM: per tap the A tile is a shifted [8 x 16] pixel box of the
 //            NHWC input fetched by a 4D TMA; out-of-bounds = the reference's explicit zero padding (efficientnet.py:1127-1161)
-//   epilogue TMEM -> registers, + folded-BN bias, exact activation (expf SiLU), + residual, fp32 NHWC store.
+//   epilogue registers (+ S from TMEM) -> + folded-BN bias, exact activation (expf SiLU), + residual, fp32 NHWC store.
 //
-// Shared-memory stage: [A raw/hi 128 rows | B raw/hi b_rows rows | A lo | B lo], rows of RB bytes (RB = 128: 32 fp32,
-// 128B swizzle; RB = 64: 16 fp32, 64B swizzle - used with 256-wide N tiles so that four stages stay in flight).  The lo
-// tiles mirror the raw tiles byte for byte, so the splitters never need to undo the TMA swizzle.
+// Tiles: M = 128 pixels x N <= 128 channels (register accumulators: 64 fp32 per accumulator thread).  TMEM columns:
+// [0,128) S0, [128,256) S1 (double-buffered across tiles), [256,384) P0, [384,512) P1 (ring of partial buffers).
+// Shared-memory stage: [A raw/hi 128 rows | B raw/hi b_rows rows | A lo | B lo], rows of 128 bytes (32 fp32, 128B
+// swizzle).  The lo tiles mirror the raw tiles byte for byte, so the splitters never need to undo the TMA swizzle.
 #pragma once
 #include "tc_gemm.cuh"
 
 namespace mtb {
 
-constexpr int T32_THREADS = 608;  // warps 0-7 epilogue, 8 A producer, 9 B producer, 10 MMA + TMEM, 11-18 splitters
-constexpr int T32_SPLIT_WARPS = 8;
+constexpr int T32_SPLIT_WARPS = 4;
+constexpr int T32_THREADS = (11 + T32_SPLIT_WARPS) * 32;  // warps 0-7 accumulate + epilogue, 8 A producer, 9 B producer, 10 MMA, 11.. splitters
 constexpr int T32_MAX_STAGES = 8;
 constexpr int T32_RING_BYTES = 216 * 1024;
 constexpr int T32_BAR_OFF = T32_RING_BYTES;
 constexpr int T32_SMEM_BYTES = T32_BAR_OFF + 512 + 1024 /*align slack*/;
+constexpr int T32_BN = 128;                                 // accumulator columns per buffer
+constexpr uint32_t T32_S_COL = 0, T32_P_COL = 2 * T32_BN;   // TMEM column bases of the S and P buffer pairs
 
 struct Tc32Params {
   const float* res;
@@ -39,9 +47,10 @@ struct Tc32Params {
   int Hin, Win;
   int M;                 // mode 0: rows
   int Cout, Cin;
-  int bn, b_rows;        // N-tile stride; rows of the weight TMA box
+  int bn, b_rows;        // N-tile stride (<= 128); rows of the weight TMA box
   int n_tiles, m_tiles, kchunks, taps;
   int nstages, stage_stride, lo_off;
+  int chain;             // k-blocks per partial accumulation chain (drained into registers after each)
   int Hout, Wout, tiles_w, tiles_h, pad_t, pad_l, R, S, stride, dil;
 };
 
@@ -66,20 +75,23 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
-template <int ACT, int RES, int RB>
+template <int ACT, int RES>
 __global__ void __launch_bounds__(T32_THREADS, 1)
 tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Tc32Params p) {
+  constexpr int RB = 128;          // bytes per operand row
   constexpr int BK = RB / 4;       // fp32 elements per row
-  constexpr int KSTEPS = RB / 32;  // MMAs (K = 8 tf32 = 32 bytes) per stage and product term
+  constexpr int KSTEPS = RB / 32;  // K steps (K = 8 tf32 = 32 bytes) per stage
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + T32_BAR_OFF);
   uint64_t* full = bars;                          // [8]  TMA landed (A + B producers)
-  uint64_t* split = bars + T32_MAX_STAGES;        // [8]  hi/lo tiles written (8 splitter warps)
+  uint64_t* split = bars + T32_MAX_STAGES;        // [8]  hi/lo tiles written (splitter warps)
   uint64_t* empty = bars + 2 * T32_MAX_STAGES;    // [8]  tcgen05.commit
-  uint64_t* tmem_full = bars + 3 * T32_MAX_STAGES;  // [2]
-  uint64_t* tmem_empty = tmem_full + 2;             // [2]
-  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  uint64_t* p_full = bars + 3 * T32_MAX_STAGES;   // [2]  partial chain complete
+  uint64_t* p_empty = p_full + 2;                 // [2]  drained by the 8 accumulator warps
+  uint64_t* s_full = p_empty + 2;                 // [2]  correction-term accumulator of a tile complete
+  uint64_t* s_empty = s_full + 2;                 // [2]
+  uint32_t* tmem_slot = (uint32_t*)(s_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 8 && lane == 0) {
@@ -93,8 +105,10 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], TCV_EPI_WARPS);
+      mbar_init(&p_full[i], 1);
+      mbar_init(&p_empty[i], TCV_EPI_WARPS);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], TCV_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -111,6 +125,7 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t b_bytes = (uint32_t)p.b_rows * RB;
   const int nstages = p.nstages;
   const int num_kb = pin(p.taps * p.kchunks);
+  const int chain = pin(p.chain);
   const uint32_t stage_stride = pin((uint32_t)p.stage_stride);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), split0 = smem_u32(split);
@@ -184,48 +199,58 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 10) {
-    // ===== MMA issuer: three tf32 products per K step into one fp32 accumulator =====
-    uint32_t acc = 0, acc_phase = 0;
-    constexpr uint32_t hi_sw = (uint32_t)((8 * RB) >> 4) | (1u << 14) | ((RB == 128 ? 2u : 4u) << 29);
+    // ===== MMA issuer: main term into the partial buffer P (short chain), correction terms into S (whole tile) =====
+    constexpr uint32_t hi_sw = (uint32_t)((8 * RB) >> 4) | (1u << 14) | (2u << 29);
     const uint32_t stride16 = stage_stride >> 4;
     const uint32_t base16 = smem_base >> 4;
     const uint32_t b_off16 = a_bytes >> 4;
     const uint32_t lo16 = (uint32_t)p.lo_off >> 4;
-    const uint32_t tmem_full0 = smem_u32(tmem_full), tmem_empty0 = smem_u32(tmem_empty);
+    const uint32_t p_full0 = smem_u32(p_full), p_empty0 = smem_u32(p_empty), s_full0 = smem_u32(s_full), s_empty0 = smem_u32(s_empty);
     const int bn = pin(p.bn), Cout = pin(p.Cout);
     TileWalk tw_(blockIdx.x, gridDim.x, p.n_tiles);
     uint32_t stage = 0, phase = 0, a16 = base16;
+    uint32_t sbuf = 0, s_phase = 0, pbuf = 0, p_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
       const int n_valid = min(bn, Cout - tw_.n_blk * bn);
       const uint32_t idesc = umma_idesc_tf32((n_valid + 15) & ~15);
-      mbar_wait_a(tmem_empty0 + acc * 8, acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * TC_MAX_BN;
+      mbar_wait_a(s_empty0 + sbuf * 8, s_phase ^ 1);
+      const uint32_t s_tmem = tmem_base + T32_S_COL + sbuf * T32_BN;
+      int pos = 0;
 #pragma unroll 1
       for (int kb = 0; kb < num_kb; ++kb) {
+        if (pos == 0) mbar_wait_a(p_empty0 + pbuf * 8, p_phase ^ 1);
         mbar_wait_a(split0 + stage * 8, phase);
         tc_fence_after();
+        const bool last_in_chain = pos == chain - 1 || kb == num_kb - 1;
         if (elect_one()) {
+          const uint32_t p_tmem = tmem_base + T32_P_COL + pbuf * T32_BN;
 #pragma unroll
           for (int k = 0; k < KSTEPS; ++k) {
             const uint64_t a_hi = make_desc(a16 + 2 * k, hi_sw), b_hi = make_desc(a16 + b_off16 + 2 * k, hi_sw);
             const uint64_t a_lo = make_desc(a16 + lo16 + 2 * k, hi_sw), b_lo = make_desc(a16 + lo16 + b_off16 + 2 * k, hi_sw);
-            umma_tf32(d_tmem, a_hi, b_hi, idesc, (uint32_t)(kb | k));
-            umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
-            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+            umma_tf32(s_tmem, a_lo, b_hi, idesc, (uint32_t)(kb | k));
+            umma_tf32(s_tmem, a_hi, b_lo, idesc, 1u);
+            umma_tf32(p_tmem, a_hi, b_hi, idesc, (uint32_t)(pos | k));
           }
           umma_commit_a(empty0 + stage * 8);
-          if (kb == num_kb - 1) umma_commit_a(tmem_full0 + acc * 8);
+          if (last_in_chain) umma_commit_a(p_full0 + pbuf * 8);
+          if (kb == num_kb - 1) umma_commit_a(s_full0 + sbuf * 8);
         }
         __syncwarp();
+        if (last_in_chain) {
+          pos = 0;
+          if (++pbuf == 2) { pbuf = 0; p_phase ^= 1; }
+        } else {
+          ++pos;
+        }
         a16 += stride16;
         if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; a16 = base16; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++sbuf == 2) { sbuf = 0; s_phase ^= 1; }
     }
   } else if (warp >= 11) {
     // ===== splitters: raw fp32 tile -> (hi in place, lo in the mirror tile); optional SE scale on A (mode 0) =====
-    const int st = (warp - 11) * 32 + lane;            // 0..255
+    const int st = (warp - 11) * 32 + lane;
     constexpr int CPR = RB / 16;                        // 16-byte chunks per row
     const int a_chunks = TC_BM * CPR;
     const int tot_chunks = (TC_BM + p.b_rows) * CPR;
@@ -240,14 +265,13 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait_a(full0 + stage * 8, phase);
         uint8_t* base = smem + stage * stage_stride;
-#pragma unroll 2
+#pragma unroll 4
         for (int i = st; i < tot_chunks; i += T32_SPLIT_WARPS * 32) {
           float4 v = *reinterpret_cast<const float4*>(base + i * 16);
           if (sc != nullptr && i < a_chunks) {
-            // physical chunk j of row r holds logical chunk j ^ swz(r)  (128B swizzle: r & 7; 64B swizzle: (r >> 1) & 3)
+            // physical chunk j of row r holds logical chunk j ^ (r & 7)  (128B swizzle)
             const int r = i / CPR, j = i - r * CPR;
-            const int jl = RB == 128 ? (j ^ (r & 7)) : (j ^ ((r >> 1) & 3));
-            const int k = kc * BK + jl * 4;
+            const int k = kc * BK + ((j ^ (r & 7)) << 2);
             const int m = m_blk * TC_BM + r;
             if (m < p.M && k < Cin) {
               const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + (size_t)(m / p.a_scale_P) * Cin + k));
@@ -270,17 +294,21 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue (warps 0-7): warp w owns TMEM lanes / tile rows [32(w&3), +32) and the 32-column chunks c = (w>>2) mod 2 =====
-    const int q = warp & 3, par = warp >> 2;
+    // ===== accumulator + epilogue warps 0-7: warp w owns tile rows [32(w&3), +32) and columns [64(w>>2), +64) of the tile.
+    // Every partial chain is drained from TMEM and added to the register accumulators with round-to-nearest FADDs. =====
+    const int q = warp & 3, half = warp >> 2;
     const int row = q * 32 + lane;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t sbuf = 0, s_phase = 0, pbuf = 0, p_phase = 0;
     const float* __restrict__ res = p.res;
     float* __restrict__ out = p.out;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+    const int n_chains = (num_kb + chain - 1) / chain;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int m_blk = t / p.n_tiles, n_blk = t - m_blk * p.n_tiles;
-      const int n0 = n_blk * p.bn;
-      const int n_valid = min(p.bn, p.Cout - n0);
+      const int n0 = n_blk * p.bn + half * 64;                       // first channel of this warp's columns
+      const int n_tile = min(p.bn, p.Cout - n_blk * p.bn);           // valid channels of the tile
+      const int ncols = max(0, min(64, n_tile - half * 64));         // valid columns of this warp (multiple of 4)
+      const int n_ld = min(64, max(0, ((n_tile + 15) & ~15) - half * 64));  // columns of this warp the MMA wrote
       bool valid;
       size_t off;
       if (p.mode == 0) {
@@ -295,48 +323,69 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         valid = oh < p.Hout && ow < p.Wout;
         off = ((size_t)(b * p.Hout + oh) * p.Wout + ow) * p.Cout;
       }
-      mbar_wait_a(smem_u32(&tmem_full[acc]), acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_MAX_BN;
-      const int nchunks = (n_valid + 31) >> 5;
-      for (int ch = par; ch < nchunks; ch += 2) {
+      float acc[64];
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const int c0 = ch * 32 + hf * 16;
-          if (c0 >= n_valid) break;  // warp-uniform
-          float4 rv[4];
-          if constexpr (RES != 0) {
+      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      for (int c = 0; c < n_chains; ++c) {
+        mbar_wait_a(smem_u32(&p_full[pbuf]), p_phase);
+        tc_fence_after();
+        const uint32_t taddr = lane_base + T32_P_COL + pbuf * T32_BN;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              rv[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (valid && c0 + g * 4 < n_valid) rv[g] = *reinterpret_cast<const float4*>(res + off + n0 + c0 + g * 4);
-            }
+        for (int g = 0; g < 4; ++g) {
+          if (g * 16 < n_ld) {  // warp-uniform
+            float v[16];
+            tmem_ld16(taddr + g * 16, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[g * 16 + i] += v[i];
           }
-          float v[16];
-          tmem_ld16(taddr + c0, v);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_empty[pbuf]);
+        if (++pbuf == 2) { pbuf = 0; p_phase ^= 1; }
+      }
+      mbar_wait_a(smem_u32(&s_full[sbuf]), s_phase);
+      tc_fence_after();
+      {
+        const uint32_t taddr = lane_base + T32_S_COL + sbuf * T32_BN;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (c0 + g * 4 < n_valid) {  // Cout is a multiple of 4
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g * 4));
-              float o[4] = {v[g * 4 + 0] + b4.x, v[g * 4 + 1] + b4.y, v[g * 4 + 2] + b4.z, v[g * 4 + 3] + b4.w};
-              if constexpr (RES == 2) {
-                o[0] = act_t<ACT>(o[0] + rv[g].x); o[1] = act_t<ACT>(o[1] + rv[g].y);
-                o[2] = act_t<ACT>(o[2] + rv[g].z); o[3] = act_t<ACT>(o[3] + rv[g].w);
-              } else {
+        for (int g = 0; g < 4; ++g) {
+          if (g * 16 < n_ld) {
+            float v[16];
+            tmem_ld16(taddr + g * 16, v);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) o[i] = act_t<ACT>(o[i]);
-                if constexpr (RES == 1) { o[0] += rv[g].x; o[1] += rv[g].y; o[2] += rv[g].z; o[3] += rv[g].w; }
-              }
-              if (valid) *reinterpret_cast<float4*>(out + off + n0 + c0 + g * 4) = make_float4(o[0], o[1], o[2], o[3]);
-            }
+            for (int i = 0; i < 16; ++i) acc[g * 16 + i] += v[i];
           }
         }
       }
-      // hand the accumulator back (every epilogue warp arrives once per tile, after its last TMEM read)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (lane == 0) mbar_arrive(&s_empty[sbuf]);
+      if (++sbuf == 2) { sbuf = 0; s_phase ^= 1; }
+      // epilogue from registers: + bias, activation, residual, fp32 store (each thread: one pixel, <= 64 contiguous channels)
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+          if (g * 4 < ncols) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + g * 4));
+            float o[4] = {acc[g * 4 + 0] + b4.x, acc[g * 4 + 1] + b4.y, acc[g * 4 + 2] + b4.z, acc[g * 4 + 3] + b4.w};
+            if constexpr (RES != 0) {
+              const float4 rv = *reinterpret_cast<const float4*>(res + off + n0 + g * 4);
+              if constexpr (RES == 2) {
+                o[0] = act_t<ACT>(o[0] + rv.x); o[1] = act_t<ACT>(o[1] + rv.y);
+                o[2] = act_t<ACT>(o[2] + rv.z); o[3] = act_t<ACT>(o[3] + rv.w);
+              } else {
+                o[0] = act_t<ACT>(o[0]) + rv.x; o[1] = act_t<ACT>(o[1]) + rv.y;
+                o[2] = act_t<ACT>(o[2]) + rv.z; o[3] = act_t<ACT>(o[3]) + rv.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) o[i] = act_t<ACT>(o[i]);
+            }
+            *reinterpret_cast<float4*>(out + off + n0 + g * 4) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
     }
   }
   tc_fence_before();
@@ -415,59 +464,47 @@ inline bool tc32_eligible(bool is_conv, bool depthwise, bool small_io, int k, in
   return (stride == 1 || stride == 2) && (k == 1 || k == 3);
 }
 
-// N-tile stride and row bytes.  Per-stage MMA time (cycles) = 3 products x (RB/32) K steps x N/2; a stage of 256-wide
-// tiles with 128-byte rows is 96 KB (two stages in flight: TMA + split + MMA serialise), so those use 64-byte rows
-// (48 KB stages, four in flight).
-inline void tc32_pick_tile(int cout, int m_tiles, int num_kb32, int* bn_out, int* rb_out) {
-  int best = 64, best_rb = 128;
+// N-tile stride (<= 128: the register accumulators hold 64 columns per accumulator thread).  Per k-block: three products x
+// 4 K steps x N/2 cycles of MMA against ~350 cycles of fixed issue cost and the L2 -> SM operand fill at ~40 B/clk.
+inline int tc32_pick_bn(int cout, int m_tiles, int num_kb) {
+  int best = 64;
   double best_cost = 1e30;
-  for (int bn = 256; bn >= 64; bn -= 64) {
+  for (int bn = 128; bn >= 32; bn -= 32) {
     const int nt = (cout + bn - 1) / bn;
     const long tiles = (long)m_tiles * nt;
     const long waves = (tiles + 147) / 148;
     const int last = cout - (nt - 1) * bn;
     const double avg_n = ((double)(nt - 1) * bn + ((last + 15) & ~15)) / nt;
-    const int rb = bn > 128 ? 64 : 128;
-    const int kb = rb == 128 ? num_kb32 : 2 * num_kb32;
-    const double mma_kb = 3.0 * (rb / 32) * avg_n / 2.0;
-    // L2 -> SM operand bytes per k-block at ~40 B/clk, and the fixed per-k-block issue cost
-    const double fill_kb = (128.0 + (nt == 1 ? ((cout + 15) & ~15) : bn)) * rb / 40.0;
+    const double mma_kb = 3.0 * 4.0 * (avg_n < 32 ? 32 : avg_n) / 2.0;
+    const double fill_kb = (128.0 + (nt == 1 ? ((cout + 15) & ~15) : bn)) * 128.0 / 40.0;
     double per_kb = mma_kb;
     if (fill_kb > per_kb) per_kb = fill_kb;
     if (per_kb < 350.0) per_kb = 350.0;
-    const double cost = (double)waves * (kb * per_kb + 600.0);
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; best_rb = rb; }
+    const double cost = (double)waves * (num_kb * per_kb + 800.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
-  *bn_out = best;
-  *rb_out = best_rb;
+  return best;
 }
 
-template <int ACT, int RES, int RB>
+template <int ACT, int RES>
 inline const char* tc32_launch_k(int grid, const CUtensorMap& a, const CUtensorMap& b, const Tc32Params& q, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc32_conv_kernel<ACT, RES, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, T32_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc32_conv_kernel<ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, T32_SMEM_BYTES) != cudaSuccess)
       return "cannot raise dynamic shared memory for tc32_conv_kernel";
     attr_set = true;
   }
-  launch_k(tc32_conv_kernel<ACT, RES, RB>, dim3(grid), dim3(T32_THREADS), T32_SMEM_BYTES, st, a, b, q);
+  launch_k(tc32_conv_kernel<ACT, RES>, dim3(grid), dim3(T32_THREADS), T32_SMEM_BYTES, st, a, b, q);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 template <int ACT>
-inline const char* tc32_dispatch_res(int res_mode, int rb, int grid, const CUtensorMap& a, const CUtensorMap& b, const Tc32Params& q,
+inline const char* tc32_dispatch_res(int res_mode, int grid, const CUtensorMap& a, const CUtensorMap& b, const Tc32Params& q,
                                      cudaStream_t st) {
-  if (rb == 128) {
-    switch (res_mode) {
-      case 0: return tc32_launch_k<ACT, 0, 128>(grid, a, b, q, st);
-      case 1: return tc32_launch_k<ACT, 1, 128>(grid, a, b, q, st);
-      default: return tc32_launch_k<ACT, 2, 128>(grid, a, b, q, st);
-    }
-  }
   switch (res_mode) {
-    case 0: return tc32_launch_k<ACT, 0, 64>(grid, a, b, q, st);
-    case 1: return tc32_launch_k<ACT, 1, 64>(grid, a, b, q, st);
-    default: return tc32_launch_k<ACT, 2, 64>(grid, a, b, q, st);
+    case 0: return tc32_launch_k<ACT, 0>(grid, a, b, q, st);
+    case 1: return tc32_launch_k<ACT, 1>(grid, a, b, q, st);
+    default: return tc32_launch_k<ACT, 2>(grid, a, b, q, st);
   }
 }
 
@@ -486,14 +523,15 @@ inline const char* tc32_conv_launch(const Tc32Weights& w, const ConvParams& p, b
   q.tiles_h = (p.Hout + TC_TILE_H - 1) / TC_TILE_H;
   q.M = p.B * p.Hout * p.Wout;
   q.m_tiles = q.mode == 0 ? (q.M + TC_BM - 1) / TC_BM : p.B * q.tiles_w * q.tiles_h;
-  int bn = 64, rb = 128;
-  tc32_pick_tile(p.Cout, q.m_tiles, q.taps * ((p.Cin + 31) / 32), &bn, &rb);
+  const int rb = 128;
+  int bn = tc32_pick_bn(p.Cout, q.m_tiles, q.taps * ((p.Cin + 31) / 32));
+  q.chain = 2;
   {
-    static int rb_env = -1, bn_env = -1;  // A/B switches: MTB_T32_RB = 64 | 128, MTB_T32_BN = 64..256
-    if (rb_env < 0) { const char* e = getenv("MTB_T32_RB"); rb_env = e ? atoi(e) : 0; }
+    static int bn_env = -1, chain_env = -1;  // A/B switches: MTB_T32_BN = 32..128, MTB_T32_CHAIN = k-blocks per partial chain
     if (bn_env < 0) { const char* e = getenv("MTB_T32_BN"); bn_env = e ? atoi(e) : 0; }
-    if (rb_env == 64 || rb_env == 128) rb = rb_env;
-    if (bn_env >= 64 && bn_env <= 256 && bn_env % 64 == 0) bn = bn_env;
+    if (chain_env < 0) { const char* e = getenv("MTB_T32_CHAIN"); chain_env = e ? atoi(e) : 0; }
+    if (bn_env >= 32 && bn_env <= 128 && bn_env % 32 == 0) bn = bn_env;
+    if (chain_env >= 1) q.chain = chain_env;
   }
   const int bk = rb / 4;
   q.bn = bn;
@@ -529,10 +567,10 @@ inline const char* tc32_conv_launch(const Tc32Weights& w, const ConvParams& p, b
   const int grid = total < 148 ? total : 148;
   const int res_mode = p.res ? (res_first ? 2 : 1) : 0;
   switch (p.act) {
-    case ACT_NONE: return tc32_dispatch_res<ACT_NONE>(res_mode, rb, grid, ms->a, ms->b, q, st);
-    case ACT_SILU: return tc32_dispatch_res<ACT_SILU>(res_mode, rb, grid, ms->a, ms->b, q, st);
-    case ACT_RELU: return tc32_dispatch_res<ACT_RELU>(res_mode, rb, grid, ms->a, ms->b, q, st);
-    case ACT_HSWISH: return tc32_dispatch_res<ACT_HSWISH>(res_mode, rb, grid, ms->a, ms->b, q, st);
+    case ACT_NONE: return tc32_dispatch_res<ACT_NONE>(res_mode, grid, ms->a, ms->b, q, st);
+    case ACT_SILU: return tc32_dispatch_res<ACT_SILU>(res_mode, grid, ms->a, ms->b, q, st);
+    case ACT_RELU: return tc32_dispatch_res<ACT_RELU>(res_mode, grid, ms->a, ms->b, q, st);
+    case ACT_HSWISH: return tc32_dispatch_res<ACT_HSWISH>(res_mode, grid, ms->a, ms->b, q, st);
     default: return "unsupported activation in the 3xTF32 epilogue";
   }
 }

@@ -167,6 +167,14 @@ int mtb_forward_host_wait(mtb_handle* h, int slot);
 int mtb_comm_unique_id(void* id128 /* host, 128 bytes */);
 int mtb_comm_init(mtb_handle* h, const void* id128, int rank, int world_size);
 int mtb_allgather_joints(mtb_handle* h, const float* local, int floats_per_rank, float* all, void* stream);
+/* The sharded forward in one call, no allocation: this rank's `batch_local` crops (the same count on every rank) ->
+ * backbone -> head decode -> ONE ncclAllGather of [coords2d | coords3d_rel] (5 floats per joint) -> absolute reconstruction
+ * of the full batch on every rank (reconstruct_ref_fullpersp uses batch-global RMS scalars, ptu3d.py:71-74, so the result
+ * equals the unsharded Metrabs.forward on the concatenated batch).  intrinsics_all [world*batch_local,3,3] and
+ * coords3d_abs_all [world*batch_local,J,3] are in rank order; scratch >= mtb_sharded_scratch_bytes(h, batch_local). */
+size_t mtb_sharded_scratch_bytes(const mtb_handle* h, int batch_local);
+int mtb_forward_sharded(mtb_handle* h, const float* crops_local, int batch_local, const float* intrinsics_all,
+                        float* coords3d_abs_all, void* scratch, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * The callers either side of the crop model (/root/reference/metrabs_pytorch/multiperson/).  Handle-free

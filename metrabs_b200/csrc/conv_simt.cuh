@@ -398,6 +398,88 @@ __global__ void __launch_bounds__(256, OW == 2 ? 3 : 2) dwconv3x3_pool_bf16_kern
   }
 }
 
+// fp32-storage twin of the strip kernel above for the 3xTF32 parity mode: 4 channels (one 16-byte vector) x OW output pixels
+// per thread, exact activation (expf SiLU), the same block-reduced partial pooling slices.  grid (ceil(C/128), slices, B).
+template <int STRIDE, int ACT, int OW = 4>
+__global__ void __launch_bounds__(256, 2) dwconv3x3_pool_f32_kernel(ConvParams p, float* __restrict__ pooled) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int NCOL = (OW - 1) * STRIDE + 3;
+  const float* __restrict__ in = reinterpret_cast<const float*>(p.in);
+  float* __restrict__ out = reinterpret_cast<float*>(p.out);
+  const int C = p.Cout;
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int strips_w = (p.Wout + OW - 1) / OW;
+  const int b = blockIdx.z;
+  const int cstride = C >> 2;  // float4 per pixel
+  float psum[4] = {0.f, 0.f, 0.f, 0.f};
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) bias4 = *reinterpret_cast<const float4*>(p.bias + c);
+  for (int strip = blockIdx.y * 8 + threadIdx.y; c < C && strip < strips_w * p.Hout; strip += gridDim.y * 8) {
+    const int oh = strip / strips_w;
+    const int ow0 = (strip - oh * strips_w) * OW;
+    const int iw0 = ow0 * STRIDE - p.pad_l;
+    unsigned colmask = 0;
+#pragma unroll
+    for (int x = 0; x < NCOL; ++x)
+      if (iw0 + x >= 0 && iw0 + x < p.Win) colmask |= 1u << x;
+    float4 acc[OW];
+#pragma unroll
+    for (int i = 0; i < OW; ++i) acc[i] = bias4;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * STRIDE - p.pad_t + r;
+      if (ih < 0 || ih >= p.Hin) continue;  // warp-uniform (a warp shares its strip)
+      const float4* rowp = reinterpret_cast<const float4*>(in + ((size_t)(b * p.Hin + ih) * p.Win) * C + c) + (ptrdiff_t)iw0 * cstride;
+      float4 raw[NCOL];
+#pragma unroll
+      for (int x = 0; x < NCOL; ++x) raw[x] = (colmask >> x) & 1u ? __ldg(rowp + (ptrdiff_t)x * cstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 w[3];
+#pragma unroll
+      for (int s_ = 0; s_ < 3; ++s_) w[s_] = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)(r * 3 + s_) * C + c));
+#pragma unroll
+      for (int x = 0; x < NCOL; ++x) {
+#pragma unroll
+        for (int i = 0; i < OW; ++i) {
+          const int s_ = x - i * STRIDE;  // compile-time after unrolling
+          if (s_ >= 0 && s_ < 3) {
+            acc[i].x = fmaf(raw[x].x, w[s_].x, acc[i].x);
+            acc[i].y = fmaf(raw[x].y, w[s_].y, acc[i].y);
+            acc[i].z = fmaf(raw[x].z, w[s_].z, acc[i].z);
+            acc[i].w = fmaf(raw[x].w, w[s_].w, acc[i].w);
+          }
+        }
+      }
+    }
+    float* orow = out + ((size_t)(b * p.Hout + oh) * p.Wout + ow0) * C + c;
+#pragma unroll
+    for (int i = 0; i < OW; ++i) {
+      if (ow0 + i >= p.Wout) continue;
+      float4 o = make_float4(act_t<ACT>(acc[i].x), act_t<ACT>(acc[i].y), act_t<ACT>(acc[i].z), act_t<ACT>(acc[i].w));
+      psum[0] += o.x; psum[1] += o.y; psum[2] += o.z; psum[3] += o.w;
+      *reinterpret_cast<float4*>(orow + (size_t)i * C) = o;
+    }
+  }
+  if (pooled) {
+    __shared__ float red[8][32][5];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[threadIdx.y][threadIdx.x][k] = psum[k];
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+      const float inv = 1.0f / (float)(p.Hout * p.Wout);
+      float t[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        t[k] = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) t[k] += red[y][threadIdx.x][k];
+        t[k] *= inv;
+      }
+      *reinterpret_cast<float4*>(pooled + ((size_t)blockIdx.y * gridDim.z + b) * C + c) = make_float4(t[0], t[1], t[2], t[3]);
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------------------
 // stem: direct conv for tiny Cin (3) reading the caller's NCHW fp32 crops, with the per-channel input affine
 // (PreprocLayer x*2-1, backbones/efficientnet.py:1185) applied to in-bounds pixels only (pad happens AFTER
@@ -559,113 +641,6 @@ __global__ void __launch_bounds__(256) se_reduce_kernel(const float* __restrict_
   float v = 0.f;
   for (int z = 0; z < ksplit; ++z) v += partial[(size_t)z * n + i];
   out[i] = apply_act(v + bias[i % C], act);
-}
-
-// ----------------------------------------------------------------------------------------------------------
-// Squeeze-excitation in ONE launch (bf16 throughput mode): scale[b, c] = act2(W2^T act1(W1^T mean[b] + b1) + b2)
-// (SqueezeExcitation.forward, backbones/efficientnet.py / torchvision ops.misc: avgpool -> fc1 -> act -> fc2 -> gate).
-// Input: the `slices` partial means the fused depthwise kernel left ([slice][B][C], summed here in a fixed order).
-// One CTA owns CPB crops and streams both weight matrices once from L2; 16 warps split K for fc1 (each lane owns hidden
-// units j = lane, lane+32, ...) and the cross-warp sum goes through shared memory in a fixed order (deterministic).
-// Replaces split-K fc1 + reduce + fc2 = three dependent launches whose cost was launch/drain latency, not work.
-// ----------------------------------------------------------------------------------------------------------
-constexpr int SE_THREADS = 512, SE_MAX_JPL = 5;  // hidden units per lane: csq <= 160
-template <int CPB>
-__global__ void __launch_bounds__(SE_THREADS) se_fused_kernel(const float* __restrict__ pooled, int slices, size_t slice_stride,
-                                                              const float* __restrict__ w1, const float* __restrict__ b1,
-                                                              const float* __restrict__ w2, const float* __restrict__ b2,
-                                                              float* __restrict__ scale, int B, int C, int csq, int act1, int act2) {
-  pdl_trigger();
-  pdl_wait();
-  extern __shared__ float se_smem[];
-  float* x = se_smem;                          // [CPB][C]
-  float* hpart = x + (size_t)CPB * C;          // [16 warps][CPB][csq]
-  float* hid = hpart + 16 * CPB * csq;         // [CPB][csq]
-  const int b0 = blockIdx.x * CPB;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // squeezed input: sum of the partial-mean slices
-  for (int i = tid; i < CPB * C; i += SE_THREADS) {
-    const int cb = i / C, c = i - cb * C;
-    // all (<= 8) slice loads issued before the first add: one L2 round trip per element instead of `slices`
-    float pv[8];
-#pragma unroll
-    for (int sidx = 0; sidx < 8; ++sidx)
-      pv[sidx] = (sidx < slices && b0 + cb < B) ? __ldg(pooled + (size_t)sidx * slice_stride + (size_t)(b0 + cb) * C + c) : 0.f;
-    float v = 0.f;
-#pragma unroll
-    for (int sidx = 0; sidx < 8; ++sidx) v += pv[sidx];
-    x[i] = v;
-  }
-  __syncthreads();
-  // fc1: warp w takes input channels c = w, w+16, ... (rows of w1 are csq contiguous floats: coalesced)
-  float acc[CPB][SE_MAX_JPL];
-#pragma unroll
-  for (int cb = 0; cb < CPB; ++cb)
-#pragma unroll
-    for (int i = 0; i < SE_MAX_JPL; ++i) acc[cb][i] = 0.f;
-  // Every CTA streams the SAME weight rows: started together they would all hit the same L2 lines at the same time
-  // (measured: same-line reads from 128 SMs serialise to ~1.9 TB/s aggregate, 121 us for 1.8 MB).  Each CTA therefore
-  // starts at its own rotation of the row order.
-  const int T1 = (C + 15) >> 4;
-  const int rot1 = (int)((blockIdx.x * 37u) % (unsigned)T1);
-#pragma unroll 8
-  for (int kk = 0; kk < T1; ++kk) {
-    int k = kk + rot1;
-    if (k >= T1) k -= T1;
-    const int c = warp + 16 * k;
-    if (c >= C) continue;
-    const float* wr = w1 + (size_t)c * csq;
-    float wv[SE_MAX_JPL];
-#pragma unroll
-    for (int i = 0; i < SE_MAX_JPL; ++i) wv[i] = (lane + 32 * i < csq) ? __ldg(wr + lane + 32 * i) : 0.f;
-#pragma unroll
-    for (int cb = 0; cb < CPB; ++cb) {
-      const float xv = x[cb * C + c];
-#pragma unroll
-      for (int i = 0; i < SE_MAX_JPL; ++i) acc[cb][i] = fmaf(xv, wv[i], acc[cb][i]);
-    }
-  }
-#pragma unroll
-  for (int cb = 0; cb < CPB; ++cb)
-#pragma unroll
-    for (int i = 0; i < SE_MAX_JPL; ++i)
-      if (lane + 32 * i < csq) hpart[(warp * CPB + cb) * csq + lane + 32 * i] = acc[cb][i];
-  __syncthreads();
-  for (int i = tid; i < CPB * csq; i += SE_THREADS) {
-    const int cb = i / csq, j = i - cb * csq;
-    float v = b1[j];
-#pragma unroll
-    for (int w = 0; w < 16; ++w) v += hpart[(w * CPB + cb) * csq + j];
-    hid[i] = apply_act(v, act1);
-  }
-  __syncthreads();
-  // fc2: thread t takes 4 consecutive output channels (rows of w2 are C contiguous floats: coalesced float4)
-  for (int c4 = tid; c4 * 4 < C; c4 += SE_THREADS) {
-    const int c = c4 * 4;
-    float4 o[CPB];
-    const float4 bv = *reinterpret_cast<const float4*>(b2 + c);
-#pragma unroll
-    for (int cb = 0; cb < CPB; ++cb) o[cb] = bv;
-    const int rot2 = (int)((blockIdx.x * 37u) % (unsigned)csq);
-#pragma unroll 8
-    for (int jj = 0; jj < csq; ++jj) {
-      int j = jj + rot2;
-      if (j >= csq) j -= csq;
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(w2 + (size_t)j * C + c));
-#pragma unroll
-      for (int cb = 0; cb < CPB; ++cb) {
-        const float hv = hid[cb * csq + j];
-        o[cb].x = fmaf(hv, wv.x, o[cb].x); o[cb].y = fmaf(hv, wv.y, o[cb].y);
-        o[cb].z = fmaf(hv, wv.z, o[cb].z); o[cb].w = fmaf(hv, wv.w, o[cb].w);
-      }
-    }
-#pragma unroll
-    for (int cb = 0; cb < CPB; ++cb) {
-      if (b0 + cb >= B) continue;
-      float4 r = make_float4(apply_act(o[cb].x, act2), apply_act(o[cb].y, act2), apply_act(o[cb].z, act2), apply_act(o[cb].w, act2));
-      *reinterpret_cast<float4*>(scale + (size_t)(b0 + cb) * C + c) = r;
-    }
-  }
 }
 
 // max pool (ResNet stem, metrabs_tf/backbones/resnet.py:187-193), NHWC.  The reference pads with ZeroPadding2D and

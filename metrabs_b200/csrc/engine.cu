@@ -19,9 +19,6 @@
 #include "tc_gemm.cuh"
 #include "tc_tf32.cuh"
 #include "dw_tma.cuh"
-#include "tc_gemm_pair.cuh"
-#include "tc_gemm_bres.cuh"
-#include "se_cluster.cuh"
 #include "multiperson.cuh"
 
 using namespace mtb;
@@ -61,9 +58,6 @@ struct Op {
   bool small_io = false;  // squeeze-excitation FCs on [B,1,1,C] fp32 tensors
   float pre_scale[3] = {2.f, 2.f, 2.f}, pre_shift[3] = {-1.f, -1.f, -1.f};  // stem input affine (PreprocLayer: x*2-1)
   bool fused_pool = false;  // bf16 modes: this depthwise op also produces the SE pooled means (next op is skipped)
-  bool se_fused = false;    // fc1 of a squeeze-excitation whose fc1 + fc2 run as one se_fused_kernel launch
-  bool se_skip = false;     // fc2 of such a block (its output is written by the fc1 op's launch)
-  bool se_cluster = false;  // with se_fused: the launch is se_cluster_kernel (8-CTA clusters) instead of se_fused_kernel
   bool res_first = false;  // residual added BEFORE the activation (ResNet); EfficientNet adds it after
   int pool_src = -1;       // fc1: index of the OP_POOL op that produces its input (fused pooling leaves partial slices)
   int ksplit = 1;          // split-K (squeeze-excitation fc1): raw sums, bias/act deferred to the consumer
@@ -76,8 +70,6 @@ struct Op {
   TcWeights tc;             // bf16 K-major copy + TMA descriptor state for the tcgen05 path
   Tc32Weights tc32;         // fp32 K-major copy + TMA descriptor state for the 3xTF32 tcgen05 path (MTB_PRECISION_TF32X3)
   mutable DwTmaCache dw_cache;  // input tensor map of the TMA-staged depthwise kernel
-  mutable TcPairMaps pair_maps; // tensor maps of the (opt-in, MTB_TC_PAIR=1) cta_group::2 GEMM
-  mutable TcBresMaps bres_maps; // tensor maps of the (opt-in, MTB_TC_BRES=1) resident-weight-panel GEMM
   double flops = 0;         // 2*MACs per crop
   int stage = 0;            // EfficientNet stage (1-based; 0 = stem / last conv / other backbones)
 };
@@ -677,29 +669,7 @@ struct ProfScope {
   }
 };
 
-// shapes covered by dwconv3x3_pool_bf16_kernel
-bool se_fused_enabled() {  // MTB_SE_FUSED=1 enables the one-launch squeeze-excitation (measured SLOWER than split-K fc1 + reduce + fc2: every CTA streams the whole weight matrices through one SM; 76 vs 36 us per block at 2 x 0.9 MB)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MTB_SE_FUSED");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
-// MTB_SE_CLUSTER=1: squeeze-excitation fc1 + fc2 as one 8-CTA-cluster launch (se_cluster.cuh).  Off by default - measured
-// at 256 crops (r1): 2.10 ms per step against 1.95 ms for split-K fc1 + reduce + fc2; every cluster re-reads both weight
-// matrices (32 clusters x 1.8 MB in stage 6) and those same-line L2 reads serialise, whereas the tiled fc GEMMs read each
-// weight from only four CTAs.  Variants (16 crops per cluster, fc2 slice prefetched by bulk copies) were slower still.
-bool se_cluster_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MTB_SE_CLUSTER");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
+// shapes covered by the strip depthwise kernels (dwconv3x3_pool_bf16_kernel / dwconv3x3_pool_f32_kernel)
 bool dw_strip_eligible(const Op& op) {
   return op.type == OP_DW && op.R == 3 && op.S == 3 && op.dil == 1 && op.Cout % 8 == 0 && (op.stride == 1 || op.stride == 2) &&
          (op.act == ACT_SILU || op.act == ACT_RELU || op.act == ACT_HSWISH);
@@ -716,15 +686,16 @@ bool dw_tma_enabled() {
   }
   return v == 1;
 }
-DwTmaPlan dw_tma_plan_for(const Op& op) {
+DwTmaPlan dw_tma_plan_for(const Op& op, bool bf16_tc = true) {
   DwTmaPlan none;
+  if (!bf16_tc) return none;  // the TMA-staged kernel is bf16-only; the 3xTF32 mode runs the fp32 strip kernel
   if (!dw_tma_enabled() || !dw_strip_eligible(op) || op.stride != 1 || op.Hin != op.Hout || op.Win != op.Wout) return none;
   DwTmaPlan pl = dw_tma_plan(op.Hout, op.Wout);
   if (!pl.ok || pl.n_rb > kPoolSlices) return none;
   return pl;
 }
-int dw_pool_slices(const Op& dw) {
-  const DwTmaPlan pl = dw_tma_plan_for(dw);
+int dw_pool_slices(const Op& dw, bool bf16_tc = true) {
+  const DwTmaPlan pl = dw_tma_plan_for(dw, bf16_tc);
   if (pl.ok) return pl.n_rb;
   const int strips = dw.Hout * ((dw.Wout + kDwOW - 1) / kDwOW);
   return std::min((strips + 7) / 8, kPoolSlices);
@@ -760,15 +731,6 @@ double op_bytes(const mtb_handle* h, const Op& op, int B) {
 }
 
 // ---------------------------------------------------------------------------------------------- executor
-// the projection conv of this op would run as a CTA-pair GEMM that applies the SE scale itself (MTB_TC_PAIR=1 + MTB_TC_PAIR_SCALE=1)
-bool op_pair_fuses_scale(const Op& op, int B) {
-  if (op.type != OP_CONV || !op.tc.ready || op.scale_buf == BUF_NONE) return false;
-  ConvParams q;
-  q.R = op.R; q.S = op.S; q.stride = op.stride; q.Cin = op.Cin; q.Cout = op.Cout; q.B = B; q.Hout = op.Hout; q.Wout = op.Wout;
-  q.act = op.act;
-  return tc_pair_fuses_scale(q, true);
-}
-
 bool pdl_se_enabled() {  // MTB_PDL_SE=1: programmatic dependent launch for the squeeze-excitation chain only
   static int v = -1;
   if (v < 0) {
@@ -782,8 +744,7 @@ template <typename T>
 int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Workspace& ws, void* features,
              cudaStream_t st) {
   PdlScope pdl_scope(pdl_se_enabled() && op.small_io);
-  if (op.type == OP_CONV && op.tc.ready && op.scale_buf != BUF_NONE && !tc_can_fuse_se(op.R, op.stride, op.Cin) &&
-      !op_pair_fuses_scale(op, B)) {
+  if (op.type == OP_CONV && op.tc.ready && op.scale_buf != BUF_NONE && !tc_can_fuse_se(op.R, op.stride, op.Cin)) {
     // squeeze-excitation scale applied in place ahead of a tensor-core conv that cannot fuse it (1x1 stride-1 projections
     // apply it to the A tiles in shared memory inside tc_conv_kernel)
     void* x = act_ptr(h, ws, op.in_buf, features, op.Hin, op.Win, op.Cin);
@@ -847,6 +808,15 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
             if (op.stride == 1) launch_k(dwconv3x3_pool_bf16_kernel<1, ACT_HSWISH, kDwOW>, dim3(grid), dim3(block), 0, st, p, pooled);
             else launch_k(dwconv3x3_pool_bf16_kernel<2, ACT_HSWISH, kDwOW>, dim3(grid), dim3(block), 0, st, p, pooled);
           }
+        } else if (h->cfg.precision == MTB_PRECISION_TF32X3 && dw_strip_eligible(op) && op.Cout % 4 == 0) {
+          // fp32 strip kernel: 4 channels x 4 pixels per thread, SE squeeze fused (partial slices summed by fc1)
+          float* pooled = op.fused_pool ? (float*)buf_ptr(ws, BUF_SMALL0, features) : nullptr;
+          dim3 grid((op.Cout / 4 + 31) / 32, dw_pool_slices(op, false), B), block(32, 8);
+#define MTB_DWF32(ST, AC) launch_k(dwconv3x3_pool_f32_kernel<ST, AC, kDwOW>, dim3(grid), dim3(block), 0, st, p, pooled)
+          if (op.act == ACT_SILU) { if (op.stride == 1) MTB_DWF32(1, ACT_SILU); else MTB_DWF32(2, ACT_SILU); }
+          else if (op.act == ACT_RELU) { if (op.stride == 1) MTB_DWF32(1, ACT_RELU); else MTB_DWF32(2, ACT_RELU); }
+          else { if (op.stride == 1) MTB_DWF32(1, ACT_HSWISH); else MTB_DWF32(2, ACT_HSWISH); }
+#undef MTB_DWF32
         } else {
           size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
           launch_k(dwconv_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, st, p);
@@ -854,60 +824,9 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
       } else if (op.type == OP_MAXPOOL) {
         size_t total = (size_t)B * op.Hout * op.Wout * (op.Cout / 4);
         launch_k(maxpool_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, st, p);
-      } else if (op.small_io && op.se_fused && op.se_cluster) {
-        // squeeze-excitation fc1 + fc2 in one cluster launch over the partial pooling slices of the depthwise kernel
-        const Op& f2 = *(&op + 1);
-        const int slices = dw_pool_slices(h->ops[op.pool_src - 1]);
-        // MTB_SE_CB (crops per cluster, 8 | 16) and MTB_SE_STAGE_W2 (prefetch the fc2 weight slice into shared memory) are
-        // A/B switches; the defaults are the measured best
-        static int cb_env = -1, st_env = -1;
-        if (cb_env < 0) { const char* e = getenv("MTB_SE_CB"); cb_env = (e && atoi(e) == 16) ? 16 : 8; }
-        if (st_env < 0) { const char* e = getenv("MTB_SE_STAGE_W2"); st_env = (e && e[0] == '1') ? 1 : 0; }
-        const int cb = cb_env;
-        bool stage_w2 = st_env && sec_stage_w2(op.Cin, op.Cout);
-        size_t smem = sec_smem_bytes(op.Cin, op.Cout, cb, stage_w2);
-        if (smem > 220 * 1024) { stage_w2 = false; smem = sec_smem_bytes(op.Cin, op.Cout, cb, false); }
-        static bool attr_set = false;
-        if (!attr_set) {
-          cudaFuncSetAttribute(se_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-          cudaFuncSetAttribute(se_cluster_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-          attr_set = true;
-        }
-        const int groups = (B + cb - 1) / cb;
-        float* dst = (float*)buf_ptr(ws, f2.out_buf, features);
-        if (cb == 16)
-          launch_k(se_cluster_kernel<16>, dim3(groups * SEC_CL), dim3(SEC_THREADS), smem, st, (const float*)p.in, slices, (size_t)B * op.Cin,
-                   (const float*)op.d_w, (const float*)op.d_bias, (const float*)f2.d_w, (const float*)f2.d_bias, dst, B, op.Cin, op.Cout,
-                   op.act, f2.act, stage_w2 ? 1 : 0);
-        else
-          launch_k(se_cluster_kernel<8>, dim3(groups * SEC_CL), dim3(SEC_THREADS), smem, st, (const float*)p.in, slices, (size_t)B * op.Cin,
-                   (const float*)op.d_w, (const float*)op.d_bias, (const float*)f2.d_w, (const float*)f2.d_bias, dst, B, op.Cin, op.Cout,
-                   op.act, f2.act, stage_w2 ? 1 : 0);
-      } else if (op.small_io && op.se_fused) {
-        // squeeze-excitation fc1 + fc2 in one launch over the partial pooling slices of the depthwise kernel
-        const Op& f2 = *(&op + 1);
-        const int slices = dw_pool_slices(h->ops[op.pool_src - 1]);
-        static bool attr_set = false;
-        if (!attr_set) {
-          cudaFuncSetAttribute(se_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-          cudaFuncSetAttribute(se_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-          attr_set = true;
-        }
-        // one crop per CTA while that still leaves SMs idle, two beyond (halves the L2 weight traffic)
-        const int cpb = B > 148 ? 2 : 1;
-        const size_t smem = ((size_t)cpb * op.Cin + 17 * cpb * op.Cout) * sizeof(float);
-        float* dst = (float*)buf_ptr(ws, f2.out_buf, features);
-        if (cpb == 1)
-          launch_k(se_fused_kernel<1>, dim3(B), dim3(SE_THREADS), smem, st, (const float*)p.in, slices, (size_t)B * op.Cin,
-                   (const float*)op.d_w, (const float*)op.d_bias, (const float*)f2.d_w, (const float*)f2.d_bias, dst, B, op.Cin, op.Cout,
-                   op.act, f2.act);
-        else
-          launch_k(se_fused_kernel<2>, dim3((B + 1) / 2), dim3(SE_THREADS), smem, st, (const float*)p.in, slices, (size_t)B * op.Cin,
-                   (const float*)op.d_w, (const float*)op.d_bias, (const float*)f2.d_w, (const float*)f2.d_bias, dst, B, op.Cin, op.Cout,
-                   op.act, f2.act);
       } else if (op.small_io) {
         if (op.pool_src > 0 && h->ops[op.pool_src].fused_pool) {  // input = partial pooling slices of the depthwise kernel
-          p.a_splits = dw_pool_slices(h->ops[op.pool_src - 1]);
+          p.a_splits = dw_pool_slices(h->ops[op.pool_src - 1], h->cfg.precision == MTB_PRECISION_BF16_TC);
           p.a_split_stride = (size_t)B * op.Cin;
         }
         float* final_out = (float*)p.out;
@@ -924,13 +843,6 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
           e = cudaGetLastError();
         }
         if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "launch %s: %s", op.name.c_str(), cudaGetErrorString(e));
-      } else if (op.tc.ready && tc_bres_eligible(p) && !op_pair_fuses_scale(op, B) &&
-                 !(op.scale_buf != BUF_NONE && tc_can_fuse_se(op.R, op.stride, op.Cin))) {
-        const char* e = tc_bres_launch(op.tc, op.bres_maps, p, op.res_first, st);  // opt-in short-K GEMM (never run yet)
-        if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 resident-panel launch %s: %s", op.name.c_str(), e);
-      } else if (op.tc.ready && tc_pair_eligible(p) && !(op.scale_buf != BUF_NONE && tc_can_fuse_se(op.R, op.stride, op.Cin))) {
-        const char* e = tc_pair_launch(op.tc, op.pair_maps, p, op.res_first, op_pair_fuses_scale(op, B), st);  // opt-in, never run yet
-        if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 pair launch %s: %s", op.name.c_str(), e);
       } else if (op.tc.ready) {
         const char* e = tc_conv_launch(op.tc, p, op.res_first, st);
         if (e) return fail(h, MTB_ERR_CUDA, "tcgen05 launch %s: %s", op.name.c_str(), e);
@@ -959,7 +871,6 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
 
 int run_op(mtb_handle* h, const Op& op, const float* crops, int B, const Workspace& ws, void* features, cudaStream_t st) {
   if (op.type == OP_POOL && op.fused_pool) return MTB_OK;  // produced by the preceding depthwise kernel
-  if (op.se_skip) return MTB_OK;                            // produced by the fc1 op's se_fused_kernel launch
   if (is_bf16(h)) return run_op_t<__nv_bfloat16>(h, op, crops, B, ws, features, st);
   return run_op_t<float>(h, op, crops, B, ws, features, st);
 }
@@ -1090,6 +1001,30 @@ __global__ void from_float_kernel(const float* in, __nv_bfloat16* out, size_t n)
   pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(in[i]);
+}
+
+// [b,J,2] + [b,J,3] -> [b,J,5] (what travels in the all-gather) and back
+__global__ void pack_decoded_kernel(const float* __restrict__ c2d, const float* __restrict__ c3d, float* __restrict__ packed, int n) {
+  pdl_trigger();
+  pdl_wait();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    packed[(size_t)i * 5 + 0] = c2d[(size_t)i * 2 + 0];
+    packed[(size_t)i * 5 + 1] = c2d[(size_t)i * 2 + 1];
+    packed[(size_t)i * 5 + 2] = c3d[(size_t)i * 3 + 0];
+    packed[(size_t)i * 5 + 3] = c3d[(size_t)i * 3 + 1];
+    packed[(size_t)i * 5 + 4] = c3d[(size_t)i * 3 + 2];
+  }
+}
+__global__ void unpack_decoded_kernel(const float* __restrict__ packed, float* __restrict__ c2d, float* __restrict__ c3d, int n) {
+  pdl_trigger();
+  pdl_wait();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    c2d[(size_t)i * 2 + 0] = packed[(size_t)i * 5 + 0];
+    c2d[(size_t)i * 2 + 1] = packed[(size_t)i * 5 + 1];
+    c3d[(size_t)i * 3 + 0] = packed[(size_t)i * 5 + 2];
+    c3d[(size_t)i * 3 + 1] = packed[(size_t)i * 5 + 3];
+    c3d[(size_t)i * 3 + 2] = packed[(size_t)i * 5 + 4];
+  }
 }
 
 struct DeviceGuard {
@@ -1235,27 +1170,11 @@ int mtb_finalize_weights(mtb_handle* h) {
   h->graphs.clear();
   for (void* p : h->dev_allocs) cudaFree(p);
   h->dev_allocs.clear();
-  for (auto& op : h->ops) op.fused_pool = op.se_fused = op.se_skip = op.se_cluster = false;
+  for (auto& op : h->ops) op.fused_pool = false;
   for (size_t i = 0; i + 1 < h->ops.size(); ++i) {
-    const bool fuse = h->cfg.precision == MTB_PRECISION_BF16_TC && dw_strip_eligible(h->ops[i]) && h->ops[i + 1].type == OP_POOL;
+    const bool fuse = (h->cfg.precision == MTB_PRECISION_BF16_TC || h->cfg.precision == MTB_PRECISION_TF32X3) &&
+                      dw_strip_eligible(h->ops[i]) && h->ops[i + 1].type == OP_POOL;
     if (fuse) h->ops[i].fused_pool = h->ops[i + 1].fused_pool = true;
-    // fc1 + fc2 behind a fused pool run as one launch when both weight matrices stream through one SM quickly enough
-    // (<= 2 MB; EfficientNetV2-L stage 7 with 2 x 2.4 MB keeps the split-K path) and fit the kernel's register tiling
-    if (fuse && i + 3 < h->ops.size() && se_fused_enabled()) {
-      Op& f1 = h->ops[i + 2];
-      Op& f2 = h->ops[i + 3];
-      const bool ok = f1.small_io && f2.small_io && f1.pool_src == (int)i + 1 && f2.Cin == f1.Cout && f2.Cout == f1.Cin &&
-                      f1.Cout <= 32 * SE_MAX_JPL && f1.Cin % 4 == 0 && (size_t)f1.Cin * f1.Cout * 8 <= (2u << 20) &&
-                      ((size_t)2 * f1.Cin + 34 * f1.Cout) * sizeof(float) <= 96 * 1024;
-      if (ok) { f1.se_fused = true; f2.se_skip = true; }
-    }
-    if (fuse && i + 3 < h->ops.size() && se_cluster_enabled() && !h->ops[i + 2].se_fused) {
-      Op& f1 = h->ops[i + 2];
-      Op& f2 = h->ops[i + 3];
-      const bool ok = f1.small_io && f2.small_io && f1.pool_src == (int)i + 1 && f2.Cin == f1.Cout && f2.Cout == f1.Cin &&
-                      sec_eligible(f1.Cin, f1.Cout);
-      if (ok) { f1.se_fused = f1.se_cluster = true; f2.se_skip = true; }
-    }
   }
   for (auto& op : h->ops) {
     int rc = prepare_op_weights(h, op);
@@ -1757,6 +1676,55 @@ int mtb_filter_poses(const mtb_filter_args* a, void* stream) {
   return MTB_OK;
 }
 
+// Data-parallel forward: local crops -> backbone -> head decode, ONE all-gather of [coords2d | coords3d_rel]
+// (5 floats per joint), absolute reconstruction of the FULL batch on every rank - reconstruct_ref_fullpersp normalises with
+// batch-global RMS scalars (ptu3d.py:71-74), so only a full-batch solve reproduces the unsharded result exactly.
+size_t mtb_sharded_scratch_bytes(const mtb_handle* h, int batch_local) {
+  if (!h || batch_local <= 0 || h->nccl_world <= 0) return 0;
+  const size_t J = (size_t)h->cfg.n_joints, bl = (size_t)batch_local, bt = bl * (size_t)h->nccl_world;
+  return align_up(bl * J * 5 * 4, 256) + align_up(bt * J * 5 * 4, 256) + align_up(bt * J * 2 * 4, 256) + align_up(bt * J * 3 * 4, 256) +
+         align_up(bt * J * 2 * 4, 256) + align_up(bt * 2 * 8, 256);
+}
+
+int mtb_forward_sharded(mtb_handle* h, const float* crops_local, int batch_local, const float* intrinsics_all, float* coords3d_abs_all,
+                        void* scratch, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(h, batch_local, workspace_bytes, workspace);
+  if (rc) return rc;
+  if (!crops_local || !intrinsics_all || !coords3d_abs_all || !scratch) return fail(h, MTB_ERR_INVALID_ARG, "null argument");
+  if (!h->nccl_comm) return fail(h, MTB_ERR_NCCL, "mtb_comm_init has not been called");
+  if (h->ops.empty()) return fail(h, MTB_ERR_UNSUPPORTED, "this handle has no backbone (head-only)");
+  DeviceGuard g(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t J = (size_t)h->cfg.n_joints, bl = (size_t)batch_local, bt = bl * (size_t)h->nccl_world;
+  char* sp = (char*)scratch;
+  float* packed_local = (float*)sp; sp += align_up(bl * J * 5 * 4, 256);
+  float* packed_all = (float*)sp;   sp += align_up(bt * J * 5 * 4, 256);
+  float* c2d_all = (float*)sp;      sp += align_up(bt * J * 2 * 4, 256);
+  float* c3d_all = (float*)sp;      sp += align_up(bt * J * 3 * 4, 256);
+  float* n2d = (float*)sp;          sp += align_up(bt * J * 2 * 4, 256);
+  double* partial = (double*)sp;
+  h->launches = 0;
+  Workspace ws = layout(h, batch_local, workspace);
+  void* features = ws.base + ws.off_features;
+  rc = run_backbone(h, crops_local, batch_local, ws, features, st);
+  if (rc) return rc;
+  float* c2d = (float*)(ws.base + ws.off_c2d);
+  float* c3d = (float*)(ws.base + ws.off_c3d);
+  rc = head_decode_impl(h, features, batch_local, c2d, c3d, ws, st);
+  if (rc) return rc;
+  const int64_t before = h->launches;
+  launch_k(pack_decoded_kernel, dim3(grid_for(bl * J, 256)), dim3(256), 0, st, (const float*)c2d, (const float*)c3d, packed_local,
+           (int)(bl * J));
+  rc = mtb_allgather_joints(h, packed_local, (int)(bl * J * 5), packed_all, stream);
+  if (rc) return rc;
+  launch_k(unpack_decoded_kernel, dim3(grid_for(bt * J, 256)), dim3(256), 0, st, (const float*)packed_all, c2d_all, c3d_all, (int)(bt * J));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, MTB_ERR_CUDA, "pack/unpack launch: %s", cudaGetErrorString(e));
+  rc = recon_impl(h, c2d_all, c3d_all, intrinsics_all, (int)bt, coords3d_abs_all, n2d, partial, st);
+  h->launches = before + 3 + 2;  // pack, all-gather, unpack, reconstruction passes
+  return rc;
+}
+
 // ---------------------------------------------------------------------------------------- introspection
 int mtb_num_ops(const mtb_handle* h) { return h ? (int)h->ops.size() : 0; }
 
@@ -1905,10 +1873,7 @@ int mtb_debug_run_op(mtb_handle* h, int op_index, const float* in, const float* 
   o.tc.map_sets.clear();
   o.tc32.map_sets.clear();
   o.dw_cache = DwTmaCache();
-  o.pair_maps = TcPairMaps();
-  o.bres_maps = TcBresMaps();
   o.fused_pool = false;      // in isolation a depthwise op does not pool and a pool op runs its own kernel
-  o.se_fused = o.se_skip = false;
   rc = run_op(h, o, crops, batch, ws, nullptr, st);
   if (rc) return rc;
   void* src = buf_ptr(ws, o.out_buf, nullptr);

@@ -28,7 +28,7 @@
 
 namespace mtb {
 
-constexpr int T32_SPLIT_WARPS = 4;
+constexpr int T32_SPLIT_WARPS = 5;
 constexpr int T32_THREADS = (11 + T32_SPLIT_WARPS) * 32;  // warps 0-7 accumulate + epilogue, 8 A producer, 9 B producer, 10 MMA, 11.. splitters
 constexpr int T32_MAX_STAGES = 8;
 constexpr int T32_RING_BYTES = 216 * 1024;
@@ -73,6 +73,32 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(int n) {
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
   lo = x - hi;
+}
+
+// acc[0..63] += 64 TMEM columns of this warp's 32 lanes (columns >= n_ld were not written by the MMA and are skipped)
+__device__ __forceinline__ void t32_drain(uint32_t taddr, int n_ld, float* acc) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (g * 16 < n_ld) {  // warp-uniform
+      float v[16];
+      tmem_ld16(taddr + g * 16, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[g * 16 + i] += v[i];
+    }
+  }
+}
+// SiLU for the parity epilogue: x * 1/(1 + 2^(-x log2 e)) on the MUFU units (ex2.approx, rcp.approx: ~2 ulp each); the
+// CUDA-core fp32 mode's expf + IEEE division costs ~3x the instructions and sat on the accumulator warps' critical path
+template <int ACT>
+__device__ __forceinline__ float t32_act(float x) {
+  if constexpr (ACT == ACT_SILU) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+  } else {
+    return act_t<ACT>(x);
+  }
 }
 
 template <int ACT, int RES>
@@ -250,13 +276,19 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 11) {
     // ===== splitters: raw fp32 tile -> (hi in place, lo in the mirror tile); optional SE scale on A (mode 0) =====
+    // Thread st handles the 16-byte chunks st, st + NT, st + 2 NT, ... of the stage: NT is a multiple of 8 chunks per row, so
+    // its chunk column j = st & 7 is fixed and its rows are r0 + (NT/8) t.  With the 128B swizzle the logical K offset of its
+    // chunk depends on (j, r & 7) only - fixed per thread when NT/8 is a multiple of 8, else it cycles with t.
+    constexpr int NT = T32_SPLIT_WARPS * 32;
+    constexpr int CPR = RB / 16;                        // 16-byte chunks per row (8)
+    constexpr int RSTEP = NT / CPR;                     // rows between consecutive chunks of one thread
     const int st = (warp - 11) * 32 + lane;
-    constexpr int CPR = RB / 16;                        // 16-byte chunks per row
+    const int j = st & (CPR - 1), r0 = st / CPR;
     const int a_chunks = TC_BM * CPR;
     const int tot_chunks = (TC_BM + p.b_rows) * CPR;
     const uint32_t lo_off = (uint32_t)p.lo_off;
     const float* __restrict__ sc = p.a_scale;
-    const int kchunks = pin(p.kchunks), Cin = pin(p.Cin);
+    const int kchunks = pin(p.kchunks), Cin = pin(p.Cin), P = pin(p.a_scale_P);
     uint32_t stage = 0, phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int m_blk = t / p.n_tiles;
@@ -265,19 +297,39 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait_a(full0 + stage * 8, phase);
         uint8_t* base = smem + stage * stage_stride;
-#pragma unroll 4
-        for (int i = st; i < tot_chunks; i += T32_SPLIT_WARPS * 32) {
-          float4 v = *reinterpret_cast<const float4*>(base + i * 16);
-          if (sc != nullptr && i < a_chunks) {
-            // physical chunk j of row r holds logical chunk j ^ (r & 7)  (128B swizzle)
-            const int r = i / CPR, j = i - r * CPR;
+        int i = st;
+        if (sc != nullptr) {
+          // A rows with the squeeze-excitation scale: s[crop(row)][k .. k+3]; the scale vector is re-read only when the crop
+          // (or the swizzled K offset) changes from one of this thread's rows to the next
+          int last_key = -1;
+          float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          int r = r0;
+#pragma unroll 2
+          for (; i < a_chunks; i += NT, r += RSTEP) {
+            float4 v = *reinterpret_cast<const float4*>(base + i * 16);
             const int k = kc * BK + ((j ^ (r & 7)) << 2);
             const int m = m_blk * TC_BM + r;
             if (m < p.M && k < Cin) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + (size_t)(m / p.a_scale_P) * Cin + k));
+              const int crop = m / P;
+              const int key = crop * 8 + (r & 7);
+              if (key != last_key) {
+                s4 = __ldg(reinterpret_cast<const float4*>(sc + (size_t)crop * Cin + k));
+                last_key = key;
+              }
               v.x *= s4.x; v.y *= s4.y; v.z *= s4.z; v.w *= s4.w;
             }
+            float4 h, l;
+            split_tf32(v.x, h.x, l.x);
+            split_tf32(v.y, h.y, l.y);
+            split_tf32(v.z, h.z, l.z);
+            split_tf32(v.w, h.w, l.w);
+            *reinterpret_cast<float4*>(base + i * 16) = h;
+            *reinterpret_cast<float4*>(base + lo_off + i * 16) = l;
           }
+        }
+#pragma unroll 4
+        for (; i < tot_chunks; i += NT) {
+          const float4 v = *reinterpret_cast<const float4*>(base + i * 16);
           float4 h, l;
           split_tf32(v.x, h.x, l.x);
           split_tf32(v.y, h.y, l.y);
@@ -330,15 +382,7 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait_a(smem_u32(&p_full[pbuf]), p_phase);
         tc_fence_after();
         const uint32_t taddr = lane_base + T32_P_COL + pbuf * T32_BN;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g * 16 < n_ld) {  // warp-uniform
-            float v[16];
-            tmem_ld16(taddr + g * 16, v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc[g * 16 + i] += v[i];
-          }
-        }
+        t32_drain(taddr, n_ld, acc);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_empty[pbuf]);
@@ -348,15 +392,7 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       {
         const uint32_t taddr = lane_base + T32_S_COL + sbuf * T32_BN;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g * 16 < n_ld) {
-            float v[16];
-            tmem_ld16(taddr + g * 16, v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc[g * 16 + i] += v[i];
-          }
-        }
+        t32_drain(taddr, n_ld, acc);
       }
       tc_fence_before();
       __syncwarp();
@@ -372,15 +408,15 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if constexpr (RES != 0) {
               const float4 rv = *reinterpret_cast<const float4*>(res + off + n0 + g * 4);
               if constexpr (RES == 2) {
-                o[0] = act_t<ACT>(o[0] + rv.x); o[1] = act_t<ACT>(o[1] + rv.y);
-                o[2] = act_t<ACT>(o[2] + rv.z); o[3] = act_t<ACT>(o[3] + rv.w);
+                o[0] = t32_act<ACT>(o[0] + rv.x); o[1] = t32_act<ACT>(o[1] + rv.y);
+                o[2] = t32_act<ACT>(o[2] + rv.z); o[3] = t32_act<ACT>(o[3] + rv.w);
               } else {
-                o[0] = act_t<ACT>(o[0]) + rv.x; o[1] = act_t<ACT>(o[1]) + rv.y;
-                o[2] = act_t<ACT>(o[2]) + rv.z; o[3] = act_t<ACT>(o[3]) + rv.w;
+                o[0] = t32_act<ACT>(o[0]) + rv.x; o[1] = t32_act<ACT>(o[1]) + rv.y;
+                o[2] = t32_act<ACT>(o[2]) + rv.z; o[3] = t32_act<ACT>(o[3]) + rv.w;
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) o[i] = act_t<ACT>(o[i]);
+              for (int i = 0; i < 4; ++i) o[i] = t32_act<ACT>(o[i]);
             }
             *reinterpret_cast<float4*>(out + off + n0 + g * 4) = make_float4(o[0], o[1], o[2], o[3]);
           }

@@ -167,11 +167,13 @@ class Engine:
         b, s = crops.shape[0], self.cfg.proc_side
         crops = self._check_in(crops, (b, 3, s, s))
         k = self._check_in(intrinsics, (b, 3, 3))
-        self.workspace(b)
+        ws = self.workspace(b)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             self.forward(crops, k, out=out)
-        graph._mtb_keepalive = (crops, k, out)
+        # the captured launches write into THIS workspace tensor: keep it alive with the graph even if a later, larger
+        # batch makes workspace() replace self._ws (a freed workspace would be reused by the allocator under the graph)
+        graph._mtb_keepalive = (crops, k, out, ws)
         return graph
 
     def forward_host(self, crops_host, intrinsics_host, out_host=None):
@@ -212,9 +214,31 @@ class Engine:
         check(lib().mtb_comm_init(self._h, buf, rank, world_size), self._h)
         self.world_size = world_size
 
-    def allgather(self, local):
+    def forward_sharded(self, crops_local, intrinsics_all, out=None):
+        """mtb_forward_sharded: local crops [b,3,S,S] (the same b on every rank) + intrinsics of the FULL batch
+        [world*b,3,3] -> joints of the full batch [world*b,J,3]; one all-gather of [c2d|c3d], full-batch reconstruction.
+        Buffers (scratch, workspace, and `out` when given) are reused across calls."""
+        b, s = crops_local.shape[0], self.cfg.proc_side
+        crops_local = self._check_in(crops_local, (b, 3, s, s))
+        k = self._check_in(intrinsics_all, (self.world_size * b, 3, 3))
+        if out is None:
+            out = torch.empty(self.world_size * b, self.n_joints, 3, dtype=torch.float32, device=self.device)
+        need = lib().mtb_sharded_scratch_bytes(self._h, b)
+        if getattr(self, '_sh_scratch', None) is None or self._sh_scratch.numel() < need:
+            self._sh_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        ws = self.workspace(b)
+        check(lib().mtb_forward_sharded(self._h, crops_local.data_ptr(), b, k.data_ptr(), out.data_ptr(),
+                                        self._sh_scratch.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(self.device)), self._h)
+        return out
+
+    def allgather(self, local, out=None):
         local = local.contiguous()
-        out = torch.empty((self.world_size,) + tuple(local.shape), dtype=torch.float32, device=self.device)
+        if out is None:
+            key = tuple(local.shape)
+            cache = getattr(self, '_gather_out', None)
+            if cache is None or cache[0] != key:  # one buffer per shape, reused across calls
+                self._gather_out = (key, torch.empty((self.world_size,) + key, dtype=torch.float32, device=self.device))
+            out = self._gather_out[1]
         check(lib().mtb_allgather_joints(self._h, local.data_ptr(), local.numel(), out.data_ptr(),
                                          _stream_ptr(self.device)), self._h)
         return out

@@ -143,7 +143,12 @@ class Pose3dEstimator(torch.nn.Module):
 
     # ------------------------------------------------------------------------------------------------ the path
     def _device(self):
-        return self.crop_model.heatmap_heads.conv_final.weight.device
+        cm = self.crop_model
+        if hasattr(cm, 'heatmap_heads'):
+            return cm.heatmap_heads.conv_final.weight.device
+        for t in list(cm.parameters()) + list(cm.buffers()):
+            return t.device
+        return torch.device(getattr(cm, 'device', 'cuda'))
 
     def _estimate_poses_batched(self, images, boxes, intrinsic_matrix, distortion_coeffs, extrinsic_matrix, world_up_vector,
                                 default_fov_degrees, internal_batch_size, antialias_factor, num_aug, average_aug, skeleton,

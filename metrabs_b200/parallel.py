@@ -43,21 +43,33 @@ def gather_decoded(local_packed, n_total, world_size, all_gather_fn):
 
 class ShardedMetrabs:
     """Runs ``model`` (metrabs_b200.models.metrabs.Metrabs) data-parallel: every rank passes the FULL flat crop batch
-    (or just its own chunk with ``presharded=True``) and gets the full [B,J,3] result."""
+    (or just its own chunk with ``presharded=True``) and gets the full [B,J,3] result.  ``engine`` (optional) replaces
+    ``model.engine(device)``: any object with ``n_joints``, ``backbone``, ``head_decode``, ``allgather``,
+    ``reconstruct_absolute`` (and optionally ``forward_sharded``) - the CPU tests drive the host logic through it."""
 
-    def __init__(self, model, rank, world_size):
-        self.model, self.rank, self.world = model, rank, world_size
+    def __init__(self, model, rank, world_size, engine=None):
+        self.model, self.rank, self.world, self._engine = model, rank, world_size, engine
 
     def forward(self, crops, intrinsics, n_total=None, presharded=False):
-        eng = self.model.engine(crops.device)
+        eng = self._engine if self._engine is not None else self.model.engine(crops.device)
         if presharded:
             local = crops
         else:
             n_total = crops.shape[0]
             s, e = shard_range(n_total, self.world, self.rank)
             local = crops[s:e]
-        feats = eng.backbone(local)
-        c2d, c3d = eng.head_decode(feats)
-        packed = gather_decoded(pack_decoded(c2d, c3d), n_total, self.world, eng.allgather)
+        sizes = shard_sizes(n_total, self.world)
+        if min(sizes) == max(sizes) and sizes[0] > 0 and hasattr(eng, 'forward_sharded'):
+            # equal shards: the whole step in one library call on preallocated buffers (mtb_forward_sharded)
+            return eng.forward_sharded(local, intrinsics)
+        if local.shape[0] == 0:
+            # fewer crops than ranks (e.g. 3 person-crops on 8 GPUs): this rank has nothing to compute but must still
+            # take part in the collective
+            packed_local = torch.zeros((0, eng.n_joints, 5), dtype=torch.float32, device=crops.device)
+        else:
+            feats = eng.backbone(local)
+            c2d, c3d = eng.head_decode(feats)
+            packed_local = pack_decoded(c2d, c3d)
+        packed = gather_decoded(packed_local, n_total, self.world, lambda t: eng.allgather(t).clone())
         g2d, g3d = unpack_decoded(packed)
         return eng.reconstruct_absolute(g2d, g3d, intrinsics)

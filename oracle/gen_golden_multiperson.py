@@ -137,6 +137,10 @@ def main():
                 data[tag] = crops.reshape(-1, 3, 64, 64).numpy()
                 data[tag + '_newk'] = new_k.numpy()
                 data[tag + '_rot'] = rot.numpy()
+                invp = torch.linalg.inv(new_k @ rot)  # the reference's own fp32 inverse (multiperson_model.py:288, :292-295)
+                if af > 1:
+                    invp = invp @ wp.corner_aligned_scale_mat(1 / af)
+                data[tag + '_invproj'] = invp.reshape(-1, 3, 3).numpy()
         # 12-coefficient distortion through warp_images_with_pyramid directly (warping.py:6-28, :80-99)
         d12 = torch.tensor([[-0.1, 0.03, 0.001, -0.002, 0.004, 0.02, -0.01, 0.003, 0.0005, -0.0004, 0.0003, 0.0002]]).repeat(5, 1)
         gam, sc, fl, rf = aug_parameters(5)
@@ -155,6 +159,26 @@ def main():
             for sk in ('', 'upper'):
                 res = est._estimate_poses_batched(images, [b.clone() for b in boxes], intr, dist, ext, up, 55, 64, 1, 5, avg, sk, False)
                 tag = f'pipe_avg{int(avg)}_{sk or "all"}'
+                for i in range(2):
+                    data[f'{tag}_p3d_{i}'] = res['poses3d'][i].numpy()
+                    data[f'{tag}_p2d_{i}'] = res['poses2d'][i].numpy()
+        # ---- the TTA merge alone: the reference caller around a STUB crop model that returns a fixed table of well-conditioned
+        # poses (z = 2-4 m), so that mirror swap / poses @ R / joint transform / projection / extrinsics / mean are pinned
+        # tightly (the tiny random crop model above emits poses with z near 0, whose 2D projection is ill-conditioned)
+        g2 = torch.Generator().manual_seed(33)
+        table = torch.cat([400 * torch.randn(25, 8, 2, generator=g2), 2000 + 2000 * torch.rand(25, 8, 1, generator=g2)], dim=-1)
+
+        class TableModel(torch.nn.Module):
+            joint_names, joint_edges, input_resolution = np.array(JOINT_NAMES), np.array(JOINT_EDGES), np.int32(64)
+
+            def forward(self, inp):
+                return table[:inp[0].shape[0]].clone()
+        est2 = mm.Pose3dEstimator(TableModel(), skel, jt.numpy())
+        data['merge_table'] = table.numpy()
+        for avg in (True, False):
+            for sk in ('', 'upper'):
+                res = est2._estimate_poses_batched(images, [b.clone() for b in boxes], intr, dist, ext, up, 55, 0, 1, 5, avg, sk, False)
+                tag = f'merge_avg{int(avg)}_{sk or "all"}'
                 for i in range(2):
                     data[f'{tag}_p3d_{i}'] = res['poses3d'][i].numpy()
                     data[f'{tag}_p2d_{i}'] = res['poses2d'][i].numpy()

@@ -40,6 +40,7 @@ def parse():
     ap.add_argument('--batch', type=int, default=256, help='crops per GPU per step (weak scaling) / per step in total (strong)')
     ap.add_argument('--scaling', default=os.environ.get('MTB_BENCH_SCALING', 'weak'), choices=['weak', 'strong'],
                     help='weak: --batch crops per GPU; strong: --batch crops in total, split over the GPUs (BASELINE config c3)')
+    ap.add_argument('--no-frames', action='store_true', help='skip the frames -> poses leg (crop generation + TTA merge around the model)')
     ap.add_argument('--no-parity', action='store_true', help='skip the device-vs-oracle joint error of the benchmarked mode')
     ap.add_argument('--no-parity-line', action='store_true', help='skip the tf32x3 (parity mode) sibling measurement')
     ap.add_argument('--precision', default=os.environ.get('MTB_BENCH_PRECISION', 'bf16'), choices=['fp32', 'bf16', 'tf32x3'])
@@ -286,6 +287,65 @@ def parity_check(args, model, n_crops=4, setup=None):
     err = port.relative_error(out, ref)
     return {'joints_rel_err_vs_oracle': err, 'tolerance': 1e-3, 'meets_tolerance': bool(err < 1e-3), 'crops': n_crops,
             'precision_mode': args.precision}
+
+
+def frames_leg(args, model, device, iters=5):
+    """the same crop model fed from FULL FRAMES by this package's Pose3dEstimator - u8 frames + person boxes
+    -> pyramid -> per-crop matrices -> ONE warp launch for all num_aug x n_boxes crops -> mtb_forward -> TTA merge - all on
+    the device.  8 frames of 720x1280 with 51 boxes in total x 5 augmentations = 255 crops per call (about one bench batch)."""
+    from metrabs_b200.multiperson import Pose3dEstimator, warping
+    from metrabs_b200.multiperson.multiperson_model import aug_parameters
+    j = args.joints
+    model.joint_names = [f'j{i}' for i in range(j)]
+    model.joint_edges = [[0, 1]]
+    est = Pose3dEstimator(model, {'': dict(indices=list(range(j)), names=model.joint_names, edges=[[0, 1]])}, None)
+    g = torch.Generator().manual_seed(11)
+    n_img, h, w = 8, 720, 1280
+    frames = torch.randint(0, 256, (n_img, 3, h, w), generator=g, dtype=torch.uint8).to(device)
+    counts = [7, 6, 7, 6, 6, 7, 6, 6]
+    boxes = []
+    for c in counts:
+        xy = torch.rand(c, 2, generator=g) * torch.tensor([w - 400., h - 500.])
+        wh = torch.tensor([180., 400.]) * (0.6 + 0.8 * torch.rand(c, 2, generator=g))
+        boxes.append(torch.cat([xy, wh, torch.rand(c, 1, generator=g)], dim=1))
+    kw = dict(intrinsic_matrix=torch.tensor([[[1100., 0, w / 2], [0, 1100., h / 2], [0, 0, 1]]]),
+              distortion_coeffs=torch.tensor([[-0.05, 0.01, 0.0005, -0.0005, 0.001]]),
+              extrinsic_matrix=torch.eye(4)[None], world_up_vector=torch.tensor([0., -1., 0.]), default_fov_degrees=55,
+              internal_batch_size=0, antialias_factor=1, num_aug=5, average_aug=True, skeleton='', suppress_implausible_poses=False)
+    for _ in range(2):
+        est._estimate_poses_batched(frames, boxes, **kw)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(iters):
+        res = est._estimate_poses_batched(frames, boxes, **kw)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / iters
+    n_box = sum(counts)
+    # the warp launch alone (255 crops of SxS fp32 written, bilinear gathers from the u8 frames / the pyramid)
+    pyr = warping.build_pyramid(frames)
+    k_box = kw['intrinsic_matrix'].repeat(n_box, 1, 1).to(device)
+    d_box = kw['distortion_coeffs'].repeat(n_box, 1).to(device)
+    up = torch.tensor([[0., -1., 0.]]).repeat(n_box, 1).to(device)
+    ids = torch.repeat_interleave(torch.arange(n_img), torch.tensor(counts))
+    gam, sc, fl, rf = aug_parameters(5)
+    new_k, rot, inv, lev = warping.crop_setup(torch.cat(boxes).to(device), k_box, d_box, up, rf, sc, args.side, 1)
+    out = torch.empty(5 * n_box, 3, args.side, args.side, device=device)
+    for _ in range(2):
+        warping.warp_images_with_pyramid(frames, pyr, k_box, inv, d_box, lev, gam / 2.2, args.side, ids, 5, 1, out=out)
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
+    for _ in range(iters):
+        warping.warp_images_with_pyramid(frames, pyr, k_box, inv, d_box, lev, gam / 2.2, args.side, ids, 5, 1, out=out)
+    w1.record()
+    torch.cuda.synchronize()
+    warp_ms = w0.elapsed_time(w1) / iters
+    return {'what': 'frames -> poses through metrabs_b200.multiperson.Pose3dEstimator (pyramid, crop setup, one-launch warp, crop model, '
+                    'TTA merge), device resident', 'frames': n_img, 'frame_size': [h, w], 'boxes': n_box, 'num_aug': 5,
+            'crops_per_call': 5 * n_box, 'ms_per_call': ms, 'crops_per_s': 5 * n_box / (ms / 1e3), 'persons_per_s': n_box / (ms / 1e3),
+            'warp_kernel_ms': warp_ms, 'warp_kernel_write_gbs': out.numel() * 4 / (warp_ms / 1e3) / 1e9,
+            'poses3d_finite': bool(all(torch.isfinite(p).all() for p in res['poses3d']))}
 
 
 def time_mode(args, eng, world, rank, device, dist, sharded_inputs):
@@ -552,6 +612,11 @@ def run_b200(args):
             'gpu_launches': rp['launches'], 'clocks': rp['clocks'], 'roofline': roofline_of(rp, 'tf32x3'),
             'tensor_util_of_peak': pv / world * flops_crop / 1e12 / pk['tflops'],
             'parity': parity_check(sibling['args'], sibling['model'], setup=setup) if not args.no_parity else None}
+    if world == 1 and not args.no_frames:
+        try:
+            line['frames_pipeline'] = frames_leg(a_main, model, device)
+        except Exception as e:  # noqa: BLE001  (an auxiliary leg must not cost the headline line)
+            line['frames_pipeline'] = {'error': repr(e)}
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sec, desc = cpu_reference_forward(a_main, args.cpu_sample, 5, 2, setup=setup)
         line['cpu_baseline'] = {'value': v, 'unit': 'crops/s', 'cores': cores, 'kind': 'port',

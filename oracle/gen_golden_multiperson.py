@@ -93,6 +93,8 @@ def tiny_reference_estimator(R, mm):
     skeleton_infos = {'': dict(indices=list(range(10)), names=[f'k{i}' for i in range(10)], edges=[[0, 1]]),
                       'upper': dict(indices=[5, 6, 7, 9, 0], names=['a', 'b', 'c', 'd', 'e'], edges=[[0, 1]])}
     est = mm.Pose3dEstimator(model, skeleton_infos, jt.numpy())
+    # the on-disk format of scripts/demo_image.py:59-74: torch.save(model.state_dict()) of the REFERENCE model object
+    torch.save(model.state_dict(), os.path.join(OUT, 'tiny_ckpt.pt'))
     return est, jt, skeleton_infos
 
 

@@ -259,3 +259,37 @@ def test_errors_are_loud(H):
     eng = Engine(make_config(metrabs_b200.get_config(), 8, stages=stages, last_channel=last))
     with pytest.raises(MetrabsB200Error, match='backbone.1.3.0.block.1.1'):
         eng.load_state_dict(sd)
+
+
+def test_checkpoint_file_round_trip(H, golden_dir, tmp_path):
+    """the on-disk format.  tests/golden/tiny_ckpt.pt is ``torch.save(model.state_dict())`` of the REFERENCE
+    Metrabs object (scripts/demo_image.py:59-74 loads exactly this); it must load with strict=True through the reference key
+    schema (BN fold + NHWC / K-major repack inside mtb_load_weight) and reproduce the reference's own outputs.  A half-precision
+    copy of the file (how released checkpoints are often stored) goes through the F16 loader path.  No trained weights exist
+    offline, so the fast-mode deviation on TRAINED weights cannot be measured here - said so instead of guessed."""
+    g = _golden(golden_dir, 'tiny_s64_j8.npz')
+    sd = torch.load(os.path.join(golden_dir, 'tiny_ckpt.pt'), weights_only=True)
+    assert any(k.endswith('num_batches_tracked') for k in sd)  # the real file carries keys the engine must ignore
+    pcfg = port.PathConfig(proc_side=64)
+    crops, k = torch.from_numpy(g['crops']), torch.from_numpy(g['intrinsics'])
+    m = H.device_model('efficientnetv2-tiny', pcfg, 8, sd)
+    out = m((crops.cuda(), k.cuda()))
+    assert H.rel_err(out, g['coords3d_abs']) < 1e-3
+    # save / load cycle of THIS package's module: identical bits
+    path = tmp_path / 'ckpt.pt'
+    torch.save(m.state_dict(), path)
+    m2 = H.device_model('efficientnetv2-tiny', pcfg, 8, torch.load(path, weights_only=True))
+    assert torch.equal(m2((crops.cuda(), k.cuda())), out)
+    # fp16 file: the engine converts on load; the result equals the fp32 engine fed the fp16-rounded weights
+    sd16 = {kk: (v.half() if v.is_floating_point() else v) for kk, v in sd.items()}
+    torch.save(sd16, path)
+    ld = torch.load(path, weights_only=True)
+    from metrabs_b200.engine import Engine, make_config
+    import metrabs_b200
+    from metrabs_b200.backbones.efficientnet import stage_table
+    stages, last = stage_table('tiny', True)
+    metrabs_b200.set_config(metrabs_b200.Config(proc_side=64))
+    e16 = Engine(make_config(metrabs_b200.get_config(), 8, stages=stages, last_channel=last))
+    e16.load_state_dict(ld)  # fp16 tensors straight into mtb_load_weight (MTB_DTYPE_F16)
+    m3 = H.device_model('efficientnetv2-tiny', pcfg, 8, {kk: (v.float() if v.is_floating_point() else v) for kk, v in sd16.items()})
+    assert torch.equal(e16.forward(crops.cuda(), k.cuda()), m3((crops.cuda(), k.cuda())))

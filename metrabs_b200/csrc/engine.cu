@@ -1336,11 +1336,11 @@ static int forward_body(mtb_handle* h, const float* crops, const float* intrinsi
                     (double*)(ws.base + ws.off_partial), st);
 }
 
-// MTB_GRAPH=1 (opt-in until measured on the GPU box): mtb_forward captures its own launches into a CUDA graph the second
-// time it sees the same (buffers, batch, stream) and replays that graph from then on - the 465 launches of a step were
-// 8-9 % faster as one graph launch than as stream submissions (bench.py --graph 1).  A profiling window bypasses it
-// (events cannot be timed inside a graph), any capture failure falls back to plain launches for that key.
-// destroys and forgets the captured forwards whose workspace is `ws` (nullptr: all of them)
+// mtb_forward captures its own launches into a CUDA graph the second time it sees the same (buffers, batch, stream) and
+// replays that graph from then on: the ~465 launches of a step cost less as one graph launch than as stream submissions
+// (measured, round 2: 12.28 k vs 11.83 k crops/s end to end through mtb_forward_host_submit/_wait, EfficientNetV2-L@256, 256
+// crops).  MTB_GRAPH=0 disables it.  A profiling window bypasses it (events cannot be timed inside a graph), a caller that
+// is itself capturing the stream just records our launches, any capture failure falls back to plain launches for that key.
 static void drop_graphs_on(mtb_handle* h, const void* ws) {
   for (size_t i = 0; i < h->graphs.size();) {
     if (ws == nullptr || h->graphs[i].ws == ws) {
@@ -1356,7 +1356,7 @@ static bool graph_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MTB_GRAPH");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
 }

@@ -51,6 +51,8 @@ struct Tc32Params {
   int n_tiles, m_tiles, kchunks, taps;
   int nstages, stage_stride, lo_off;
   int chain;             // k-blocks per partial accumulation chain (drained into registers after each)
+  int debug;             // MTB_T32_DEBUG bits (perf experiments only, results are wrong): 1 splitters skip their work, 2 accumulator
+                         // warps skip the TMEM drains, 4 skip the epilogue math + stores
   int Hout, Wout, tiles_w, tiles_h, pad_t, pad_l, R, S, stride, dil;
 };
 
@@ -75,6 +77,15 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
+// explicit shared-window 16-byte accesses (a generic pointer into dynamic shared memory compiles to LD.E / ST.E)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 // acc[0..63] += 64 TMEM columns of this warp's 32 lanes (columns >= n_ld were not written by the MMA and are skipped)
 __device__ __forceinline__ void t32_drain(uint32_t taddr, int n_ld, float* acc) {
 #pragma unroll
@@ -296,8 +307,8 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait_a(full0 + stage * 8, phase);
-        uint8_t* base = smem + stage * stage_stride;
-        int i = st;
+        const uint32_t base = smem_base + stage * stage_stride;
+        int i = (p.debug & 1) ? tot_chunks : st;
         if (sc != nullptr) {
           // A rows with the squeeze-excitation scale: s[crop(row)][k .. k+3]; the scale vector is re-read only when the crop
           // (or the swizzled K offset) changes from one of this thread's rows to the next
@@ -306,7 +317,7 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           int r = r0;
 #pragma unroll 2
           for (; i < a_chunks; i += NT, r += RSTEP) {
-            float4 v = *reinterpret_cast<const float4*>(base + i * 16);
+            float4 v = lds128(base + i * 16);
             const int k = kc * BK + ((j ^ (r & 7)) << 2);
             const int m = m_blk * TC_BM + r;
             if (m < p.M && k < Cin) {
@@ -323,20 +334,20 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             split_tf32(v.y, h.y, l.y);
             split_tf32(v.z, h.z, l.z);
             split_tf32(v.w, h.w, l.w);
-            *reinterpret_cast<float4*>(base + i * 16) = h;
-            *reinterpret_cast<float4*>(base + lo_off + i * 16) = l;
+            sts128(base + i * 16, h);
+            sts128(base + lo_off + i * 16, l);
           }
         }
 #pragma unroll 4
         for (; i < tot_chunks; i += NT) {
-          const float4 v = *reinterpret_cast<const float4*>(base + i * 16);
+          const float4 v = lds128(base + i * 16);
           float4 h, l;
           split_tf32(v.x, h.x, l.x);
           split_tf32(v.y, h.y, l.y);
           split_tf32(v.z, h.z, l.z);
           split_tf32(v.w, h.w, l.w);
-          *reinterpret_cast<float4*>(base + i * 16) = h;
-          *reinterpret_cast<float4*>(base + lo_off + i * 16) = l;
+          sts128(base + i * 16, h);
+          sts128(base + lo_off + i * 16, l);
         }
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
@@ -382,7 +393,7 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait_a(smem_u32(&p_full[pbuf]), p_phase);
         tc_fence_after();
         const uint32_t taddr = lane_base + T32_P_COL + pbuf * T32_BN;
-        t32_drain(taddr, n_ld, acc);
+        if (!(p.debug & 2)) t32_drain(taddr, n_ld, acc);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_empty[pbuf]);
@@ -399,7 +410,7 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(&s_empty[sbuf]);
       if (++sbuf == 2) { sbuf = 0; s_phase ^= 1; }
       // epilogue from registers: + bias, activation, residual, fp32 store (each thread: one pixel, <= 64 contiguous channels)
-      if (valid) {
+      if (valid && !(p.debug & 4)) {
 #pragma unroll
         for (int g = 0; g < 16; ++g) {
           if (g * 4 < ncols) {
@@ -568,6 +579,9 @@ inline const char* tc32_conv_launch(const Tc32Weights& w, const ConvParams& p, b
     if (chain_env < 0) { const char* e = getenv("MTB_T32_CHAIN"); chain_env = e ? atoi(e) : 0; }
     if (bn_env >= 32 && bn_env <= 128 && bn_env % 32 == 0) bn = bn_env;
     if (chain_env >= 1) q.chain = chain_env;
+    static int dbg_env = -1;
+    if (dbg_env < 0) { const char* e = getenv("MTB_T32_DEBUG"); dbg_env = e ? atoi(e) : 0; }
+    q.debug = dbg_env;
   }
   const int bk = rb / 4;
   q.bn = bn;

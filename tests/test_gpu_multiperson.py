@@ -68,9 +68,11 @@ def test_crop_generation_vs_reference(H, G, num_aug, af):
 
     def linear(c):  # undo the final `crops **= gamma / 2.2` (multiperson_model.py:318): back to linear light
         return c.clamp_min(0) ** (1.0 / gexp)
-    # (1) the warp kernel alone, on the reference's own inverse projections.  Bars: 1e-5 in LINEAR light (what the gather and
-    # the bilinear weights produce); the gamma-encoded output x^(gamma/2.2) has slope 0.27 x^-0.73 -> 40 at x = 1e-3, so in
-    # dark / half-outside pixels a 3e-6 difference of the linear value shows as 1e-4 there: held to 5e-4
+    # (1) the warp kernel alone, on the reference's own inverse projections.  Bars: 5e-5 in LINEAR light - source coordinates
+    # reach 260 px, where one fp32 ulp is 3e-5 px, and across the zero-padding border of the frame the bilinear blend has a
+    # gradient of O(1) per px, so two fp32 evaluation orders of the same homography differ by ~1e-5 there (measured 1.1-1.9e-5;
+    # 9.8e-6 on the 12-coefficient case without border pixels).  The gamma-encoded output x^(gamma/2.2) has slope
+    # 0.27 x^-0.73 -> 40 at x = 1e-3, so dark / half-outside pixels show those differences as ~1e-4: held to 5e-4
     inv_ref = torch.from_numpy(G[tag + '_invproj']).cuda().contiguous()
     crops = warping.warp_images_with_pyramid(images, pyr, k_box, inv_ref, d_box, lev, gam / 2.2, 64, ids, num_aug, af).cpu()
     err_lin = (linear(crops) - linear(ref)).abs().max().item()
@@ -81,8 +83,8 @@ def test_crop_generation_vs_reference(H, G, num_aug, af):
     err2 = (crops2 - ref).abs().max().item()
     print(f'{tag}: max abs crop error, linear light {err_lin:.2e} / gamma-encoded {err:.2e} on the reference matrices; {err2_lin:.2e} / '
           f'{err2:.2e} with the device setup; inverse-projection rel diff {e_inv:.1e}; levels {sorted(set(lev.cpu().tolist()))}')
-    assert err_lin < 1e-5 and err < 5e-4
-    assert err2_lin < 5e-5 and err2 < 5e-4
+    assert err_lin < 5e-5 and err < 5e-4
+    assert err2_lin < 1e-4 and err2 < 5e-4
     assert len(set(lev.cpu().tolist())) >= 2  # the scene exercises more than one pyramid level
 
 

@@ -70,6 +70,9 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __host__ __device__ inline uint32_t umma_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
+// variant for the MTB_T32_DEBUG=8 experiment: the raw tile stays in place (the tensor core is assumed to ignore the low 13
+// mantissa bits = truncation) and only lo = x - trunc(x) is written
+__device__ __forceinline__ float split_tf32_lo_trunc(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 // hi = x rounded to tf32 (nearest, ties away: integer add on the bit pattern, carries into the exponent correctly),
 // lo = x - hi (exact: hi and x agree in sign/exponent up to one binade, the difference has <= 13 significant bits)
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
@@ -112,10 +115,9 @@ __device__ __forceinline__ float t32_act(float x) {
   }
 }
 
-template <int ACT, int RES>
+template <int ACT, int RES, int RB>  // RB: bytes per operand row of a stage: 128 (32 fp32, 128B swizzle) or 64 (16 fp32, 64B swizzle)
 __global__ void __launch_bounds__(T32_THREADS, 1)
 tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Tc32Params p) {
-  constexpr int RB = 128;          // bytes per operand row
   constexpr int BK = RB / 4;       // fp32 elements per row
   constexpr int KSTEPS = RB / 32;  // K steps (K = 8 tf32 = 32 bytes) per stage
   extern __shared__ uint8_t tc_smem_raw[];
@@ -237,7 +239,7 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 10) {
     // ===== MMA issuer: main term into the partial buffer P (short chain), correction terms into S (whole tile) =====
-    constexpr uint32_t hi_sw = (uint32_t)((8 * RB) >> 4) | (1u << 14) | (2u << 29);
+    constexpr uint32_t hi_sw = (uint32_t)((8 * RB) >> 4) | (1u << 14) | ((RB == 128 ? 2u : 4u) << 29);
     const uint32_t stride16 = stage_stride >> 4;
     const uint32_t base16 = smem_base >> 4;
     const uint32_t b_off16 = a_bytes >> 4;
@@ -287,11 +289,11 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 11) {
     // ===== splitters: raw fp32 tile -> (hi in place, lo in the mirror tile); optional SE scale on A (mode 0) =====
-    // Thread st handles the 16-byte chunks st, st + NT, st + 2 NT, ... of the stage: NT is a multiple of 8 chunks per row, so
-    // its chunk column j = st & 7 is fixed and its rows are r0 + (NT/8) t.  With the 128B swizzle the logical K offset of its
-    // chunk depends on (j, r & 7) only - fixed per thread when NT/8 is a multiple of 8, else it cycles with t.
+    // Thread st handles the 16-byte chunks st, st + NT, st + 2 NT, ... of the stage: NT is a multiple of the chunks per row, so
+    // its chunk column j is fixed and its rows are r0 + (NT/CPR) t.  The TMA swizzle puts logical chunk j ^ swz(r) at
+    // physical position j (128B swizzle: swz = r & 7; 64B swizzle: swz = (r >> 1) & 3).
     constexpr int NT = T32_SPLIT_WARPS * 32;
-    constexpr int CPR = RB / 16;                        // 16-byte chunks per row (8)
+    constexpr int CPR = RB / 16;                        // 16-byte chunks per row
     constexpr int RSTEP = NT / CPR;                     // rows between consecutive chunks of one thread
     const int st = (warp - 11) * 32 + lane;
     const int j = st & (CPR - 1), r0 = st / CPR;
@@ -318,11 +320,12 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 2
           for (; i < a_chunks; i += NT, r += RSTEP) {
             float4 v = lds128(base + i * 16);
-            const int k = kc * BK + ((j ^ (r & 7)) << 2);
+            const int swz = RB == 128 ? (r & 7) : ((r >> 1) & 3);
+            const int k = kc * BK + ((j ^ swz) << 2);
             const int m = m_blk * TC_BM + r;
             if (m < p.M && k < Cin) {
               const int crop = m / P;
-              const int key = crop * 8 + (r & 7);
+              const int key = crop * 8 + swz;
               if (key != last_key) {
                 s4 = __ldg(reinterpret_cast<const float4*>(sc + (size_t)crop * Cin + k));
                 last_key = key;
@@ -341,6 +344,11 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 4
         for (; i < tot_chunks; i += NT) {
           const float4 v = lds128(base + i * 16);
+          if (p.debug & 8) {
+            sts128(base + lo_off + i * 16, make_float4(split_tf32_lo_trunc(v.x), split_tf32_lo_trunc(v.y), split_tf32_lo_trunc(v.z),
+                                                       split_tf32_lo_trunc(v.w)));
+            continue;
+          }
           float4 h, l;
           split_tf32(v.x, h.x, l.x);
           split_tf32(v.y, h.y, l.y);
@@ -533,25 +541,32 @@ inline int tc32_pick_bn(int cout, int m_tiles, int num_kb) {
   return best;
 }
 
-template <int ACT, int RES>
+template <int ACT, int RES, int RB>
 inline const char* tc32_launch_k(int grid, const CUtensorMap& a, const CUtensorMap& b, const Tc32Params& q, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc32_conv_kernel<ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, T32_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc32_conv_kernel<ACT, RES, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, T32_SMEM_BYTES) != cudaSuccess)
       return "cannot raise dynamic shared memory for tc32_conv_kernel";
     attr_set = true;
   }
-  launch_k(tc32_conv_kernel<ACT, RES>, dim3(grid), dim3(T32_THREADS), T32_SMEM_BYTES, st, a, b, q);
+  launch_k(tc32_conv_kernel<ACT, RES, RB>, dim3(grid), dim3(T32_THREADS), T32_SMEM_BYTES, st, a, b, q);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 template <int ACT>
-inline const char* tc32_dispatch_res(int res_mode, int grid, const CUtensorMap& a, const CUtensorMap& b, const Tc32Params& q,
+inline const char* tc32_dispatch_res(int res_mode, int rb, int grid, const CUtensorMap& a, const CUtensorMap& b, const Tc32Params& q,
                                      cudaStream_t st) {
+  if (rb == 128) {
+    switch (res_mode) {
+      case 0: return tc32_launch_k<ACT, 0, 128>(grid, a, b, q, st);
+      case 1: return tc32_launch_k<ACT, 1, 128>(grid, a, b, q, st);
+      default: return tc32_launch_k<ACT, 2, 128>(grid, a, b, q, st);
+    }
+  }
   switch (res_mode) {
-    case 0: return tc32_launch_k<ACT, 0>(grid, a, b, q, st);
-    case 1: return tc32_launch_k<ACT, 1>(grid, a, b, q, st);
-    default: return tc32_launch_k<ACT, 2>(grid, a, b, q, st);
+    case 0: return tc32_launch_k<ACT, 0, 64>(grid, a, b, q, st);
+    case 1: return tc32_launch_k<ACT, 1, 64>(grid, a, b, q, st);
+    default: return tc32_launch_k<ACT, 2, 64>(grid, a, b, q, st);
   }
 }
 
@@ -570,9 +585,16 @@ inline const char* tc32_conv_launch(const Tc32Weights& w, const ConvParams& p, b
   q.tiles_h = (p.Hout + TC_TILE_H - 1) / TC_TILE_H;
   q.M = p.B * p.Hout * p.Wout;
   q.m_tiles = q.mode == 0 ? (q.M + TC_BM - 1) / TC_BM : p.B * q.tiles_w * q.tiles_h;
-  const int rb = 128;
+  // 64-byte rows (K = 16 per stage): 32 KB stages at N = 128, six in flight - the TMA -> split -> MMA chain of a stage is
+  // latency-bound (measured with MTB_T32_DEBUG: the split alone cost 42 % of the kernel time with three 64 KB stages)
+  int rb = 64;
   int bn = tc32_pick_bn(p.Cout, q.m_tiles, q.taps * ((p.Cin + 31) / 32));
-  q.chain = 2;
+  {
+    static int rb_env = -1;
+    if (rb_env < 0) { const char* e = getenv("MTB_T32_RB"); rb_env = e ? atoi(e) : 0; }
+    if (rb_env == 64 || rb_env == 128) rb = rb_env;
+  }
+  q.chain = rb == 128 ? 2 : 4;  // 8 main-term MMAs per partial chain either way
   {
     static int bn_env = -1, chain_env = -1;  // A/B switches: MTB_T32_BN = 32..128, MTB_T32_CHAIN = k-blocks per partial chain
     if (bn_env < 0) { const char* e = getenv("MTB_T32_BN"); bn_env = e ? atoi(e) : 0; }
@@ -617,10 +639,10 @@ inline const char* tc32_conv_launch(const Tc32Weights& w, const ConvParams& p, b
   const int grid = total < 148 ? total : 148;
   const int res_mode = p.res ? (res_first ? 2 : 1) : 0;
   switch (p.act) {
-    case ACT_NONE: return tc32_dispatch_res<ACT_NONE>(res_mode, grid, ms->a, ms->b, q, st);
-    case ACT_SILU: return tc32_dispatch_res<ACT_SILU>(res_mode, grid, ms->a, ms->b, q, st);
-    case ACT_RELU: return tc32_dispatch_res<ACT_RELU>(res_mode, grid, ms->a, ms->b, q, st);
-    case ACT_HSWISH: return tc32_dispatch_res<ACT_HSWISH>(res_mode, grid, ms->a, ms->b, q, st);
+    case ACT_NONE: return tc32_dispatch_res<ACT_NONE>(res_mode, rb, grid, ms->a, ms->b, q, st);
+    case ACT_SILU: return tc32_dispatch_res<ACT_SILU>(res_mode, rb, grid, ms->a, ms->b, q, st);
+    case ACT_RELU: return tc32_dispatch_res<ACT_RELU>(res_mode, rb, grid, ms->a, ms->b, q, st);
+    case ACT_HSWISH: return tc32_dispatch_res<ACT_HSWISH>(res_mode, rb, grid, ms->a, ms->b, q, st);
     default: return "unsupported activation in the 3xTF32 epilogue";
   }
 }

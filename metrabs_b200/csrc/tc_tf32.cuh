@@ -219,7 +219,8 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 9) {
     // ===== B-operand (weights) TMA producer =====
     uint32_t stage = 0, phase = 0, sb = smem_base + a_bytes;
-    const int taps = pin(p.taps), kchunks = pin(p.kchunks), Cin = pin(p.Cin), bn = pin(p.bn);
+    const int taps = pin(p.taps), kchunks = pin(p.kchunks), Cin = pin(p.Cin), bn = pin(p.bn), Cout_rows = pin(p.Cout);
+    const uint32_t lo_off_u = pin((uint32_t)p.lo_off);
     TileWalk tw_(blockIdx.x, gridDim.x, p.n_tiles);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
       const int nrow = tw_.n_blk * bn;
@@ -228,8 +229,10 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int i = 0; i < num_kb; ++i) {
         mbar_wait_a(empty0 + stage * 8, phase ^ 1);
         if (elect_one()) {
-          mbar_expect_tx_a(full0 + stage * 8, b_bytes);
+          // weights are split on the host: plane 0 = hi (tf32-rounded), plane 1 = lo, stacked as [2 * Cout][K]
+          mbar_expect_tx_a(full0 + stage * 8, 2 * b_bytes);
           tma_load_2d_a(sb, &tmB, full0 + stage * 8, tap * Cin + kc * BK, nrow);
+          tma_load_2d_a(sb + lo_off_u, &tmB, full0 + stage * 8, tap * Cin + kc * BK, Cout_rows + nrow);
         }
         __syncwarp();
         if (++kc == kchunks) { kc = 0; if (++tap == taps) tap = 0; }
@@ -298,7 +301,7 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int st = (warp - 11) * 32 + lane;
     const int j = st & (CPR - 1), r0 = st / CPR;
     const int a_chunks = TC_BM * CPR;
-    const int tot_chunks = (TC_BM + p.b_rows) * CPR;
+    const int tot_chunks = a_chunks;   // the weight tile arrives already split (hi / lo planes): only A is split here
     const uint32_t lo_off = (uint32_t)p.lo_off;
     const float* __restrict__ sc = p.a_scale;
     const int kchunks = pin(p.kchunks), Cin = pin(p.Cin), P = pin(p.a_scale_P);
@@ -482,7 +485,7 @@ inline const char* make_tmap_nhwc_f32(CUtensorMap* m, const void* ptr, uint64_t 
 
 struct Tc32Weights {
   bool ready = false;
-  float* d_w = nullptr;     // fp32 [Cout][taps*Cin] K-major (BN folded)
+  float* d_w = nullptr;     // fp32 [2][Cout][taps*Cin] K-major (BN folded): hi plane, lo plane
   float* d_bias = nullptr;  // [Cout]
   int Cout = 0, Cin = 0, taps = 1, S = 1;
   struct MapSet {
@@ -494,12 +497,22 @@ struct Tc32Weights {
   mutable size_t map_rr = 0;
 };
 
-// wk: fp32 [K = taps*Cin][Cout] (BN folded) -> fp32 [Cout][K]
+// wk: fp32 [K = taps*Cin][Cout] (BN folded) -> two K-major planes [2][Cout][K]: hi = tf32(w) (round to nearest, as
+// split_tf32 on the device) and lo = w - hi (exact in fp32)
 inline const char* tc32_prepare_weights(Tc32Weights& w, const float* wk, const float* bias, int K, int cout, int R, int S, int cin,
                                         std::vector<void*>& allocs) {
-  std::vector<float> t((size_t)K * cout);
+  std::vector<float> t((size_t)2 * K * cout);
   for (int k = 0; k < K; ++k)
-    for (int n = 0; n < cout; ++n) t[(size_t)n * K + k] = wk[(size_t)k * cout + n];
+    for (int n = 0; n < cout; ++n) {
+      const float x = wk[(size_t)k * cout + n];
+      uint32_t u;
+      memcpy(&u, &x, 4);
+      u = (u + 0x1000u) & 0xffffe000u;
+      float hi;
+      memcpy(&hi, &u, 4);
+      t[(size_t)n * K + k] = hi;
+      t[(size_t)cout * K + (size_t)n * K + k] = x - hi;
+    }
   if (cudaMalloc((void**)&w.d_w, t.size() * 4) != cudaSuccess) return "cudaMalloc failed";
   allocs.push_back(w.d_w);
   if (cudaMemcpy(w.d_w, t.data(), t.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return "cudaMemcpy failed";
@@ -585,9 +598,9 @@ inline const char* tc32_conv_launch(const Tc32Weights& w, const ConvParams& p, b
   q.tiles_h = (p.Hout + TC_TILE_H - 1) / TC_TILE_H;
   q.M = p.B * p.Hout * p.Wout;
   q.m_tiles = q.mode == 0 ? (q.M + TC_BM - 1) / TC_BM : p.B * q.tiles_w * q.tiles_h;
-  // 64-byte rows (K = 16 per stage): 32 KB stages at N = 128, six in flight - the TMA -> split -> MMA chain of a stage is
-  // latency-bound (measured with MTB_T32_DEBUG: the split alone cost 42 % of the kernel time with three 64 KB stages)
-  int rb = 64;
+  // 128-byte rows (K = 32 per stage, three 64 KB stages at N = 128).  64-byte rows (six 32 KB stages) were measured SLOWER
+  // (64.6 vs 55.8 ms of tc32 time per 128 crops): the per-k-block costs of the issuing warps double; MTB_T32_RB=64 selects them
+  int rb = 128;
   int bn = tc32_pick_bn(p.Cout, q.m_tiles, q.taps * ((p.Cin + 31) / 32));
   {
     static int rb_env = -1;
@@ -623,7 +636,7 @@ inline const char* tc32_conv_launch(const Tc32Weights& w, const ConvParams& p, b
     const char* e = q.mode == 0 ? make_tmap_2d_f32(&c.a, p.in, (uint64_t)q.M, (uint64_t)p.Cin, TC_BM, (uint32_t)bk)
                                 : make_tmap_nhwc_f32(&c.a, p.in, p.B, p.Hin, p.Win, p.Cin, (uint32_t)p.stride, (uint32_t)bk);
     if (e) return e;
-    e = make_tmap_2d_f32(&c.b, w.d_w, (uint64_t)p.Cout, (uint64_t)w.taps * p.Cin, (uint32_t)q.b_rows, (uint32_t)bk);
+    e = make_tmap_2d_f32(&c.b, w.d_w, (uint64_t)2 * p.Cout, (uint64_t)w.taps * p.Cin, (uint32_t)q.b_rows, (uint32_t)bk);
     if (e) return e;
     c.in = p.in; c.B = p.B; c.bn = bn; c.rb = rb;
     if (w.map_sets.size() < 16) {

@@ -35,6 +35,8 @@ constexpr int T32_RING_BYTES = 216 * 1024;
 constexpr int T32_BAR_OFF = T32_RING_BYTES;
 constexpr int T32_SMEM_BYTES = T32_BAR_OFF + 512 + 1024 /*align slack*/;
 constexpr int T32_BN = 128;                                 // accumulator columns per buffer
+constexpr int T32_ACC_SHARE = 64;                           // A-tile rows [0, 64) of every stage are split by the 8 accumulator warps,
+                                                            // rows [64, 128) by the dedicated splitter warps
 constexpr uint32_t T32_S_COL = 0, T32_P_COL = 2 * T32_BN;   // TMEM column bases of the S and P buffer pairs
 
 struct Tc32Params {
@@ -115,6 +117,84 @@ __device__ __forceinline__ float t32_act(float x) {
   }
 }
 
+// Splits the 16-byte chunks first, first + step, ... (< end) of the A tile of one stage: raw fp32 -> hi in place + lo in the
+// mirror tile; with `sc` the squeeze-excitation scale s[crop(row)][k..k+3] is applied first (mode 0).  The TMA swizzle puts
+// logical chunk j ^ swz(r) at physical position j of row r (128B swizzle: swz = r & 7; 64B swizzle: swz = (r >> 1) & 3).
+template <int RB>
+__device__ __forceinline__ void t32_split_a(uint32_t base, uint32_t lo_off, int first, int end, int step, const float* __restrict__ sc,
+                                            int m_row0, int M, int P, int Cin, int k0) {
+  constexpr int CPR = RB / 16;
+  if (sc != nullptr) {
+    int last_key = -1;
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int i = first; i < end; i += step) {
+      float4 v = lds128(base + i * 16);
+      const int r = i / CPR, j = i - r * CPR;
+      const int swz = RB == 128 ? (r & 7) : ((r >> 1) & 3);
+      const int k = k0 + ((j ^ swz) << 2);
+      const int m = m_row0 + r;
+      if (m < M && k < Cin) {
+        const int crop = m / P;
+        const int key = crop * 8 + swz;
+        if (key != last_key) {  // the scale vector is re-read only when the crop (or the swizzled K offset) changes
+          s4 = __ldg(reinterpret_cast<const float4*>(sc + (size_t)crop * Cin + k));
+          last_key = key;
+        }
+        v.x *= s4.x; v.y *= s4.y; v.z *= s4.z; v.w *= s4.w;
+      }
+      float4 h, l;
+      split_tf32(v.x, h.x, l.x);
+      split_tf32(v.y, h.y, l.y);
+      split_tf32(v.z, h.z, l.z);
+      split_tf32(v.w, h.w, l.w);
+      sts128(base + i * 16, h);
+      sts128(base + lo_off + i * 16, l);
+    }
+  } else {
+#pragma unroll 4
+    for (int i = first; i < end; i += step) {
+      const float4 v = lds128(base + i * 16);
+      float4 h, l;
+      split_tf32(v.x, h.x, l.x);
+      split_tf32(v.y, h.y, l.y);
+      split_tf32(v.z, h.z, l.z);
+      split_tf32(v.w, h.w, l.w);
+      sts128(base + i * 16, h);
+      sts128(base + lo_off + i * 16, l);
+    }
+  }
+}
+
+// The accumulator warps' side job: while they wait (for a partial chain, for the correction accumulator) or between the
+// store groups of their epilogue they split THEIR share of whatever operand stage has landed next - the dedicated splitter
+// warps alone made the split the bottleneck (MTB_T32_DEBUG=1: 31 vs 48-54 ms of kernel time per 128 crops without / with it).
+// Stages are helped strictly in order, each exactly once; nothing here blocks.
+template <int RB>
+struct T32Helper {
+  uint32_t stage = 0, phase = 0;
+  int tile, kb = 0;
+  __device__ __forceinline__ bool help(const Tc32Params& p, uint32_t smem_base, uint32_t full0, uint64_t* split, int total_tiles, int num_kb,
+                                       int tid256, int lane) {
+    if (tile >= total_tiles) return false;
+    uint32_t ok = lane == 0 ? (uint32_t)mbar_try_wait_a(full0 + stage * 8, phase) : 0u;
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (!ok) return false;
+    constexpr int CPR = RB / 16, BK = RB / 4;
+    const int kc = kb % p.kchunks;
+    const uint32_t base = smem_base + stage * (uint32_t)p.stage_stride;
+    if (!(p.debug & 1))
+      t32_split_a<RB>(base, (uint32_t)p.lo_off, tid256, T32_ACC_SHARE * CPR, 256, p.a_scale, (tile / p.n_tiles) * TC_BM, p.M, p.a_scale_P,
+                      p.Cin, kc * BK);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&split[stage]);
+    if (++kb == num_kb) { kb = 0; tile += gridDim.x; }
+    if (++stage == (uint32_t)p.nstages) { stage = 0; phase ^= 1; }
+    return true;
+  }
+};
+
 template <int ACT, int RES, int RB>  // RB: bytes per operand row of a stage: 128 (32 fp32, 128B swizzle) or 64 (16 fp32, 64B swizzle)
 __global__ void __launch_bounds__(T32_THREADS, 1)
 tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Tc32Params p) {
@@ -140,7 +220,7 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 9 && lane == 0) {
     for (int i = 0; i < T32_MAX_STAGES; ++i) {
       mbar_init(&full[i], 2);
-      mbar_init(&split[i], T32_SPLIT_WARPS);
+      mbar_init(&split[i], T32_SPLIT_WARPS + TCV_EPI_WARPS);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -291,75 +371,23 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (++sbuf == 2) { sbuf = 0; s_phase ^= 1; }
     }
   } else if (warp >= 11) {
-    // ===== splitters: raw fp32 tile -> (hi in place, lo in the mirror tile); optional SE scale on A (mode 0) =====
-    // Thread st handles the 16-byte chunks st, st + NT, st + 2 NT, ... of the stage: NT is a multiple of the chunks per row, so
-    // its chunk column j is fixed and its rows are r0 + (NT/CPR) t.  The TMA swizzle puts logical chunk j ^ swz(r) at
-    // physical position j (128B swizzle: swz = r & 7; 64B swizzle: swz = (r >> 1) & 3).
+    // ===== dedicated splitters: rows [T32_ACC_SHARE, 128) of the A tile of every stage (the accumulator warps take the rest;
+    // the weight tile arrives already split into hi / lo planes) =====
     constexpr int NT = T32_SPLIT_WARPS * 32;
-    constexpr int CPR = RB / 16;                        // 16-byte chunks per row
-    constexpr int RSTEP = NT / CPR;                     // rows between consecutive chunks of one thread
+    constexpr int CPR = RB / 16;
     const int st = (warp - 11) * 32 + lane;
-    const int j = st & (CPR - 1), r0 = st / CPR;
-    const int a_chunks = TC_BM * CPR;
-    const int tot_chunks = a_chunks;   // the weight tile arrives already split (hi / lo planes): only A is split here
     const uint32_t lo_off = (uint32_t)p.lo_off;
-    const float* __restrict__ sc = p.a_scale;
-    const int kchunks = pin(p.kchunks), Cin = pin(p.Cin), P = pin(p.a_scale_P);
+    const int kchunks = pin(p.kchunks);
     uint32_t stage = 0, phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int m_blk = t / p.n_tiles;
+      const int m_row0 = (t / p.n_tiles) * TC_BM;
       int kc = 0;
 #pragma unroll 1
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait_a(full0 + stage * 8, phase);
         const uint32_t base = smem_base + stage * stage_stride;
-        int i = (p.debug & 1) ? tot_chunks : st;
-        if (sc != nullptr) {
-          // A rows with the squeeze-excitation scale: s[crop(row)][k .. k+3]; the scale vector is re-read only when the crop
-          // (or the swizzled K offset) changes from one of this thread's rows to the next
-          int last_key = -1;
-          float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          int r = r0;
-#pragma unroll 2
-          for (; i < a_chunks; i += NT, r += RSTEP) {
-            float4 v = lds128(base + i * 16);
-            const int swz = RB == 128 ? (r & 7) : ((r >> 1) & 3);
-            const int k = kc * BK + ((j ^ swz) << 2);
-            const int m = m_blk * TC_BM + r;
-            if (m < p.M && k < Cin) {
-              const int crop = m / P;
-              const int key = crop * 8 + swz;
-              if (key != last_key) {
-                s4 = __ldg(reinterpret_cast<const float4*>(sc + (size_t)crop * Cin + k));
-                last_key = key;
-              }
-              v.x *= s4.x; v.y *= s4.y; v.z *= s4.z; v.w *= s4.w;
-            }
-            float4 h, l;
-            split_tf32(v.x, h.x, l.x);
-            split_tf32(v.y, h.y, l.y);
-            split_tf32(v.z, h.z, l.z);
-            split_tf32(v.w, h.w, l.w);
-            sts128(base + i * 16, h);
-            sts128(base + lo_off + i * 16, l);
-          }
-        }
-#pragma unroll 4
-        for (; i < tot_chunks; i += NT) {
-          const float4 v = lds128(base + i * 16);
-          if (p.debug & 8) {
-            sts128(base + lo_off + i * 16, make_float4(split_tf32_lo_trunc(v.x), split_tf32_lo_trunc(v.y), split_tf32_lo_trunc(v.z),
-                                                       split_tf32_lo_trunc(v.w)));
-            continue;
-          }
-          float4 h, l;
-          split_tf32(v.x, h.x, l.x);
-          split_tf32(v.y, h.y, l.y);
-          split_tf32(v.z, h.z, l.z);
-          split_tf32(v.w, h.w, l.w);
-          sts128(base + i * 16, h);
-          sts128(base + lo_off + i * 16, l);
-        }
+        if (!(p.debug & 1))
+          t32_split_a<RB>(base, lo_off, T32_ACC_SHARE * CPR + st, TC_BM * CPR, NT, p.a_scale, m_row0, p.M, p.a_scale_P, p.Cin, kc * BK);
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&split[stage]);
@@ -377,6 +405,18 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float* __restrict__ out = p.out;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
     const int n_chains = (num_kb + chain - 1) / chain;
+    T32Helper<RB> helper;
+    helper.tile = blockIdx.x;
+    const int tid256 = warp * 32 + lane;
+    auto help = [&]() { return helper.help(p, smem_base, full0, split, total_tiles, num_kb, tid256, lane); };
+    auto wait_helping = [&](uint32_t bar, uint32_t parity) {  // warp-uniform poll (lane 0 decides); split work fills the wait
+      for (;;) {
+        uint32_t ok = lane == 0 ? (uint32_t)mbar_try_wait_a(bar, parity) : 0u;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (ok) break;
+        help();
+      }
+    };
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int m_blk = t / p.n_tiles, n_blk = t - m_blk * p.n_tiles;
       const int n0 = n_blk * p.bn + half * 64;                       // first channel of this warp's columns
@@ -401,7 +441,7 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = 0.f;
       for (int c = 0; c < n_chains; ++c) {
-        mbar_wait_a(smem_u32(&p_full[pbuf]), p_phase);
+        wait_helping(smem_u32(&p_full[pbuf]), p_phase);
         tc_fence_after();
         const uint32_t taddr = lane_base + T32_P_COL + pbuf * T32_BN;
         if (!(p.debug & 2)) t32_drain(taddr, n_ld, acc);
@@ -410,7 +450,7 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) mbar_arrive(&p_empty[pbuf]);
         if (++pbuf == 2) { pbuf = 0; p_phase ^= 1; }
       }
-      mbar_wait_a(smem_u32(&s_full[sbuf]), s_phase);
+      wait_helping(smem_u32(&s_full[sbuf]), s_phase);
       tc_fence_after();
       {
         const uint32_t taddr = lane_base + T32_S_COL + sbuf * T32_BN;
@@ -421,10 +461,11 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(&s_empty[sbuf]);
       if (++sbuf == 2) { sbuf = 0; s_phase ^= 1; }
       // epilogue from registers: + bias, activation, residual, fp32 store (each thread: one pixel, <= 64 contiguous channels)
-      if (valid && !(p.debug & 4)) {
+      {
+        const bool do_store = valid && !(p.debug & 4);
 #pragma unroll
         for (int g = 0; g < 16; ++g) {
-          if (g * 4 < ncols) {
+          if (do_store && g * 4 < ncols) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + g * 4));
             float o[4] = {acc[g * 4 + 0] + b4.x, acc[g * 4 + 1] + b4.y, acc[g * 4 + 2] + b4.z, acc[g * 4 + 3] + b4.w};
             if constexpr (RES != 0) {
@@ -442,6 +483,7 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             *reinterpret_cast<float4*>(out + off + n0 + g * 4) = make_float4(o[0], o[1], o[2], o[3]);
           }
+          if ((g & 3) == 3) help();  // all lanes, whatever `do_store`: keeps the operand pipeline fed during the epilogue
         }
       }
     }

@@ -129,7 +129,8 @@ int mtb_backbone_forward(mtb_handle* h, const float* crops, int batch, void* fea
 int mtb_head_decode(mtb_handle* h, const void* features, int batch, float* coords2d, float* coords3d_rel,
                     void* workspace, size_t workspace_bytes, void* stream);
 
-/* ptu.soft_argmax (ptu.py:54-75), standalone over materialised logits (config c5 / roofline sweep).
+/* ptu.soft_argmax (ptu.py:54-75), standalone over materialised logits (config c5 / roofline sweep); dtype f32, bf16 or
+ * f16 (f16: what the reference's head emits under autocast, multiperson_model.py:241; reference layout only).
  * BDJHW: logits [B,D,J,H,W] -> out [B,J,3] = (x,y,z) in [0,1];  with depth == 0: logits [B,J,H,W] -> out
  * [B,J,2].  BHWN: logits [B,H,W,J*(1+D)] -> out2d [B,J,2] and out3d [B,J,3] (either may be NULL). */
 int mtb_softargmax(const void* logits, int dtype, int layout, int batch, int n_joints, int depth, int height,

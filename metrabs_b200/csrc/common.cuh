@@ -134,6 +134,8 @@ template <>
 __device__ __forceinline__ float load1<float>(const float* p) { return *p; }
 template <>
 __device__ __forceinline__ float load1<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <>
+__device__ __forceinline__ float load1<__half>(const __half* p) { return __half2float(*p); }
 template <typename T>
 __device__ __forceinline__ void store1(T* p, float v);
 template <>

@@ -69,6 +69,46 @@ struct Vec16<__nv_bfloat16> {
   }
 };
 
+template <>
+struct Vec16<__half> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __half* p, float* v) {
+    uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+    const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+};
+
+// packed fp32 pairs (FFMA2 / FADD2 / FMUL2 on sm_100): the 16-bit-logit soft-argmax spends 8 elements per 16-byte load and
+// is issue-bound, not bandwidth-bound, with scalar math (r1: 0.42-0.45 of the HBM peak)
+typedef unsigned long long sa_f2;
+__device__ __forceinline__ sa_f2 sa_pack(float lo, float hi) {
+  sa_f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void sa_unpack(sa_f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ sa_f2 sa_fma(sa_f2 a, sa_f2 b, sa_f2 c) {
+  sa_f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ sa_f2 sa_mul(sa_f2 a, sa_f2 b) {
+  sa_f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ sa_f2 sa_add(sa_f2 a, sa_f2 b) {
+  sa_f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 __device__ __forceinline__ float ex2_fast(float x) {  // one MUFU op; inputs here are <= 0
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -143,11 +183,32 @@ __global__ void __launch_bounds__(256) softargmax_bdjhw_kernel(const T* __restri
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       float es = 0.f, ex = 0.f;
+      if constexpr (VEC == 8) {
+        // 16-bit logits: scale / sum / index-weighted sum on packed fp32 pairs (4 FFMA2 + 3 FADD2 + FMUL2 + 3 FFMA2 per 8 elements)
+        const sa_f2 l2 = sa_pack(L2E, L2E), nm = sa_pack(-mL, -mL);
+        sa_f2 e2[4];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const float ee = ex2_fast(fmaf(v[u][i], L2E, -mL));
-        es += ee;
-        if (i > 0) ex = fmaf(ee, (float)i, ex);
+        for (int i = 0; i < 4; ++i) {
+          float a, b;
+          sa_unpack(sa_fma(sa_pack(v[u][2 * i], v[u][2 * i + 1]), l2, nm), a, b);
+          e2[i] = sa_pack(ex2_fast(a), ex2_fast(b));
+        }
+        float lo, hi;
+        sa_unpack(sa_add(sa_add(e2[0], e2[1]), sa_add(e2[2], e2[3])), lo, hi);
+        es = lo + hi;
+        sa_f2 xw = sa_mul(e2[0], sa_pack(0.f, 1.f));
+        xw = sa_fma(e2[1], sa_pack(2.f, 3.f), xw);
+        xw = sa_fma(e2[2], sa_pack(4.f, 5.f), xw);
+        xw = sa_fma(e2[3], sa_pack(6.f, 7.f), xw);
+        sa_unpack(xw, lo, hi);
+        ex = lo + hi;
+      } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const float ee = ex2_fast(fmaf(v[u][i], L2E, -mL));
+          es += ee;
+          if (i > 0) ex = fmaf(ee, (float)i, ex);
+        }
       }
       s_ += es;
       sx += fmaf(es, (float)xx[u], ex);

@@ -1259,7 +1259,10 @@ int mtb_softargmax(const void* logits, int dtype, int layout_, int batch, int n_
                    int width, float* out2d, float* out3d, void* stream) {
   if (!logits || batch <= 0 || n_joints <= 0 || depth < 0 || height <= 0 || width <= 0)
     return fail(nullptr, MTB_ERR_INVALID_ARG, "invalid soft-argmax arguments");
-  if (dtype != MTB_DTYPE_F32 && dtype != MTB_DTYPE_BF16) return fail(nullptr, MTB_ERR_UNSUPPORTED, "soft-argmax dtype must be f32 or bf16");
+  if (dtype != MTB_DTYPE_F32 && dtype != MTB_DTYPE_BF16 && dtype != MTB_DTYPE_F16)
+    return fail(nullptr, MTB_ERR_UNSUPPORTED, "soft-argmax dtype must be f32, bf16 or f16");
+  if (dtype == MTB_DTYPE_F16 && layout_ != MTB_LAYOUT_BDJHW)
+    return fail(nullptr, MTB_ERR_UNSUPPORTED, "f16 logits are supported in the reference layout (BDJHW) only");
   cudaStream_t st = (cudaStream_t)stream;
   if (layout_ == MTB_LAYOUT_BDJHW) {
     const bool two_d = depth == 0;
@@ -1281,10 +1284,14 @@ int mtb_softargmax(const void* logits, int dtype, int layout_, int batch, int n_
       if (vec && pow2) MTB_SA_LAUNCH(float, 4, true);
       else if (vec) MTB_SA_LAUNCH(float, 4, false);
       else MTB_SA_LAUNCH(float, 1, false);
-    } else {
+    } else if (dtype == MTB_DTYPE_BF16) {
       if (vec && pow2) MTB_SA_LAUNCH(__nv_bfloat16, 8, true);
       else if (vec) MTB_SA_LAUNCH(__nv_bfloat16, 8, false);
       else MTB_SA_LAUNCH(__nv_bfloat16, 1, false);
+    } else {  // fp16: what the reference's head emits under its autocast (multiperson_model.py:241, models/metrabs.py:80)
+      if (vec && pow2) MTB_SA_LAUNCH(__half, 8, true);
+      else if (vec) MTB_SA_LAUNCH(__half, 8, false);
+      else MTB_SA_LAUNCH(__half, 1, false);
     }
 #undef MTB_SA_LAUNCH
     cudaError_t e = cudaGetLastError();

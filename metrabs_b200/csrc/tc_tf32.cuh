@@ -31,8 +31,10 @@ namespace mtb {
 constexpr int T32_SPLIT_WARPS = 5;
 constexpr int T32_THREADS = (11 + T32_SPLIT_WARPS) * 32;  // warps 0-7 accumulate + epilogue, 8 A producer, 9 B producer, 10 MMA, 11.. splitters
 constexpr int T32_MAX_STAGES = 8;
-constexpr int T32_RING_BYTES = 216 * 1024;
-constexpr int T32_BAR_OFF = T32_RING_BYTES;
+constexpr int T32_RING_BYTES = 192 * 1024;                  // three 64 KB stages at N = 128
+constexpr int T32_STG_OFF = T32_RING_BYTES;                 // epilogue staging: 8 warps x [32 rows x 128 B] (register row-domain ->
+constexpr int T32_STG_BYTES = 8 * 4096;                     // coalesced column-domain stores)
+constexpr int T32_BAR_OFF = T32_STG_OFF + T32_STG_BYTES;
 constexpr int T32_SMEM_BYTES = T32_BAR_OFF + 512 + 1024 /*align slack*/;
 constexpr int T32_BN = 128;                                 // accumulator columns per buffer
 constexpr int T32_ACC_SHARE = 64;                           // A-tile rows [0, 64) of every stage are split by the 8 accumulator warps,
@@ -423,19 +425,12 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n_tile = min(p.bn, p.Cout - n_blk * p.bn);           // valid channels of the tile
       const int ncols = max(0, min(64, n_tile - half * 64));         // valid columns of this warp (multiple of 4)
       const int n_ld = min(64, max(0, ((n_tile + 15) & ~15) - half * 64));  // columns of this warp the MMA wrote
-      bool valid;
-      size_t off;
-      if (p.mode == 0) {
-        const int m = m_blk * TC_BM + row;
-        valid = m < p.M;
-        off = (size_t)m * p.Cout;
-      } else {
-        const int tw = m_blk % p.tiles_w;
-        const int th = (m_blk / p.tiles_w) % p.tiles_h;
-        const int b = m_blk / (p.tiles_w * p.tiles_h);
-        const int oh = th * TC_TILE_H + (row >> 4), ow = tw * TC_TILE_W + (row & 15);
-        valid = oh < p.Hout && ow < p.Wout;
-        off = ((size_t)(b * p.Hout + oh) * p.Wout + ow) * p.Cout;
+      // tile geometry (the rows of this warp are resolved in the epilogue's column domain)
+      int tw = 0, th = 0, tb = 0;
+      if (p.mode != 0) {
+        tw = m_blk % p.tiles_w;
+        th = (m_blk / p.tiles_w) % p.tiles_h;
+        tb = m_blk / (p.tiles_w * p.tiles_h);
       }
       float acc[64];
 #pragma unroll
@@ -460,30 +455,61 @@ tc32_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sbuf]);
       if (++sbuf == 2) { sbuf = 0; s_phase ^= 1; }
-      // epilogue from registers: + bias, activation, residual, fp32 store (each thread: one pixel, <= 64 contiguous channels)
+      // epilogue.  The accumulators sit in the ROW domain (thread = one pixel, 64 channels): storing from there writes 32
+      // scattered 16-byte pieces per instruction (measured: the epilogue cost 7-10 ms of 45 per 128 crops).  Each warp therefore
+      // transposes 32 columns at a time through its private swizzled staging tile and runs bias + activation + residual + store
+      // in the COLUMN domain: 4 rows x 128 contiguous bytes per load / store instruction.
       {
-        const bool do_store = valid && !(p.debug & 4);
+        const uint32_t stg = smem_base + T32_STG_OFF + warp * 4096;
+        const int cj = lane & 7, rsub = lane >> 3;
 #pragma unroll
-        for (int g = 0; g < 16; ++g) {
-          if (do_store && g * 4 < ncols) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + g * 4));
-            float o[4] = {acc[g * 4 + 0] + b4.x, acc[g * 4 + 1] + b4.y, acc[g * 4 + 2] + b4.z, acc[g * 4 + 3] + b4.w};
-            if constexpr (RES != 0) {
-              const float4 rv = *reinterpret_cast<const float4*>(res + off + n0 + g * 4);
-              if constexpr (RES == 2) {
-                o[0] = t32_act<ACT>(o[0] + rv.x); o[1] = t32_act<ACT>(o[1] + rv.y);
-                o[2] = t32_act<ACT>(o[2] + rv.z); o[3] = t32_act<ACT>(o[3] + rv.w);
+        for (int rd = 0; rd < 2; ++rd) {
+          if (rd * 32 < ncols) {  // warp-uniform
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              sts128(stg + lane * 128 + ((g ^ (lane & 7)) << 4),
+                     make_float4(acc[rd * 32 + g * 4 + 0], acc[rd * 32 + g * 4 + 1], acc[rd * 32 + g * 4 + 2], acc[rd * 32 + g * 4 + 3]));
+            __syncwarp();
+            const int col = rd * 32 + cj * 4;
+            const bool cok = col < ncols && !(p.debug & 4);
+            const float4 b4 = cok ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = rsub + it * 4;  // row of this warp's 32
+              const float4 v = lds128(stg + rr * 128 + ((cj ^ (rr & 7)) << 4));
+              bool rvalid;
+              size_t off;
+              if (p.mode == 0) {
+                const int m = m_blk * TC_BM + q * 32 + rr;
+                rvalid = m < p.M;
+                off = (size_t)m * p.Cout;
               } else {
-                o[0] = t32_act<ACT>(o[0]) + rv.x; o[1] = t32_act<ACT>(o[1]) + rv.y;
-                o[2] = t32_act<ACT>(o[2]) + rv.z; o[3] = t32_act<ACT>(o[3]) + rv.w;
+                const int trow = q * 32 + rr;
+                const int oh = th * TC_TILE_H + (trow >> 4), ow = tw * TC_TILE_W + (trow & 15);
+                rvalid = oh < p.Hout && ow < p.Wout;
+                off = ((size_t)(tb * p.Hout + oh) * p.Wout + ow) * p.Cout;
               }
-            } else {
+              if (rvalid && cok) {
+                float o[4] = {v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w};
+                if constexpr (RES != 0) {
+                  const float4 rv = *reinterpret_cast<const float4*>(res + off + n0 + col);
+                  if constexpr (RES == 2) {
+                    o[0] = t32_act<ACT>(o[0] + rv.x); o[1] = t32_act<ACT>(o[1] + rv.y);
+                    o[2] = t32_act<ACT>(o[2] + rv.z); o[3] = t32_act<ACT>(o[3] + rv.w);
+                  } else {
+                    o[0] = t32_act<ACT>(o[0]) + rv.x; o[1] = t32_act<ACT>(o[1]) + rv.y;
+                    o[2] = t32_act<ACT>(o[2]) + rv.z; o[3] = t32_act<ACT>(o[3]) + rv.w;
+                  }
+                } else {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) o[i] = t32_act<ACT>(o[i]);
+                  for (int i = 0; i < 4; ++i) o[i] = t32_act<ACT>(o[i]);
+                }
+                *reinterpret_cast<float4*>(out + off + n0 + col) = make_float4(o[0], o[1], o[2], o[3]);
+              }
             }
-            *reinterpret_cast<float4*>(out + off + n0 + g * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            __syncwarp();  // the staging tile is rewritten by the next round
           }
-          if ((g & 3) == 3) help();  // all lanes, whatever `do_store`: keeps the operand pipeline fed during the epilogue
+          help();  // all lanes: keeps the operand pipeline fed during the epilogue
         }
       }
     }

@@ -319,7 +319,7 @@ def soft_argmax_device(logits, layout, n_joints, depth, height, width):
     """Standalone soft-argmax on materialised logits (mtb_softargmax).  Returns (out2d, out3d)."""
     if not logits.is_cuda:
         raise _lib.MetrabsB200Error('soft_argmax needs a CUDA tensor (no CPU fallback)')
-    if logits.dtype not in (torch.float32, torch.bfloat16):
+    if logits.dtype not in (torch.float32, torch.bfloat16, torch.float16):
         logits = logits.float()
     logits = logits.contiguous()
     dev = logits.device

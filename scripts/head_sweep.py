@@ -34,7 +34,7 @@ def main():
     pk = bench.peaks()
     dev = torch.device('cuda', 0)
     J = 24
-    for dtype in (torch.float32, torch.bfloat16):
+    for dtype in (torch.float32, torch.bfloat16, torch.float16):
         for B in (64, 128, 256, 512, 1024):
             D = H = W = 32
             if B * J * D * H * W * (4 if dtype == torch.float32 else 2) > 8e9:

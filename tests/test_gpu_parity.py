@@ -54,6 +54,11 @@ def test_soft_argmax_layouts_vs_oracle(H, shape):
     # bf16 storage of the same values
     _, out3b = soft_argmax_device(l3.bfloat16().cuda(), _lib.LAYOUT_BDJHW, j, d, h, w)
     assert (out3b.cpu() - port.soft_argmax(l3.bfloat16().float(), (4, 3, 1))).abs().max() < 5e-6
+    # fp16 storage: what the reference's head emits under its autocast (multiperson_model.py:241, models/metrabs.py:80 `.float()`)
+    _, out3h = soft_argmax_device(l3.half().cuda(), _lib.LAYOUT_BDJHW, j, d, h, w)
+    assert (out3h.cpu() - port.soft_argmax(l3.half().float(), (4, 3, 1))).abs().max() < 5e-6
+    out2h, _ = soft_argmax_device(l2.half().cuda(), _lib.LAYOUT_BDJHW, j, 0, h, w)
+    assert (out2h.cpu() - port.soft_argmax(l2.half().float(), (3, 2))).abs().max() < 5e-6
     # internal NHWC layout: channel n = J + d*J + j
     nhwc = torch.cat([l2, l3.reshape(b, d * j, h, w)], dim=1).permute(0, 2, 3, 1).contiguous()
     out2n, out3n = soft_argmax_device(nhwc.cuda(), _lib.LAYOUT_BHWN, j, d, h, w)

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256, OW == 2 ? 3 : 2) dwconv3x3_pool_bf16_kern
 // fp32-storage twin of the strip kernel above for the 3xTF32 parity mode: 4 channels (one 16-byte vector) x OW output pixels
 // per thread, exact activation (expf SiLU), the same block-reduced partial pooling slices.  grid (ceil(C/128), slices, B).
 template <int STRIDE, int ACT, int OW = 4>
-__global__ void __launch_bounds__(256, 2) dwconv3x3_pool_f32_kernel(ConvParams p, float* __restrict__ pooled) {
+__global__ void __launch_bounds__(256, 3) dwconv3x3_pool_f32_kernel(ConvParams p, float* __restrict__ pooled) {
   pdl_trigger();
   pdl_wait();
   constexpr int NCOL = (OW - 1) * STRIDE + 3;

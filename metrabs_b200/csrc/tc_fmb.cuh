@@ -1,0 +1,502 @@
+// Fused FusedMBConv block (backbones/efficientnet.py:176-234, expand_ratio != 1, stride 1):
+//
+//     y = x + BN2(conv1x1( SiLU(BN1(conv3x3(x))) ))            x: [B,H,W,Cin] bf16 NHWC, expanded width Cexp = 4*Cin
+//
+// as ONE persistent tcgen05 kernel: the 128-pixel x Cexp expanded tile never leaves the SM.
+//
+//   GEMM-1  (3x3 expand, implicit GEMM)   A = resident (8+2) x (16+2) x Cin input patch (chunk-planar, no-swizzle UMMA
+//           descriptors shifted per tap, as mode 2 of tc_conv_kernel), B = one (tap, 128-channel chunk) weight block per ring
+//           stage, D = TMEM accumulator acc1[g & 1] (128 lanes x 128 columns), 9 * Cin/16 MMAs per chunk.
+//   epilogue-1 (8 warps)  acc1 -> + folded-BN bias -> SiLU -> bf16 -> shared memory, written directly in the canonical K-major
+//           no-swizzle operand layout [channel chunk of 8][128 rows][16 B]: it IS the A operand of GEMM-2.
+//   GEMM-2  (1x1 projection)  acc2[tile & 1] += A2(chunk) * W2[:, chunk]^T, 8 MMAs of N = Cout per chunk; the W2 slice of the
+//           chunk travels through the same ring (one stage).
+//   epilogue-2  acc2 -> + bias -> + residual x (re-read from L2: the patch loader fetched it two tiles ago) -> bf16 ->
+//           dense per-warp slab -> one TMA store per warp (box: Cout/2 channels x 8 x 4 pixels).
+//
+// The MMA issuer software-pipelines by one chunk:  G1(g), G2(g-1), G1(g+1), G2(g), ...  so the tensor pipe always has the
+// next chunk's GEMM-1 queued while the epilogue warps convert the previous accumulator.  HBM traffic per block = input
+// (1.4x with the halo, mostly L2 hits) + output; the expanded tensor (4x the input) is never written or re-read.
+//
+// Weights are re-packed on the host into the exact shared-memory images of the ring stages, so a stage is ONE 1-D bulk copy
+// (cp.async.bulk) with no tensor map.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace mtb {
+
+constexpr int FMB_NC = 128;                       // expanded channels per chunk (N of GEMM-1, K of GEMM-2)
+constexpr int FMB_A2_BYTES = 128 * FMB_NC * 2;    // one GEMM-2 A operand buffer
+constexpr int FMB_MAX_STAGES = 8;
+constexpr int FMB_SMEM_BUDGET = 226 * 1024;       // + 1 KB alignment slack = the 227 KB opt-in limit
+
+struct FmbParams {
+  const __nv_bfloat16* in;  // [B][H][W][Cin]; also the residual
+  const uint8_t* w1;        // chunk-major images: (chunk c, tap) -> [Cin/8][wc][8] bf16
+  const uint8_t* w2;        // chunk c -> [wc/8][Cout][8] bf16
+  const float* bias1;       // [Cexp]
+  const float* bias2;       // [Cout]
+  int H, W, Cin, Cexp, Cout;
+  int tiles_w, tiles_h, total_tiles;
+  int nch;                  // ceil(Cexp / 128)
+  int pad_t, pad_l;
+  int has_res;
+  int npatch, patch_bytes, patch_off;
+  int nstages, stage_bytes;  // ring at offset 0
+  int na2, a2_off, slab_off, bias_off, bar_off;
+  int debug;                 // MTB_FMB_DEBUG bits (perf experiments): 1 skip TMA store, 2 skip epilogue-1 math, 4 skip residual
+};
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+
+// Warp roles: 0-7 epilogue; 8, 11, 12 patch loaders; 9 weight producer; 10 TMEM allocator + MMA issuer; 13-14 idle.
+__global__ void __launch_bounds__(TC_THREADS, 1) fmb_kernel(const __grid_constant__ CUtensorMap tmO, const FmbParams p) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + p.bar_off);
+  uint64_t* full = bars;                       // [8]  ring stage landed (expect_tx)
+  uint64_t* empty = bars + 8;                  // [8]  ring stage consumed (tcgen05.commit)
+  uint64_t* patch_full = bars + 16;            // [4]
+  uint64_t* patch_empty = bars + 20;           // [4]
+  uint64_t* acc1_full = bars + 24;             // [2]
+  uint64_t* acc1_empty = bars + 26;            // [2]
+  uint64_t* a2_full = bars + 28;               // [2]
+  uint64_t* a2_empty = bars + 30;              // [2]
+  uint64_t* acc2_full = bars + 32;             // [2]
+  uint64_t* acc2_empty = bars + 34;            // [2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 36);
+  float* bias1_s = (float*)(smem + p.bias_off);
+  float* bias2_s = bias1_s + p.Cexp;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 8 && lane == 0) tma_prefetch_desc(&tmO);
+  if (warp == 9 && lane == 0) {
+    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&patch_full[i], 3); mbar_init(&patch_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], TCV_EPI_WARPS);
+      mbar_init(&a2_full[i], TCV_EPI_WARPS); mbar_init(&a2_empty[i], 1);
+      mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], TCV_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 10) tmem_alloc(tmem_slot, 512);
+  pdl_trigger();
+  pdl_wait();
+  for (int i = threadIdx.x; i < p.Cexp + p.Cout; i += blockDim.x) bias1_s[i] = i < p.Cexp ? p.bias1[i] : p.bias2[i - p.Cexp];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  const int ntl = ((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int nch = p.nch;
+  const int G = ntl * nch;                      // chunk jobs of this CTA
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+  const int nstages = p.nstages;
+  const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
+  const int planes = p.Cin >> 3;
+
+  if (warp == 9) {
+    // ===== weight producer: per chunk job g the nine (tap) blocks of W1, then the W2 slice of job g-1 =====
+    uint32_t stage = 0, phase = 0;
+    const uint32_t cin2 = (uint32_t)p.Cin * 2, cout2 = (uint32_t)p.Cout * 2;
+    auto put = [&](const uint8_t* src, uint32_t bytes) {
+      mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx_a(full0 + stage * 8, bytes);
+        bulk_load_1d(smem_base + stage * stage_bytes, src, bytes, full0 + stage * 8);
+      }
+      __syncwarp();
+      if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; }
+    };
+    int c = 0, cprev = 0;
+    for (int g = 0; g <= G; ++g) {
+      if (g < G) {
+        const int wc = min(FMB_NC, p.Cexp - c * FMB_NC);
+        const uint8_t* src = p.w1 + (size_t)c * FMB_NC * 9 * cin2;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) put(src + (size_t)tap * wc * cin2, (uint32_t)wc * cin2);
+      }
+      if (g >= 1) {
+        const int wc = min(FMB_NC, p.Cexp - cprev * FMB_NC);
+        put(p.w2 + (size_t)cprev * FMB_NC * cout2, (uint32_t)wc * cout2);
+      }
+      cprev = c;
+      if (++c == nch) c = 0;
+    }
+  } else if (warp == 10) {
+    // ===== MMA issuer =====
+    constexpr uint32_t hi_patch = (uint32_t)((TC_PATCH_W * 16) >> 4) | (1u << 14);  // SBO = one patch row
+    constexpr uint32_t hi_8 = 8u | (1u << 14);                                      // SBO = 8 rows x 16 B
+    constexpr uint32_t plane16 = TC_PLANE_BYTES >> 4;
+    const uint32_t base16 = smem_base >> 4, stage16 = stage_bytes >> 4;
+    const uint32_t patch0_16 = base16 + ((uint32_t)p.patch_off >> 4), patch_b16 = (uint32_t)p.patch_bytes >> 4;
+    const uint32_t a2_16 = base16 + ((uint32_t)p.a2_off >> 4);
+    const uint32_t acc1_full0 = smem_u32(acc1_full), acc1_empty0 = smem_u32(acc1_empty);
+    const uint32_t a2_full0 = smem_u32(a2_full), a2_empty0 = smem_u32(a2_empty);
+    const uint32_t acc2_full0 = smem_u32(acc2_full), acc2_empty0 = smem_u32(acc2_empty);
+    const uint32_t patch_full0 = smem_u32(patch_full), patch_empty0 = smem_u32(patch_empty);
+    const int k1 = p.Cin >> 4;  // K = 16 steps per tap
+    const uint32_t Cout = (uint32_t)p.Cout;
+    const uint32_t idesc2 = umma_idesc_bf16(p.Cout);
+    uint32_t stage = 0, phase = 0, s16 = base16;
+    uint32_t pb = 0, pb_phase = 0;
+    uint32_t a2b = 0, a2_phase = 0;    // A2 buffer of the NEXT G2
+    int c = 0, cprev = 0, tl_prev = 0;
+    for (int g = 0; g <= G; ++g) {
+      if (g < G) {
+        const uint32_t ab = (uint32_t)g & 1u;
+        const uint32_t wc = (uint32_t)min(FMB_NC, p.Cexp - c * FMB_NC);
+        mbar_wait_a(acc1_empty0 + ab * 8, (((uint32_t)g >> 1) & 1u) ^ 1u);
+        if (c == 0) mbar_wait_a(patch_full0 + pb * 8, pb_phase);
+        tc_fence_after();
+        const uint32_t idesc1 = umma_idesc_bf16((int)wc);
+        const uint32_t d1 = tmem_base + ab * FMB_NC;
+        const uint32_t patch16 = patch0_16 + pb * patch_b16;
+        const uint32_t lbo_b = wc << 16;  // B planes are wc rows x 16 B apart
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait_a(full0 + stage * 8, phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_lo = patch16 + (uint32_t)((tap / 3) * TC_PATCH_W + (tap % 3));
+#pragma unroll 1
+            for (int k = 0; k < k1; ++k)
+              umma_bf16(d1, make_desc((a_lo + (uint32_t)(2 * k) * plane16) | (plane16 << 16), hi_patch),
+                        make_desc((s16 + (uint32_t)(2 * k) * wc) | lbo_b, hi_8), idesc1, (uint32_t)(tap | k));
+            umma_commit_a(empty0 + stage * 8);
+          }
+          __syncwarp();
+          s16 += stage16;
+          if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; s16 = base16; }
+        }
+        if (elect_one()) {
+          umma_commit_a(acc1_full0 + ab * 8);
+          if (c == nch - 1) umma_commit_a(patch_empty0 + pb * 8);
+        }
+        __syncwarp();
+        if (c == nch - 1 && ++pb == (uint32_t)p.npatch) { pb = 0; pb_phase ^= 1; }
+      }
+      if (g >= 1) {
+        // GEMM-2 of chunk job g-1
+        const uint32_t wc = (uint32_t)min(FMB_NC, p.Cexp - cprev * FMB_NC);
+        const uint32_t acc = (uint32_t)tl_prev & 1u;
+        mbar_wait_a(a2_full0 + a2b * 8, a2_phase);
+        if (cprev == 0) mbar_wait_a(acc2_empty0 + acc * 8, (((uint32_t)tl_prev >> 1) & 1u) ^ 1u);
+        mbar_wait_a(full0 + stage * 8, phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d2 = tmem_base + 2 * FMB_NC + acc * FMB_NC;
+          const uint32_t a16 = a2_16 + a2b * (FMB_A2_BYTES >> 4);
+          const int k2 = (int)(wc >> 4);
+#pragma unroll 1
+          for (int k = 0; k < k2; ++k)
+            umma_bf16(d2, make_desc((a16 + (uint32_t)(2 * k) * 128u) | (128u << 16), hi_8),
+                      make_desc((s16 + (uint32_t)(2 * k) * Cout) | (Cout << 16), hi_8), idesc2, (uint32_t)(cprev | k));
+          umma_commit_a(empty0 + stage * 8);
+          umma_commit_a(a2_empty0 + a2b * 8);
+          if (cprev == nch - 1) umma_commit_a(acc2_full0 + acc * 8);
+        }
+        __syncwarp();
+        s16 += stage16;
+        if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; s16 = base16; }
+        if (++a2b == (uint32_t)p.na2) { a2b = 0; a2_phase ^= 1; }
+        if (cprev == nch - 1) ++tl_prev;
+      }
+      cprev = c;
+      if (++c == nch) c = 0;
+    }
+  } else if (warp == 8 || warp == 11 || warp == 12) {
+    // ===== patch loaders: the (16+2) x (8+2) x Cin input patch of a tile, chunk-planar [plane][patch row][patch col][16 B];
+    // out-of-image pixels (the reference's explicit zero padding, efficientnet.py:1127-1161) are zero-filled =====
+    const int lt = (warp == 8 ? 0 : warp == 11 ? 32 : 64) + lane;
+    const int items = TC_PATCH_H * TC_PATCH_W * planes;
+    uint32_t pb = 0, pb_phase = 0;
+    for (int i = 0; i < ntl; ++i) {
+      const int t = (int)blockIdx.x + i * (int)gridDim.x;
+      const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, b = t / (p.tiles_w * p.tiles_h);
+      const int ih0 = th * TC_PT_H - p.pad_t, iw0 = tw * TC_PT_W - p.pad_l;
+      mbar_wait_a(smem_u32(&patch_empty[pb]), pb_phase ^ 1);
+      uint8_t* patch = smem + p.patch_off + pb * p.patch_bytes;
+      for (int it = lt; it < items; it += 96) {
+        const int j = it % planes, pix = it / planes;
+        const int ph = pix / TC_PATCH_W, pw = pix - ph * TC_PATCH_W;
+        const int ih = ih0 + ph, iw = iw0 + pw;
+        const bool ok = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+        const __nv_bfloat16* src = ok ? p.in + ((size_t)(b * p.H + ih) * p.W + iw) * p.Cin + j * 8 : p.in;
+        cp_async_16(patch + j * TC_PLANE_BYTES + pix * 16, src, ok ? 16u : 0u);
+      }
+      cp_async_wait_all();
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&patch_full[pb]);
+      if (++pb == (uint32_t)p.npatch) { pb = 0; pb_phase ^= 1; }
+    }
+  } else if (warp < TCV_EPI_WARPS) {
+    // ===== epilogue warps: epilogue-1 of every chunk job, epilogue-2 of tile t after epilogue-1 of (t+1, chunk 0) =====
+    const int q = warp & 3, hh = warp >> 2;
+    const int row = q * 32 + lane;
+    const int half = p.Cout >> 1;               // output channels per warp in epilogue-2 (multiple of 8)
+    const int n8 = half >> 3;
+    uint8_t* slab = smem + p.slab_off + warp * (32 * half * 2);
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t a2b = 0, a2_phase = 0;
+
+    auto epi2 = [&](int tl) {
+      const int t = (int)blockIdx.x + tl * (int)gridDim.x;
+      const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, b = t / (p.tiles_w * p.tiles_h);
+      const int oh = th * TC_PT_H + (row >> 3), ow = tw * TC_PT_W + (row & 7);
+      const bool valid = oh < p.H && ow < p.W;
+      const uint32_t acc = (uint32_t)tl & 1u;
+      // residual (= the block input) first: its L2 round trip overlaps the wait for the accumulator
+      uint4 rv[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        rv[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < n8 && valid && p.has_res && !(p.debug & 4))
+          rv[i] = *reinterpret_cast<const uint4*>(p.in + ((size_t)(b * p.H + oh) * p.W + ow) * p.Cin + hh * half + i * 8);
+      }
+      mbar_wait_a(smem_u32(&acc2_full[acc]), ((uint32_t)tl >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = lane_taddr + 2 * FMB_NC + acc * FMB_NC + (uint32_t)(hh * half);
+      if (lane == 0) tma_store_wait_read<0>();  // the previous store of this warp has read the slab
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        if (i < n8) {
+          uint32_t v[8];
+          tmem_ld8_issue(taddr + i * 8, v);
+          tmem_ld_wait();
+          const float* bs = bias2_s + hh * half + i * 8;
+          const unsigned wd[4] = {rv[i].x, rv[i].y, rv[i].z, rv[i].w};
+          uint4 ov;
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x0 = __uint_as_float(v[2 * e]) + bs[2 * e] + __uint_as_float(wd[e] << 16);
+            const float x1 = __uint_as_float(v[2 * e + 1]) + bs[2 * e + 1] + __uint_as_float(wd[e] & 0xffff0000u);
+            o2[e] = __floats2bfloat162_rn(x0, x1);
+          }
+          *reinterpret_cast<uint4*>(slab + lane * (half * 2) + i * 16) = ov;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc2_empty[acc]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && !(p.debug & 1)) {
+        tma_store_4d(&tmO, slab, hh * half, tw * TC_PT_W, th * TC_PT_H + q * 4, b);
+        tma_store_commit();
+      }
+    };
+
+    int c = 0, tl = 0;
+    for (int g = 0; g < G; ++g) {
+      const uint32_t ab = (uint32_t)g & 1u;
+      const int wc = min(FMB_NC, p.Cexp - c * FMB_NC);
+      mbar_wait_a(smem_u32(&acc1_full[ab]), ((uint32_t)g >> 1) & 1u);
+      mbar_wait_a(smem_u32(&a2_empty[a2b]), a2_phase ^ 1);
+      tc_fence_after();
+      const int col0 = hh * 64;
+      const uint32_t taddr = lane_taddr + ab * FMB_NC + (uint32_t)col0;
+      uint8_t* a2 = smem + p.a2_off + a2b * FMB_A2_BYTES + row * 16;
+      const float* b1 = bias1_s + c * FMB_NC + col0;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int cb = hf * 32;
+        if (col0 + cb < wc) {
+          uint32_t v[32];
+          tmem_ld16_issue(taddr + cb, v);
+          if (col0 + cb + 16 < wc) tmem_ld16_issue(taddr + cb + 16, v + 16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            if (col0 + cb + gq * 8 < wc) {
+              uint4 ov = make_uint4(0u, 0u, 0u, 0u);
+              if (!(p.debug & 2)) {
+                __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+                const float4 bl = *reinterpret_cast<const float4*>(b1 + cb + gq * 8);      // broadcast reads
+                const float4 bh = *reinterpret_cast<const float4*>(b1 + cb + gq * 8 + 4);
+                const float bb[8] = {bl.x, bl.y, bl.z, bl.w, bh.x, bh.y, bh.z, bh.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float x0 = tc_act<ACT_SILU>(__uint_as_float(v[gq * 8 + 2 * e]) + bb[2 * e]);
+                  const float x1 = tc_act<ACT_SILU>(__uint_as_float(v[gq * 8 + 2 * e + 1]) + bb[2 * e + 1]);
+                  o2[e] = __floats2bfloat162_rn(x0, x1);
+                }
+              }
+              *reinterpret_cast<uint4*>(a2 + ((col0 + cb) / 8 + gq) * 2048) = ov;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&acc1_empty[ab]);
+        mbar_arrive(&a2_full[a2b]);
+      }
+      if (++a2b == (uint32_t)p.na2) { a2b = 0; a2_phase ^= 1; }
+      if (c == 0 && tl >= 1) epi2(tl - 1);
+      if (++c == nch) { c = 0; ++tl; }
+    }
+    if (ntl > 0) epi2(ntl - 1);
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct FmbWeights {
+  bool ready = false;
+  uint8_t* d_w1 = nullptr;
+  uint8_t* d_w2 = nullptr;
+  const float* d_b1 = nullptr;
+  const float* d_b2 = nullptr;
+  int Cin = 0, Cexp = 0, Cout = 0;
+  // shared-memory plan
+  int npatch = 0, patch_bytes = 0, patch_off = 0, nstages = 0, stage_bytes = 0, na2 = 1, a2_off = 0, slab_off = 0, bias_off = 0,
+      bar_off = 0, smem_bytes = 0;
+  mutable CUtensorMap mapO;
+  mutable const void* cached_out = nullptr;
+  mutable int cached_B = -1;
+};
+
+inline bool fmb_enabled() {  // MTB_FMB=0: FusedMBConv blocks run as two tc_conv_kernel launches (A/B runs, tests)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTB_FMB");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// shapes the fused kernel covers: 3x3 stride-1 expand (SiLU) + 1x1 projection, Cin = Cout (identity-shaped block)
+inline bool fmb_shape_ok(int cin, int cexp, int cout) {
+  return cin % 16 == 0 && cin >= 16 && cin <= 96 && cout == cin && cexp % 16 == 0 && cexp >= 32 && cexp <= 512;
+}
+
+inline bool fmb_plan(FmbWeights& f) {
+  const int planes = f.Cin / 8;
+  f.patch_bytes = (planes * TC_PLANE_BYTES + 1023) / 1024 * 1024;
+  f.stage_bytes = (FMB_NC * std::max(f.Cin, f.Cout) * 2 + 1023) / 1024 * 1024;
+  const int slab = 8 * 32 * (f.Cout / 2) * 2;
+  const int bias = ((f.Cexp + f.Cout) * 4 + 127) / 128 * 128;
+  static int na2_env = -1;
+  if (na2_env < 0) { const char* e = getenv("MTB_FMB_NA2"); na2_env = e ? atoi(e) : 1; }
+  f.na2 = na2_env == 2 ? 2 : 1;
+  for (int np = 3; np >= 2; --np) {
+    const int fixed = f.na2 * FMB_A2_BYTES + slab + bias + 512 + np * f.patch_bytes;
+    const int ns = std::min((FMB_SMEM_BUDGET - fixed) / f.stage_bytes, FMB_MAX_STAGES);
+    if (ns >= 4 || (np == 2 && ns >= 3)) {
+      f.npatch = np;
+      f.nstages = ns;
+      f.patch_off = ns * f.stage_bytes;
+      f.a2_off = f.patch_off + np * f.patch_bytes;
+      f.slab_off = f.a2_off + f.na2 * FMB_A2_BYTES;
+      f.bias_off = f.slab_off + slab;
+      f.bar_off = f.bias_off + bias;
+      f.smem_bytes = f.bar_off + 512 + 1024;
+      return true;
+    }
+  }
+  return false;
+}
+
+// w1: bf16 [Cexp][9*Cin] (k = tap*Cin + c), w2: bf16 [Cout][Cexp] (device copies of the two convs' tensor-core weights)
+inline const char* fmb_prepare(FmbWeights& f, const TcWeights& w1, const TcWeights& w2, std::vector<void*>& allocs) {
+  f.ready = false;
+  f.Cin = w1.Cin; f.Cexp = w1.Cout; f.Cout = w2.Cout;
+  if (!fmb_shape_ok(f.Cin, f.Cexp, f.Cout) || w2.Cin != f.Cexp || w1.taps != 9 || w2.taps != 1) return nullptr;
+  if (!fmb_plan(f)) return nullptr;
+  const int K1 = 9 * f.Cin;
+  std::vector<__nv_bfloat16> h1((size_t)f.Cexp * K1), h2((size_t)f.Cout * f.Cexp);
+  if (cudaMemcpy(h1.data(), w1.d_w, h1.size() * 2, cudaMemcpyDeviceToHost) != cudaSuccess) return "cudaMemcpy failed";
+  if (cudaMemcpy(h2.data(), w2.d_w, h2.size() * 2, cudaMemcpyDeviceToHost) != cudaSuccess) return "cudaMemcpy failed";
+  std::vector<__nv_bfloat16> i1(h1.size()), i2(h2.size());
+  const int nch = (f.Cexp + FMB_NC - 1) / FMB_NC;
+  size_t o1 = 0, o2 = 0;
+  for (int c = 0; c < nch; ++c) {
+    const int wc = std::min(FMB_NC, f.Cexp - c * FMB_NC);
+    for (int tap = 0; tap < 9; ++tap)
+      for (int j = 0; j < f.Cin / 8; ++j)
+        for (int n = 0; n < wc; ++n)
+          for (int e = 0; e < 8; ++e) i1[o1++] = h1[(size_t)(c * FMB_NC + n) * K1 + tap * f.Cin + j * 8 + e];
+    for (int j = 0; j < wc / 8; ++j)
+      for (int n = 0; n < f.Cout; ++n)
+        for (int e = 0; e < 8; ++e) i2[o2++] = h2[(size_t)n * f.Cexp + c * FMB_NC + j * 8 + e];
+  }
+  if (cudaMalloc((void**)&f.d_w1, i1.size() * 2) != cudaSuccess) return "cudaMalloc failed";
+  allocs.push_back(f.d_w1);
+  if (cudaMalloc((void**)&f.d_w2, i2.size() * 2) != cudaSuccess) return "cudaMalloc failed";
+  allocs.push_back(f.d_w2);
+  if (cudaMemcpy(f.d_w1, i1.data(), i1.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return "cudaMemcpy failed";
+  if (cudaMemcpy(f.d_w2, i2.data(), i2.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return "cudaMemcpy failed";
+  f.d_b1 = w1.d_bias; f.d_b2 = w2.d_bias;
+  f.cached_out = nullptr; f.cached_B = -1;
+  f.ready = true;
+  return nullptr;
+}
+
+// rank-4 bf16 NHWC output, box = (box_c channels) x 8 x 4 pixels, dense (no swizzle) rows in shared memory
+inline const char* make_tmap_nhwc_dense(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t box_c) {
+  tmap_encode_fn enc = get_tmap_encode();
+  if (!enc) return "cuTensorMapEncodeTiled unavailable";
+  cuuint64_t dims[4] = {C, W, H, B};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {box_c, TC_PT_W, 4, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(4d dense) failed";
+}
+
+inline const char* fmb_launch(const FmbWeights& f, const void* in, void* out, int B, int H, int W, int pad_t, int pad_l, bool has_res,
+                              cudaStream_t st) {
+  if (f.cached_out != out || f.cached_B != B) {
+    const char* e = make_tmap_nhwc_dense(&f.mapO, out, B, H, W, f.Cout, (uint32_t)(f.Cout / 2));
+    if (e) return e;
+    f.cached_out = out; f.cached_B = B;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(fmb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FMB_SMEM_BUDGET + 1024) != cudaSuccess)
+      return "cannot raise dynamic shared memory for fmb_kernel";
+    attr_set = true;
+  }
+  FmbParams p;
+  p.in = (const __nv_bfloat16*)in; p.w1 = f.d_w1; p.w2 = f.d_w2; p.bias1 = f.d_b1; p.bias2 = f.d_b2;
+  p.H = H; p.W = W; p.Cin = f.Cin; p.Cexp = f.Cexp; p.Cout = f.Cout;
+  p.tiles_w = (W + TC_PT_W - 1) / TC_PT_W; p.tiles_h = (H + TC_PT_H - 1) / TC_PT_H;
+  p.total_tiles = B * p.tiles_w * p.tiles_h;
+  p.nch = (f.Cexp + FMB_NC - 1) / FMB_NC;
+  p.pad_t = pad_t; p.pad_l = pad_l; p.has_res = has_res ? 1 : 0;
+  p.npatch = f.npatch; p.patch_bytes = f.patch_bytes; p.patch_off = f.patch_off;
+  p.nstages = f.nstages; p.stage_bytes = f.stage_bytes;
+  p.na2 = f.na2; p.a2_off = f.a2_off; p.slab_off = f.slab_off; p.bias_off = f.bias_off; p.bar_off = f.bar_off;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MTB_FMB_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
+  int grid = p.total_tiles < 148 ? p.total_tiles : 148;
+  launch_k(fmb_kernel, dim3(grid), dim3(TC_THREADS), (size_t)f.smem_bytes, st, f.mapO, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace mtb

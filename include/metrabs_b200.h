@@ -281,6 +281,14 @@ int mtb_op_input_shape(const mtb_handle* h, int op, int* height, int* width, int
  * kernels with the CUDA-core kernels on identical inputs. */
 int mtb_debug_run_op(mtb_handle* h, int op_index, const float* in, const float* res, const float* scale, int batch,
                      float* out, size_t out_floats, void* workspace, size_t workspace_bytes, void* stream);
+/* FusedMBConv block fusion (bf16 tensor-core mode): 1 when backbone op `op_index` (a 3x3 stride-1 expand conv) and the op
+ * after it (the 1x1 projection, + residual) run as ONE fmb_kernel launch (reference block:
+ * metrabs_pytorch/backbones/efficientnet.py:176-234).  mtb_debug_run_fused_block runs that pair in isolation on a
+ * caller-provided fp32 NHWC device tensor `in` [B,H,W,Cin] (also the residual when the block has one); `out` receives the
+ * block output [B,H,W,Cout] as fp32. */
+int mtb_op_is_fused_block(const mtb_handle* h, int op_index);
+int mtb_debug_run_fused_block(mtb_handle* h, int op_index, const float* in, int batch, float* out, size_t out_floats,
+                              void* workspace, size_t workspace_bytes, void* stream);
 /* CUDA-event profiler (bench.py's live roofline measurement): between begin and end, every kernel launch of the
  * classes selected by `class_mask` (bit i = class i) is bracketed by cudaEventRecord on the launching stream.
  * mtb_profile_end synchronises those events and returns, per class, the summed device time (ms), algorithmic

@@ -108,6 +108,9 @@ _SIGNATURES = {
                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'mtb_debug_run_op': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                    C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'mtb_op_is_fused_block': (C.c_int, [C.c_void_p, C.c_int]),
+    'mtb_debug_run_fused_block': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                            C.c_size_t, C.c_void_p]),
     'mtb_profile_begin': (C.c_int, [C.c_void_p, C.c_uint]),
     'mtb_profile_end': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                   C.POINTER(C.c_int64)]),

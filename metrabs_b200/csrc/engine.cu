@@ -17,6 +17,7 @@
 #include "conv_simt.cuh"
 #include "decode.cuh"
 #include "tc_gemm.cuh"
+#include "tc_fmb.cuh"
 #include "tc_tf32.cuh"
 #include "dw_tma.cuh"
 #include "multiperson.cuh"
@@ -29,11 +30,11 @@ std::string g_error;
 
 enum OpType { OP_STEM = 0, OP_CONV = 1, OP_DW = 2, OP_POOL = 3, OP_MAXPOOL = 4 };
 // kernel classes for the CUDA-event profiler (mtb_profile_begin / mtb_profile_end)
-enum KClass { KC_STEM = 0, KC_IGEMM_SIMT = 1, KC_DWCONV = 2, KC_POOL = 3, KC_SE_FC = 4, KC_TC_GEMM = 5, KC_TC_CONV3 = 6,
+enum KClass { KC_STEM = 0, KC_IGEMM_SIMT = 1, KC_DWCONV = 2, KC_POOL = 3, KC_SE_FC = 4, KC_TC_GEMM = 5, KC_FMB = 6,
               KC_HEAD_FUSED = 7, KC_HEAD_CONV_SIMT = 8, KC_SOFTARGMAX = 9, KC_RECON = 10, KC_OTHER = 11, KC_SE_SCALE = 12, KC_TC32 = 13,
               KC_COUNT = 14 };
 const char* kKClassNames[KC_COUNT] = {"stem_conv_kernel", "conv_igemm_kernel", "dwconv_kernel", "pool_mean_kernel",
-                                      "se_fc(conv_igemm_kernel)", "tc_conv_kernel", "tc_conv_kernel(unused)",
+                                      "se_fc(conv_igemm_kernel)", "tc_conv_kernel", "fmb_kernel",
                                       "tc_head_softargmax_kernel", "head_conv(conv_igemm_kernel)",
                                       "softargmax_bhwn_kernel", "recon_pass1+2_kernel", "other", "se_scale_kernel", "tc32_conv_kernel"};
 enum { BUF_FEATURES = -2, BUF_NONE = -1, BUF_SMALL0 = 4 };  // 0..3 big activation buffers, 4..6 small [B,C]
@@ -69,6 +70,7 @@ struct Op {
   float* d_bias = nullptr;  // fp32 [Cout]
   TcWeights tc;             // bf16 K-major copy + TMA descriptor state for the tcgen05 path
   Tc32Weights tc32;         // fp32 K-major copy + TMA descriptor state for the 3xTF32 tcgen05 path (MTB_PRECISION_TF32X3)
+  FmbWeights fmb;           // bf16 mode: this 3x3 expand conv and the NEXT op (1x1 projection) run as one fmb_kernel launch
   mutable DwTmaCache dw_cache;  // input tensor map of the TMA-staged depthwise kernel
   double flops = 0;         // 2*MACs per crop
   int stage = 0;            // EfficientNet stage (1-based; 0 = stem / last conv / other backbones)
@@ -710,6 +712,7 @@ int op_class(const Op& op) {
     default: break;
   }
   if (op.small_io) return KC_SE_FC;
+  if (op.fmb.ready && fmb_enabled()) return KC_FMB;
   if (op.tc.ready) return KC_TC_GEMM;  // one class per kernel: every tensor-core conv/GEMM launch is tc_conv_kernel
   if (op.tc32.ready) return KC_TC32;
   return KC_IGEMM_SIMT;
@@ -878,14 +881,38 @@ int run_op(mtb_handle* h, const Op& op, const float* crops, int B, const Workspa
 // Crop chunking (running a stage chunk by chunk so that its intermediates stay in the 126 MB L2) was built and measured
 // in round 1: 29.5 ms vs 22.7 ms per 256 crops - these kernels are latency / issue bound at 32-128 crops, not bandwidth
 // bound, so smaller launches lose more than L2 residency wins.  The executor therefore runs every op on the whole batch.
-int run_backbone(mtb_handle* h, const float* crops, int B, Workspace& ws, void* features, cudaStream_t st) {
-  for (size_t k = 0; k < h->ops.size(); ++k) {
+// one fmb_kernel launch for the FusedMBConv block (a = 3x3 expand, b = 1x1 projection [+ residual = a's input])
+int run_fused_block(mtb_handle* h, const Op& a, const Op& b, int B, const Workspace& ws, void* features, cudaStream_t st) {
+  const void* in = act_ptr(h, ws, a.in_buf, features, a.Hin, a.Win, a.Cin);
+  void* out = act_ptr(h, ws, b.out_buf, features, b.Hout, b.Wout, b.Cout);
+  const double bytes = 2.0 * B * a.Hin * a.Win * (a.Cin + b.Cout) + 2.0 * (9.0 * a.Cin * a.Cout + (double)b.Cin * b.Cout);
+  ProfScope prof(h, KC_FMB, (a.flops + b.flops) * B, bytes, st);
+  const char* e = fmb_launch(a.fmb, in, out, B, a.Hin, a.Win, a.pad_t, a.pad_l, b.res_buf != BUF_NONE, st);
+  if (e) return fail(h, MTB_ERR_CUDA, "fused FusedMBConv launch %s: %s", a.name.c_str(), e);
+  h->launches++;
+  return MTB_OK;
+}
+
+// ops [first, last): fusable pairs that lie inside the range run fused
+int run_ops_range(mtb_handle* h, size_t first, size_t last, const float* crops, int B, const Workspace& ws, void* features,
+                  cudaStream_t st) {
+  for (size_t k = first; k < last; ++k) {
     h->prof_cur_op = (int)k;
-    int rc = run_op(h, h->ops[k], crops, B, ws, features, st);
+    int rc;
+    if (h->ops[k].fmb.ready && fmb_enabled() && k + 1 < last) {
+      rc = run_fused_block(h, h->ops[k], h->ops[k + 1], B, ws, features, st);
+      ++k;
+    } else {
+      rc = run_op(h, h->ops[k], crops, B, ws, features, st);
+    }
     if (rc) return rc;
   }
   h->prof_cur_op = -1;
   return MTB_OK;
+}
+
+int run_backbone(mtb_handle* h, const float* crops, int B, Workspace& ws, void* features, cudaStream_t st) {
+  return run_ops_range(h, 0, h->ops.size(), crops, B, ws, features, st);
 }
 
 int check_common(mtb_handle* h, int B, size_t ws_bytes, const void* workspace) {
@@ -1179,6 +1206,20 @@ int mtb_finalize_weights(mtb_handle* h) {
   for (auto& op : h->ops) {
     int rc = prepare_op_weights(h, op);
     if (rc) return rc;
+  }
+  // FusedMBConv blocks (3x3 expand + SiLU -> 1x1 projection + residual, stride 1): one fused kernel per block (tc_fmb.cuh)
+  for (size_t i = 0; i + 1 < h->ops.size(); ++i) {
+    Op& a = h->ops[i];
+    const Op& b = h->ops[i + 1];
+    a.fmb.ready = false;
+    if (h->cfg.precision != MTB_PRECISION_BF16_TC || !a.tc.ready || !b.tc.ready) continue;
+    if (a.type != OP_CONV || b.type != OP_CONV || a.small_io || b.small_io) continue;
+    if (a.R != 3 || a.S != 3 || a.stride != 1 || a.dil != 1 || a.act != ACT_SILU || a.res_buf != BUF_NONE || a.scale_buf != BUF_NONE) continue;
+    if (b.R != 1 || b.stride != 1 || b.act != ACT_NONE || b.scale_buf != BUF_NONE || b.res_first || b.in_buf != a.out_buf) continue;
+    if (b.res_buf != BUF_NONE && b.res_buf != a.in_buf) continue;
+    if (a.Hin != a.Hout || a.Win != a.Wout || b.out_buf == a.in_buf) continue;
+    const char* e = fmb_prepare(a.fmb, a.tc, b.tc, h->dev_allocs);
+    if (e) return fail(h, MTB_ERR_CUDA, "fused FusedMBConv weight prep for '%s': %s", a.name.c_str(), e);
   }
   {
     Op& hd = h->head;
@@ -1758,10 +1799,8 @@ int mtb_debug_run_ops(mtb_handle* h, const float* crops, int batch, int n_ops, f
   cudaStream_t st = (cudaStream_t)stream;
   Workspace ws = layout(h, batch, workspace);
   void* features = ws.base + ws.off_features;
-  for (int i = 0; i < n_ops; ++i) {
-    rc = run_op(h, h->ops[i], crops, batch, ws, features, st);
-    if (rc) return rc;
-  }
+  rc = run_ops_range(h, 0, (size_t)n_ops, crops, batch, ws, features, st);
+  if (rc) return rc;
   const Op& o = h->ops[n_ops - 1];
   const bool small = o.type == OP_POOL || o.small_io;
   size_t n = (size_t)batch * (small ? 1 : (size_t)o.Hout * o.Wout) * o.Cout;
@@ -1886,6 +1925,32 @@ int mtb_debug_run_op(mtb_handle* h, int op_index, const float* in, const float* 
   void* src = buf_ptr(ws, o.out_buf, nullptr);
   if (small || !is_bf16(h)) CUDA_TRY(h, cudaMemcpyAsync(out, src, n_out * 4, cudaMemcpyDeviceToDevice, st));
   else launch_k(to_float_kernel, dim3(grid_for(n_out, 256)), dim3(256), 0, st, (const __nv_bfloat16*)src, out, n_out);
+  return MTB_OK;
+}
+
+int mtb_op_is_fused_block(const mtb_handle* h, int op_index) {
+  return (h && op_index >= 0 && op_index + 1 < (int)h->ops.size() && h->ops[op_index].fmb.ready && fmb_enabled()) ? 1 : 0;
+}
+
+int mtb_debug_run_fused_block(mtb_handle* h, int op_index, const float* in, int batch, float* out, size_t out_floats, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  int rc = check_common(h, batch, workspace_bytes, workspace);
+  if (rc) return rc;
+  if (op_index < 0 || op_index + 1 >= (int)h->ops.size() || !in || !out) return fail(h, MTB_ERR_INVALID_ARG, "invalid debug arguments");
+  if (!h->ops[op_index].fmb.ready) return fail(h, MTB_ERR_UNSUPPORTED, "op %d does not start a fused FusedMBConv block", op_index);
+  DeviceGuard g(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws = layout(h, batch, workspace);
+  Op a = h->ops[op_index], b = h->ops[op_index + 1];
+  const size_t n_in = (size_t)batch * a.Hin * a.Win * a.Cin, n_out = (size_t)batch * b.Hout * b.Wout * b.Cout;
+  if (n_out > out_floats) return fail(h, MTB_ERR_INVALID_ARG, "debug output buffer too small");
+  launch_k(from_float_kernel, dim3(grid_for(n_in, 256)), dim3(256), 0, st, in, (__nv_bfloat16*)buf_ptr(ws, 0, nullptr), n_in);
+  a.in_buf = 0; a.out_buf = 1; b.in_buf = 1; b.out_buf = 2;
+  if (b.res_buf != BUF_NONE) b.res_buf = 0;
+  a.fmb.cached_out = nullptr;  // the copy must not reuse a tensor map encoded for other buffers
+  rc = run_fused_block(h, a, b, batch, ws, nullptr, st);
+  if (rc) return rc;
+  launch_k(to_float_kernel, dim3(grid_for(n_out, 256)), dim3(256), 0, st, (const __nv_bfloat16*)buf_ptr(ws, 2, nullptr), out, n_out);
   return MTB_OK;
 }
 

@@ -22,6 +22,7 @@
 // (cp.async.bulk) with no tensor map.
 #pragma once
 #include "tc_gemm.cuh"
+#include "dw_tma.cuh"  // packed fp32 pairs (f2_*)
 
 namespace mtb {
 
@@ -44,7 +45,10 @@ struct FmbParams {
   int npatch, patch_bytes, patch_off;
   int nstages, stage_bytes;  // ring at offset 0
   int na2, a2_off, slab_off, bias_off, bar_off;
-  int debug;                 // MTB_FMB_DEBUG bits (perf experiments): 1 skip TMA store, 2 skip epilogue-1 math, 4 skip residual
+  long long* trace;          // MTB_FMB_TRACE=<Cin>: CTA 0 writes (code, clock64) pairs: [0,256) MMA warp, [256,512) epilogue warp 0,
+                             // [512,768) weight producer, [768,1024) patch loader warp 8
+  int debug;                 // MTB_FMB_DEBUG bits (perf experiments): 1 skip TMA store, 2 skip epilogue-1 math, 4 skip residual,
+                             // 8 skip the weight copies, 16 skip the patch copies, 32 skip the MMAs
 };
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -58,7 +62,19 @@ __device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
                : "r"(taddr));
 }
 
-// Warp roles: 0-7 epilogue; 8, 11, 12 patch loaders; 9 weight producer; 10 TMEM allocator + MMA issuer; 13-14 idle.
+#define FMB_TRACE(base, code)                                                     \
+  do {                                                                            \
+    if (trace_on && tr < 127) {                                                   \
+      p.trace[(base) + 2 * tr] = (code);                                          \
+      p.trace[(base) + 2 * tr + 1] = clock64();                                   \
+      ++tr;                                                                       \
+    }                                                                             \
+  } while (0)
+
+// Warp roles: 0-7 epilogue; 8, 11, 12 patch loaders; 9 and 13 weight producers (alternate ring stages: one bulk-copy issue
+// costs a thread ~350 cycles, a 16 KB stage is consumed in 256); 10 TMEM allocator + MMA issuer; 14 idle.
+// K1 = Cin / 16: MMAs (K = 16) per tap, compile-time so that the issue loop is straight-line code.
+template <int K1>
 __global__ void __launch_bounds__(TC_THREADS, 1) fmb_kernel(const __grid_constant__ CUtensorMap tmO, const FmbParams p) {
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
@@ -92,7 +108,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fmb_kernel(const __grid_constan
   if (warp == 10) tmem_alloc(tmem_slot, 512);
   pdl_trigger();
   pdl_wait();
-  for (int i = threadIdx.x; i < p.Cexp + p.Cout; i += blockDim.x) bias1_s[i] = i < p.Cexp ? p.bias1[i] : p.bias2[i - p.Cexp];
+  // bias1 is staged HALVED: SiLU(v + b) = h + h * tanh(h) with h = 0.5 v + 0.5 b (one FMA; scaling by 0.5 is exact)
+  for (int i = threadIdx.x; i < p.Cexp + p.Cout; i += blockDim.x) bias1_s[i] = i < p.Cexp ? 0.5f * p.bias1[i] : p.bias2[i - p.Cexp];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -106,18 +123,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fmb_kernel(const __grid_constan
   const int nstages = p.nstages;
   const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
   const int planes = p.Cin >> 3;
+  const bool trace_on = p.trace != nullptr && blockIdx.x == 0 && lane == 0;
+  int tr = 0;
 
-  if (warp == 9) {
-    // ===== weight producer: per chunk job g the nine (tap) blocks of W1, then the W2 slice of job g-1 =====
-    uint32_t stage = 0, phase = 0;
+  if (warp == 9 || warp == 13) {
+    // ===== weight producers: per chunk job g the nine (tap) blocks of W1, then the W2 slice of job g-1; ring use n is issued by
+    // warp 9 when n is even and by warp 13 when n is odd =====
+    const uint32_t mine = warp == 9 ? 0u : 1u;
+    uint32_t stage = 0, phase = 0, n = 0;
     const uint32_t cin2 = (uint32_t)p.Cin * 2, cout2 = (uint32_t)p.Cout * 2;
     auto put = [&](const uint8_t* src, uint32_t bytes) {
-      mbar_wait_a(empty0 + stage * 8, phase ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx_a(full0 + stage * 8, bytes);
-        bulk_load_1d(smem_base + stage * stage_bytes, src, bytes, full0 + stage * 8);
+      if ((n & 1u) == mine) {
+        mbar_wait_a(empty0 + stage * 8, phase ^ 1);
+        if (elect_one()) {
+          if (p.debug & 8) {  // perf experiment: no weight traffic
+            mbar_arrive((uint64_t*)(smem + p.bar_off) + stage);
+          } else {
+            mbar_expect_tx_a(full0 + stage * 8, bytes);
+            bulk_load_1d(smem_base + stage * stage_bytes, src, bytes, full0 + stage * 8);
+          }
+        }
+        __syncwarp();
+        if (warp == 9) FMB_TRACE(512, 1);
       }
-      __syncwarp();
+      ++n;
       if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; }
     };
     int c = 0, cprev = 0;
@@ -147,7 +176,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fmb_kernel(const __grid_constan
     const uint32_t a2_full0 = smem_u32(a2_full), a2_empty0 = smem_u32(a2_empty);
     const uint32_t acc2_full0 = smem_u32(acc2_full), acc2_empty0 = smem_u32(acc2_empty);
     const uint32_t patch_full0 = smem_u32(patch_full), patch_empty0 = smem_u32(patch_empty);
-    const int k1 = p.Cin >> 4;  // K = 16 steps per tap
     const uint32_t Cout = (uint32_t)p.Cout;
     const uint32_t idesc2 = umma_idesc_bf16(p.Cout);
     uint32_t stage = 0, phase = 0, s16 = base16;
@@ -159,33 +187,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fmb_kernel(const __grid_constan
         const uint32_t ab = (uint32_t)g & 1u;
         const uint32_t wc = (uint32_t)min(FMB_NC, p.Cexp - c * FMB_NC);
         mbar_wait_a(acc1_empty0 + ab * 8, (((uint32_t)g >> 1) & 1u) ^ 1u);
+        FMB_TRACE(0, 10);   // acc1 buffer free
         if (c == 0) mbar_wait_a(patch_full0 + pb * 8, pb_phase);
+        FMB_TRACE(0, 11);   // patch ready: G1 issue starts
         tc_fence_after();
         const uint32_t idesc1 = umma_idesc_bf16((int)wc);
         const uint32_t d1 = tmem_base + ab * FMB_NC;
         const uint32_t patch16 = patch0_16 + pb * patch_b16;
         const uint32_t lbo_b = wc << 16;  // B planes are wc rows x 16 B apart
+        const uint32_t wc2 = 2u * wc;
+        // one kernel row (3 taps = 3 ring stages) per elected issue block: the per-block costs of the single-thread issue
+        // path (barrier polls, fence, elect, warp re-convergence) are paid once per 3 * K1 MMAs
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait_a(full0 + stage * 8, phase);
+        for (int r = 0; r < 3; ++r) {
+          uint32_t st[3], sb[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            st[i] = stage;
+            sb[i] = s16;
+            mbar_wait_a(full0 + stage * 8, phase);
+            s16 += stage16;
+            if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; s16 = base16; }
+          }
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t a_lo = patch16 + (uint32_t)((tap / 3) * TC_PATCH_W + (tap % 3));
-#pragma unroll 1
-            for (int k = 0; k < k1; ++k)
-              umma_bf16(d1, make_desc((a_lo + (uint32_t)(2 * k) * plane16) | (plane16 << 16), hi_patch),
-                        make_desc((s16 + (uint32_t)(2 * k) * wc) | lbo_b, hi_8), idesc1, (uint32_t)(tap | k));
-            umma_commit_a(empty0 + stage * 8);
+            const uint32_t a_row = (patch16 + (uint32_t)(r * TC_PATCH_W)) | (plane16 << 16);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const uint32_t b_lo = sb[i] | lbo_b;
+#pragma unroll
+              for (int k = 0; k < K1; ++k)
+                if (!(p.debug & 32))
+                  umma_bf16(d1, make_desc(a_row + (uint32_t)i + (uint32_t)(2 * k) * plane16, hi_patch),
+                            make_desc(b_lo + (uint32_t)k * wc2, hi_8), idesc1, (uint32_t)(r | i | k));
+              umma_commit_a(empty0 + st[i] * 8);
+            }
           }
           __syncwarp();
-          s16 += stage16;
-          if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; s16 = base16; }
         }
         if (elect_one()) {
           umma_commit_a(acc1_full0 + ab * 8);
           if (c == nch - 1) umma_commit_a(patch_empty0 + pb * 8);
         }
         __syncwarp();
+        FMB_TRACE(0, 12);   // G1 issued
         if (c == nch - 1 && ++pb == (uint32_t)p.npatch) { pb = 0; pb_phase ^= 1; }
       }
       if (g >= 1) {
@@ -193,6 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fmb_kernel(const __grid_constan
         const uint32_t wc = (uint32_t)min(FMB_NC, p.Cexp - cprev * FMB_NC);
         const uint32_t acc = (uint32_t)tl_prev & 1u;
         mbar_wait_a(a2_full0 + a2b * 8, a2_phase);
+        FMB_TRACE(0, 20);   // A2 ready
         if (cprev == 0) mbar_wait_a(acc2_empty0 + acc * 8, (((uint32_t)tl_prev >> 1) & 1u) ^ 1u);
         mbar_wait_a(full0 + stage * 8, phase);
         tc_fence_after();
@@ -200,15 +246,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fmb_kernel(const __grid_constan
           const uint32_t d2 = tmem_base + 2 * FMB_NC + acc * FMB_NC;
           const uint32_t a16 = a2_16 + a2b * (FMB_A2_BYTES >> 4);
           const int k2 = (int)(wc >> 4);
-#pragma unroll 1
-          for (int k = 0; k < k2; ++k)
-            umma_bf16(d2, make_desc((a16 + (uint32_t)(2 * k) * 128u) | (128u << 16), hi_8),
-                      make_desc((s16 + (uint32_t)(2 * k) * Cout) | (Cout << 16), hi_8), idesc2, (uint32_t)(cprev | k));
+          const uint32_t a_lo = a16 | (128u << 16), b_lo = s16 | (Cout << 16), cout2 = 2u * Cout;
+#pragma unroll
+          for (int k = 0; k < FMB_NC / 16; ++k)
+            if (k < k2)
+              umma_bf16(d2, make_desc(a_lo + (uint32_t)(2 * k) * 128u, hi_8), make_desc(b_lo + (uint32_t)k * cout2, hi_8), idesc2,
+                        (uint32_t)(cprev | k));
           umma_commit_a(empty0 + stage * 8);
           umma_commit_a(a2_empty0 + a2b * 8);
           if (cprev == nch - 1) umma_commit_a(acc2_full0 + acc * 8);
         }
         __syncwarp();
+        FMB_TRACE(0, 21);   // G2 issued
         s16 += stage16;
         if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; s16 = base16; }
         if (++a2b == (uint32_t)p.na2) { a2b = 0; a2_phase ^= 1; }
@@ -228,8 +277,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fmb_kernel(const __grid_constan
       const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, b = t / (p.tiles_w * p.tiles_h);
       const int ih0 = th * TC_PT_H - p.pad_t, iw0 = tw * TC_PT_W - p.pad_l;
       mbar_wait_a(smem_u32(&patch_empty[pb]), pb_phase ^ 1);
+      if (warp == 8) FMB_TRACE(768, 30);  // patch slot free
       uint8_t* patch = smem + p.patch_off + pb * p.patch_bytes;
-      for (int it = lt; it < items; it += 96) {
+      for (int it = lt; it < items && !(p.debug & 16); it += 96) {
         const int j = it % planes, pix = it / planes;
         const int ph = pix / TC_PATCH_W, pw = pix - ph * TC_PATCH_W;
         const int ih = ih0 + ph, iw = iw0 + pw;
@@ -241,6 +291,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fmb_kernel(const __grid_constan
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&patch_full[pb]);
+      if (warp == 8) FMB_TRACE(768, 31);  // patch staged
       if (++pb == (uint32_t)p.npatch) { pb = 0; pb_phase ^= 1; }
     }
   } else if (warp < TCV_EPI_WARPS) {
@@ -267,7 +318,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fmb_kernel(const __grid_constan
         if (i < n8 && valid && p.has_res && !(p.debug & 4))
           rv[i] = *reinterpret_cast<const uint4*>(p.in + ((size_t)(b * p.H + oh) * p.W + ow) * p.Cin + hh * half + i * 8);
       }
+      if (warp == 0) FMB_TRACE(256, 50);
       mbar_wait_a(smem_u32(&acc2_full[acc]), ((uint32_t)tl >> 1) & 1u);
+      if (warp == 0) FMB_TRACE(256, 51);
       tc_fence_after();
       const uint32_t taddr = lane_taddr + 2 * FMB_NC + acc * FMB_NC + (uint32_t)(hh * half);
       if (lane == 0) tma_store_wait_read<0>();  // the previous store of this warp has read the slab
@@ -300,6 +353,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fmb_kernel(const __grid_constan
         tma_store_4d(&tmO, slab, hh * half, tw * TC_PT_W, th * TC_PT_H + q * 4, b);
         tma_store_commit();
       }
+      if (warp == 0) FMB_TRACE(256, 52);
     };
 
     int c = 0, tl = 0;
@@ -307,7 +361,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fmb_kernel(const __grid_constan
       const uint32_t ab = (uint32_t)g & 1u;
       const int wc = min(FMB_NC, p.Cexp - c * FMB_NC);
       mbar_wait_a(smem_u32(&acc1_full[ab]), ((uint32_t)g >> 1) & 1u);
+      if (warp == 0) FMB_TRACE(256, 40);
       mbar_wait_a(smem_u32(&a2_empty[a2b]), a2_phase ^ 1);
+      if (warp == 0) FMB_TRACE(256, 41);
       tc_fence_after();
       const int col0 = hh * 64;
       const uint32_t taddr = lane_taddr + ab * FMB_NC + (uint32_t)col0;
@@ -327,13 +383,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fmb_kernel(const __grid_constan
               uint4 ov = make_uint4(0u, 0u, 0u, 0u);
               if (!(p.debug & 2)) {
                 __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
-                const float4 bl = *reinterpret_cast<const float4*>(b1 + cb + gq * 8);      // broadcast reads
+                const float4 bl = *reinterpret_cast<const float4*>(b1 + cb + gq * 8);      // broadcast reads (0.5 * bias)
                 const float4 bh = *reinterpret_cast<const float4*>(b1 + cb + gq * 8 + 4);
-                const float bb[8] = {bl.x, bl.y, bl.z, bl.w, bh.x, bh.y, bh.z, bh.w};
+                const f32x2 hb[4] = {f2_pack(bl.x, bl.y), f2_pack(bl.z, bl.w), f2_pack(bh.x, bh.y), f2_pack(bh.z, bh.w)};
+                const f32x2 half2 = f2_pack(0.5f, 0.5f);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float x0 = tc_act<ACT_SILU>(__uint_as_float(v[gq * 8 + 2 * e]) + bb[2 * e]);
-                  const float x1 = tc_act<ACT_SILU>(__uint_as_float(v[gq * 8 + 2 * e + 1]) + bb[2 * e + 1]);
+                  // SiLU(x) = h + h * tanh(h), h = x / 2 (the arithmetic of tc_act<ACT_SILU>, two elements per FFMA2)
+                  const f32x2 h = f2_fma(f2_pack(__uint_as_float(v[gq * 8 + 2 * e]), __uint_as_float(v[gq * 8 + 2 * e + 1])), half2, hb[e]);
+                  float h0, h1, x0, x1;
+                  f2_unpack(h, h0, h1);
+                  f2_unpack(f2_fma(h, f2_pack(tanh_approx(h0), tanh_approx(h1)), h), x0, x1);
                   o2[e] = __floats2bfloat162_rn(x0, x1);
                 }
               }
@@ -349,6 +409,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) fmb_kernel(const __grid_constan
         mbar_arrive(&acc1_empty[ab]);
         mbar_arrive(&a2_full[a2b]);
       }
+      if (warp == 0) FMB_TRACE(256, 42);
       if (++a2b == (uint32_t)p.na2) { a2b = 0; a2_phase ^= 1; }
       if (c == 0 && tl >= 1) epi2(tl - 1);
       if (++c == nch) { c = 0; ++tl; }
@@ -469,18 +530,24 @@ inline const char* make_tmap_nhwc_dense(CUtensorMap* m, const void* ptr, uint64_
   return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(4d dense) failed";
 }
 
+template <int K1>
+inline cudaError_t fmb_launch_k(int grid, const FmbWeights& f, const FmbParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fmb_kernel<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FMB_SMEM_BUDGET + 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  launch_k(fmb_kernel<K1>, dim3(grid), dim3(TC_THREADS), (size_t)f.smem_bytes, st, f.mapO, p);
+  return cudaGetLastError();
+}
+
 inline const char* fmb_launch(const FmbWeights& f, const void* in, void* out, int B, int H, int W, int pad_t, int pad_l, bool has_res,
                               cudaStream_t st) {
   if (f.cached_out != out || f.cached_B != B) {
     const char* e = make_tmap_nhwc_dense(&f.mapO, out, B, H, W, f.Cout, (uint32_t)(f.Cout / 2));
     if (e) return e;
     f.cached_out = out; f.cached_B = B;
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(fmb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FMB_SMEM_BUDGET + 1024) != cudaSuccess)
-      return "cannot raise dynamic shared memory for fmb_kernel";
-    attr_set = true;
   }
   FmbParams p;
   p.in = (const __nv_bfloat16*)in; p.w1 = f.d_w1; p.w2 = f.d_w2; p.bias1 = f.d_b1; p.bias2 = f.d_b2;
@@ -494,8 +561,44 @@ inline const char* fmb_launch(const FmbWeights& f, const void* in, void* out, in
   p.na2 = f.na2; p.a2_off = f.a2_off; p.slab_off = f.slab_off; p.bias_off = f.bias_off; p.bar_off = f.bar_off;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MTB_FMB_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
   int grid = p.total_tiles < 148 ? p.total_tiles : 148;
-  launch_k(fmb_kernel, dim3(grid), dim3(TC_THREADS), (size_t)f.smem_bytes, st, f.mapO, p);
-  cudaError_t e = cudaGetLastError();
+  p.trace = nullptr;
+  static const char* trace_env = getenv("MTB_FMB_TRACE");  // "<Cin>": trace the first launch with that input width
+  static long long* trace_buf = nullptr;
+  static bool traced = false;
+  bool dump = false;
+  if (trace_env && !traced && atoi(trace_env) == f.Cin) {
+    if (!trace_buf) cudaMalloc(&trace_buf, 1024 * sizeof(long long));
+    cudaMemsetAsync(trace_buf, 0, 1024 * sizeof(long long), st);
+    p.trace = trace_buf;
+    dump = traced = true;
+  }
+  cudaError_t e = cudaSuccess;
+  switch (f.Cin / 16) {
+    case 1: e = fmb_launch_k<1>(grid, f, p, st); break;
+    case 2: e = fmb_launch_k<2>(grid, f, p, st); break;
+    case 3: e = fmb_launch_k<3>(grid, f, p, st); break;
+    case 4: e = fmb_launch_k<4>(grid, f, p, st); break;
+    case 5: e = fmb_launch_k<5>(grid, f, p, st); break;
+    default: e = fmb_launch_k<6>(grid, f, p, st); break;
+  }
+  if (dump && e == cudaSuccess) {
+    std::vector<long long> hb(1024);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hb.data(), trace_buf, 1024 * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long t0 = 1LL << 62;
+    for (int r = 0; r < 4; ++r)
+      if (hb[r * 256] && hb[r * 256 + 1] < t0) t0 = hb[r * 256 + 1];
+    fprintf(stderr, "MTB_FMB_TRACE Cin=%d Cexp=%d H=%d W=%d tiles=%d grid=%d nstages=%d npatch=%d na2=%d (code:cycles since first event)\n", f.Cin,
+            f.Cexp, H, W, p.total_tiles, grid, f.nstages, f.npatch, f.na2);
+    const char* names[4] = {"mma (10 acc1 free, 11 patch ready, 12 G1 issued, 20 A2 ready, 21 G2 issued)",
+                            "epilogue warp 0 (40 acc1 full, 41 A2 free, 42 epi1 done, 50 epi2 start, 51 acc2 full, 52 epi2 done)",
+                            "weight producer (1 stage issued)", "patch loader (30 slot free, 31 staged)"};
+    for (int r = 0; r < 4; ++r) {
+      fprintf(stderr, "  %s:", names[r]);
+      for (int i = 0; i < 127 && hb[r * 256 + 2 * i]; ++i) fprintf(stderr, " %lld:%lld", hb[r * 256 + 2 * i], hb[r * 256 + 2 * i + 1] - t0);
+      fprintf(stderr, "\n");
+    }
+  }
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 

@@ -281,6 +281,21 @@ class Engine:
                                      ws.data_ptr(), ws.numel(), _stream_ptr(self.device)), self._h)
         return out
 
+    def op_is_fused_block(self, op):
+        """True when backbone op `op` (3x3 expand) and op + 1 (1x1 projection) run as one fused FusedMBConv kernel."""
+        return bool(lib().mtb_op_is_fused_block(self._h, op))
+
+    def debug_run_fused_block(self, op, x):
+        """The fused FusedMBConv block starting at op `op` in isolation: x [B,H,W,Cin] fp32 (also the residual)."""
+        io = self.op_io(op + 1)
+        b = x.shape[0]
+        out = torch.empty((b,) + io['out_shape'], dtype=torch.float32, device=self.device)
+        ws = self.workspace(b)
+        x = x.float().contiguous()
+        check(lib().mtb_debug_run_fused_block(self._h, op, x.data_ptr(), b, out.data_ptr(), out.numel(), ws.data_ptr(),
+                                              ws.numel(), _stream_ptr(self.device)), self._h)
+        return out
+
     def profile_begin(self, classes=None):
         """Brackets every launch of the selected kernel classes (None = all) with CUDA events on the launch stream."""
         n = lib().mtb_num_kernel_classes()

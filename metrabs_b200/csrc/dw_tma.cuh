@@ -85,31 +85,6 @@ inline const char* make_tmap_dw(CUtensorMap* m, const void* ptr, uint64_t B, uin
   return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(dw) failed";
 }
 
-// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): two IEEE fp32 operations per issued instruction, bit-identical to the
-// scalar fmaf / fmul / fadd.  The kernel is issue-bound (ncu: 56 % issue-active with 2 warps per scheduler), so halving
-// the FMA instruction count is worth more than any memory-side change.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 // activation of a pair; SiLU(x) = h + h * tanh(h), h = x / 2 (same arithmetic as fast_act<ACT_SILU>)
 template <int ACT>
 __device__ __forceinline__ f32x2 f2_act(f32x2 x) {

@@ -747,7 +747,7 @@ template <typename T>
 int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Workspace& ws, void* features,
              cudaStream_t st) {
   PdlScope pdl_scope(pdl_se_enabled() && op.small_io);
-  if (op.type == OP_CONV && op.tc.ready && op.scale_buf != BUF_NONE && !tc_can_fuse_se(op.R, op.stride, op.Cin)) {
+  if (op.type == OP_CONV && op.tc.ready && op.scale_buf != BUF_NONE && !tc_can_fuse_se(op.R, op.stride, op.Cin, op.act)) {
     // squeeze-excitation scale applied in place ahead of a tensor-core conv that cannot fuse it (1x1 stride-1 projections
     // apply it to the A tiles in shared memory inside tc_conv_kernel)
     void* x = act_ptr(h, ws, op.in_buf, features, op.Hin, op.Win, op.Cin);

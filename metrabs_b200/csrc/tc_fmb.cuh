@@ -22,7 +22,6 @@
 // (cp.async.bulk) with no tensor map.
 #pragma once
 #include "tc_gemm.cuh"
-#include "dw_tma.cuh"  // packed fp32 pairs (f2_*)
 
 namespace mtb {
 

@@ -302,6 +302,9 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
   if (!mbar_try_wait_a(bar, parity)) mbar_wait_slow(bar, parity);
 }
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -356,7 +359,13 @@ struct TileWalk {
 //   warp 9     B-operand (weights) TMA producer
 //   warp 10    TMEM allocator + single-thread tcgen05.mma issuer
 //   warp 11    second patch loader (mode 2)
-template <int ACT, int RES, int BK, bool PATCH>
+//
+// SCALE (flat 1x1 GEMMs with a squeeze-excitation scale on their input, BK = 64): the A operand does NOT travel by TMA.  Eight
+// loader warps (4-7, 11-14; the epilogue runs on warps 0-3 only - one tile's epilogue per >= 8 k-blocks leaves them idle most
+// of the time) read the activations from global memory into registers three k-blocks ahead, multiply by s[crop(row)][k] and
+// store the bf16 products straight into 128B-swizzled A slots; only the weights use the TMA ring.  The in-flight A bytes
+// live in registers instead of ring stages, and there is no second barrier hop between "landed" and "scaled".
+template <int ACT, int RES, int BK, bool PATCH, bool SCALE = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const TcConvParams p) {
@@ -381,13 +390,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 9 && lane == 0) {
     for (int i = 0; i < TCV_MAX_STAGES; ++i) {
-      mbar_init(&full[i], patch_mode ? 1 : 2);  // one arrive.expect_tx per TMA producer
+      mbar_init(&full[i], (patch_mode || SCALE) ? 1 : 2);  // one arrive.expect_tx per TMA producer
       mbar_init(&empty[i], 1);                  // tcgen05.commit
-      mbar_init(&scaled[i], 4);                 // one arrive per scaler warp
+      mbar_init(&scaled[i], 8);                 // one arrive per scaler warp
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], TCV_EPI_WARPS);
+      mbar_init(&tmem_empty[i], SCALE ? 4 : TCV_EPI_WARPS);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&patch_full[i], p.b_resident ? 3 : 2);   // one arrive per loader warp
@@ -412,7 +421,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_g0));
   }
   const int total_tiles = p.m_tiles * p.n_tiles;
-  const uint32_t a_bytes = patch_mode ? 0u : (uint32_t)TC_BM * BK * 2;
+  const uint32_t a_bytes = (patch_mode || SCALE) ? 0u : (uint32_t)TC_BM * BK * 2;  // A bytes inside a ring stage
   const uint32_t b_bytes = (uint32_t)p.b_rows * BK * 2;
   const int nstages = p.nstages;
   const int planes = p.kchunks * (BK / 8);  // 16-byte channel chunks per pixel in the patch (zero beyond Cin/8)
@@ -428,7 +437,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t stage_stride = pin((uint32_t)p.stage_stride);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
-  if (warp == 8 && !patch_mode) {
+  if (warp == 8 && !patch_mode && !SCALE) {
     // ===== A-operand TMA producer =====
     uint32_t stage = 0, phase = 0, sa = smem_base;
     int tr = 0;
@@ -538,7 +547,39 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t patch_full0 = smem_u32(patch_full), patch_empty0 = smem_u32(patch_empty);
     const int bn = pin(p.bn), Cout = pin(p.Cout);
     TileWalk tw_(blockIdx.x, gridDim.x, p.n_tiles);
-    if (!patch_mode) {
+    if constexpr (SCALE) {
+      // ---- SCALE: B streams through the ring, A sits in one of three slots written by the loader warps ----
+      uint32_t stage = 0, phase = 0, b16 = base16, as = 0, a_phase = 0;
+      const uint32_t aslot16 = base16 + ((uint32_t)p.patch_off >> 4);
+      const uint32_t a_full0 = smem_u32(scaled), a_empty0 = patch_empty0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
+        const int n_valid = min(bn, Cout - tw_.n_blk * bn);
+        const uint32_t idesc = umma_idesc_bf16((n_valid + 15) & ~15);
+        mbar_wait_a(tmem_empty0 + acc * 8, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TC_MAX_BN;
+#pragma unroll 1
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait_a(full0 + stage * 8, phase);
+          mbar_wait_a(a_full0 + as * 8, a_phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a16 = aslot16 + as * (uint32_t)(TC_A_BYTES >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, make_desc(a16 + 2 * k, hi_sw), make_desc(b16 + 2 * k, hi_sw), idesc, (uint32_t)(kb | k));
+            umma_commit_a(empty0 + stage * 8);
+            umma_commit_a(a_empty0 + as * 8);
+            if (kb == num_kb - 1) umma_commit_a(tmem_full0 + acc * 8);
+          }
+          __syncwarp();
+          b16 += stride16;
+          if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; b16 = base16; }
+          if (++as == 3u) { as = 0; a_phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else if (!patch_mode) {
       // ---- modes 0 / 1: both operands stream through the ring; the k-block loop does not depend on the tap ----
       uint32_t stage = 0, phase = 0, a16 = base16;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
@@ -645,57 +686,88 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   }
-  if (warp >= 11 && p.a_scale != nullptr) {
-    // ===== squeeze-excitation scalers (mode 0, BK = 64; warps 11-14): once the TMA has landed a stage, multiply its A tile
-    // IN SHARED MEMORY by s[crop(row)][k] (the reference's `scale * x` ahead of the projection conv,
-    // backbones/efficientnet.py:110-173; fp32 product rounded once to bf16 = bit-identical to se_scale_kernel), then hand
-    // the stage to the MMA warp.  Warp w owns tile rows [32w, 32w+32); a quarter-warp (8 lanes) covers one 128-byte row, so
-    // every 16-byte shared-memory access of the warp is bank-conflict free (thread-per-row, the first version, was 8-way
-    // conflicted and 2.5x slower than the separate pass). =====
-    const int sw = warp - 11;
-    const int sub = lane >> 3, pos = lane & 7;
-    uint32_t stage = 0, phase = 0;
-    const int kchunks = pin(p.kchunks), Cin = pin(p.Cin);
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int m_blk = t / p.n_tiles;
-      const int m0 = m_blk * TC_BM + sw * 32 + sub;
-      int soff[8];            // crop(row) * Cin for this thread's 8 rows (row = 32 sw + 4 it + sub)
-      uint32_t rok = 0;
+  if constexpr (SCALE) {
+    if ((warp >= 4 && warp < 8) || warp >= 11) {
+      // ===== A loaders + squeeze-excitation scalers (the reference's `scale * x` ahead of the projection conv,
+      // backbones/efficientnet.py:110-173; fp32 product rounded once to bf16 = bit-identical to se_scale_kernel).
+      // 256 threads: thread st owns the LOGICAL 16-byte chunk j = st & 7 (channels 8j .. 8j+7 of the k-block) of tile rows
+      // (st >> 3) + 32 i, i = 0..3 - all with the same row & 7, i.e. the same physical chunk position j ^ (row & 7) under the
+      // 128B swizzle.  A quarter-warp reads one 128-byte row segment from global memory and writes one 128-byte shared-memory
+      // row: coalesced and bank-conflict free.  Three k-blocks of loads are in flight per thread (12 x 16 B). =====
+      const int st = (warp < 8 ? warp - 4 : warp - 7) * 32 + lane;
+      const int j = st & 7, rb = st >> 3;
+      const uint32_t chunk_off = (uint32_t)p.patch_off + (uint32_t)(rb * 128 + ((j ^ (rb & 7)) << 4));
+      const int kchunks = pin(p.kchunks), Cin = pin(p.Cin), n_tiles = pin(p.n_tiles);
+      const __nv_bfloat16* __restrict__ A = (const __nv_bfloat16*)p.res_in;
+      const uint32_t a_full0 = smem_u32(scaled), a_empty0 = smem_u32(patch_empty);
+      uint4 av[3][4];
+      // load cursor (runs three k-blocks ahead of the store cursor)
+      int lt = blockIdx.x, lkc = 0;
+      auto issue = [&](uint4 (&dst)[4]) {
+        const int m0 = (lt / n_tiles) * TC_BM + rb;
+        const int k = lkc * 64 + j * 8;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int m = m0 + it * 4;
-        const bool ok = m < p.M;
-        rok |= ok ? (1u << it) : 0u;
-        soff[it] = (ok ? m / p.a_scale_P : 0) * Cin;
-      }
-#pragma unroll 1
-      for (int kc = 0; kc < kchunks; ++kc) {
-        mbar_wait_a(full0 + stage * 8, phase);
-        uint8_t* sa = smem + stage * stage_stride + (sw * 32 + sub) * 128 + pos * 16;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          // 128B swizzle: logical 16-byte chunk (pos ^ (row & 7)) sits at physical position pos; row & 7 = 4 (it & 1) + sub
-          const int k = kc * 64 + ((pos ^ (((it & 1) << 2) | sub)) << 3);
-          if (!((rok >> it) & 1u) || k >= Cin) continue;  // K tail / M tail: the tile holds TMA zero fill there
-          uint4* ptr = reinterpret_cast<uint4*>(sa + it * 512);
-          uint4 v = *ptr;
-          const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.a_scale + soff[it] + k));
-          const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.a_scale + soff[it] + k + 4));
-          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-          unsigned wd[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float lo = __uint_as_float(wd[i] << 16) * sc[2 * i];
-            const float hi = __uint_as_float(wd[i] & 0xffff0000u) * sc[2 * i + 1];
-            __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
-            wd[i] = *reinterpret_cast<unsigned*>(&pk);
-          }
-          *ptr = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        for (int i = 0; i < 4; ++i) {
+          const int m = m0 + 32 * i;
+          dst[i] = make_uint4(0u, 0u, 0u, 0u);  // M tail / K tail: zeros, as the TMA fill of the unscaled path
+          if (lt < total_tiles && m < p.M && k < Cin) dst[i] = __ldg(reinterpret_cast<const uint4*>(A + (size_t)m * Cin + k));
         }
-        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&scaled[stage]);
-        if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; }
+        if (++lkc == kchunks) { lkc = 0; lt += gridDim.x; }
+      };
+#pragma unroll
+      for (int d = 0; d < 3; ++d) issue(av[d]);
+      uint32_t as = 0, a_phase = 0;
+      int t = blockIdx.x, kc = 0;
+      const float* srow[4] = {p.a_scale, p.a_scale, p.a_scale, p.a_scale};
+      bool rok[4] = {false, false, false, false};
+      while (t < total_tiles) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          if (t < total_tiles) {
+            if (kc == 0) {
+              const int m0 = (t / n_tiles) * TC_BM + rb;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int m = m0 + 32 * i;
+                rok[i] = m < p.M;
+                srow[i] = p.a_scale + (size_t)(rok[i] ? m / p.a_scale_P : 0) * Cin + j * 8;
+              }
+            }
+            const bool kok = kc * 64 + j * 8 < Cin;
+            f32x2 sc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+              if (kok && rok[i]) {
+                s0 = __ldg(reinterpret_cast<const float4*>(srow[i] + kc * 64));
+                s1 = __ldg(reinterpret_cast<const float4*>(srow[i] + kc * 64 + 4));
+              }
+              sc[i][0] = f2_pack(s0.x, s0.y); sc[i][1] = f2_pack(s0.z, s0.w);
+              sc[i][2] = f2_pack(s1.x, s1.y); sc[i][3] = f2_pack(s1.z, s1.w);
+            }
+            mbar_wait_a(a_empty0 + as * 8, a_phase ^ 1);
+            uint8_t* sa = smem + chunk_off + as * TC_A_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const unsigned wd[4] = {av[d][i].x, av[d][i].y, av[d][i].z, av[d][i].w};
+              unsigned od[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float lo, hi;
+                f2_unpack(f2_mul(f2_pack(__uint_as_float(wd[e] << 16), __uint_as_float(wd[e] & 0xffff0000u)), sc[i][e]), lo, hi);
+                __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+                od[e] = *reinterpret_cast<unsigned*>(&pk);
+              }
+              *reinterpret_cast<uint4*>(sa + i * 32 * 128) = make_uint4(od[0], od[1], od[2], od[3]);
+            }
+            fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(a_full0 + as * 8);
+            if (++as == 3u) { as = 0; a_phase ^= 1; }
+            issue(av[d]);  // refill this register set: three k-blocks ahead
+            if (++kc == kchunks) { kc = 0; t += gridDim.x; }
+          }
+        }
       }
     }
   }
@@ -760,9 +832,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&patch_full[pb_sig]);
     }
   }
-  if (warp < TCV_EPI_WARPS) {
+  if (warp < (SCALE ? 4 : TCV_EPI_WARPS)) {
     // ===== epilogue =====
-    const int q = warp & 3, par = warp >> 2;
+    constexpr int ch_step = SCALE ? 1 : 2;  // SCALE: one warp group walks every 64-column chunk of its rows
+    const int q = warp & 3, par = SCALE ? 0 : warp >> 2;
     const int row = q * 32 + lane;
     // long-K GEMMs (epi_single) run an epilogue once per >= 8 k-blocks: one staging slab per warp is enough there, and the
     // other 32 KB buy one more operand stage in flight (those GEMMs stream A from HBM and are bound by bytes in flight)
@@ -793,7 +866,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         off = ((size_t)(b * p.Hout + oh) * p.Wout + ow) * p.Cout;
       }
       const int nchunks = (n_valid + 63) >> 6;
-      const int ch_first = par ^ (nchunks == 1 ? (tile_i & 1) : 0);
+      const int ch_first = SCALE ? 0 : par ^ (nchunks == 1 ? (tile_i & 1) : 0);
       // residual of this warp's FIRST half-chunk of the tile: issued BEFORE the accumulator wait, so its HBM round trip
       // overlaps the tile's MMAs instead of starting when they end (the 32->32 stage-1 conv has one half-chunk per tile:
       // its whole epilogue latency was this load)
@@ -812,7 +885,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_MAX_BN;
       bool released = false;
       // two warp groups (par 0 / 1) alternate the 64-column chunks; one-chunk tiles alternate between the groups tile by tile
-      for (int ch = ch_first; ch < nchunks && !(p.debug & 128); ch += 2) {
+      for (int ch = ch_first; ch < nchunks && !(p.debug & 128); ch += ch_step) {
         const int c0 = ch * 64;
         const int ncols = min(64, n_valid - c0);  // multiple of 8
         // bias of the chunk -> this warp's staging (64 floats), broadcast-read below
@@ -846,7 +919,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (cb < ncols) tmem_ld16_issue(taddr + c0 + cb, v);
           if (cb + 16 < ncols) tmem_ld16_issue(taddr + c0 + cb + 16, v + 16);
           tmem_ld_wait();
-          if (hf == 1 && ch + 2 >= nchunks) {  // last TMEM read of this warp in the tile
+          if (hf == 1 && ch + ch_step >= nchunks) {  // last TMEM read of this warp in the tile
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -1013,10 +1086,18 @@ struct TcWeights {
   mutable size_t map_rr = 0;
 };
 
-// MTB_FUSE_SE=1: the scaler warps of tc_conv_kernel apply the squeeze-excitation scale to the A tiles in shared memory.
-// Off by default - measured at 256 crops (r1): the projection GEMMs stream A from HBM with a 3-stage ring and are latency
-// bound (~2100 cycles per 44 KB stage); the scaling hand-off (full -> scaled -> MMA) lengthens every stage's round trip,
-// so the fused GEMMs got slower by as much as the separate se_scale_kernel pass costs (23.96 vs 22.65 ms per step).
+// MTB_FUSE_SE=1: the projection GEMM applies the squeeze-excitation scale itself (SCALE variant of tc_conv_kernel) instead of
+// an in-place se_scale_kernel pass ahead of it.  OFF by default - built three ways and measured each time (V2-L, 256 crops;
+// profiles/r2_fused_se_*):
+//   round 1: TMA -> 4 scaler warps rewrite the A tile in shared memory -> MMA: step 23.96 vs 22.65 ms;
+//   round 2: the same with 8 scaler warps, scale values prefetched, FMUL2: projections 5.40 vs 3.06 ms, i.e. again what the
+//            separate pass costs (2.45 ms); with the scalers reduced to wait + arrive still 1.65 vs 1.08 ms on the 2304->384
+//            GEMMs: the extra barrier hop on a 3-stage 48 KB/stage ring that is bound by bytes in flight;
+//   round 2: A loaded by 8 loader warps straight from global memory (registers three k-blocks ahead), scaled, stored swizzled
+//            (the version below): projections 6.04 ms; ncu: 22.6 M warp instructions per launch against 4.0 M (250 per thread
+//            and k-block against 384 cycles of MMA per k-block) - issue-bound.
+// What would change the picture is a cheaper multiply (bf16 x bf16 HMUL2 with a bf16 scale: 4 instructions per 16-byte chunk
+// instead of ~24, at the price of a second rounding) - not taken: it would move the mode further from the reference arithmetic.
 inline bool tc_fuse_se() {
   static int v = -1;
   if (v < 0) {
@@ -1025,8 +1106,10 @@ inline bool tc_fuse_se() {
   }
   return v == 1;
 }
-// the scaler warps of tc_conv_kernel handle flat 1x1 GEMMs with 128-byte (BK = 64) A rows
-inline bool tc_can_fuse_se(int R, int stride, int cin) { return tc_fuse_se() && R == 1 && stride == 1 && cin > 32 && cin % 8 == 0; }
+// the scaler warps of tc_conv_kernel handle flat 1x1 GEMMs with 128-byte (BK = 64) A rows and no activation (projections)
+inline bool tc_can_fuse_se(int R, int stride, int cin, int act = ACT_NONE) {
+  return tc_fuse_se() && R == 1 && stride == 1 && cin > 32 && cin % 8 == 0 && act == ACT_NONE;
+}
 
 inline bool tc_patch_disabled() {  // MTB_DISABLE_PATCH=1: 3x3 convs fall back to the per-tap TMA mode (A/B testing)
   static int v = -1;
@@ -1107,23 +1190,26 @@ inline int tc_pick_bn(int cout, int m_tiles, int num_kb, int bk) {
   return best;
 }
 
-template <int ACT, int RES, int BK, bool PATCH>
+template <int ACT, int RES, int BK, bool PATCH, bool SCALE = false>
 inline const char* tc_conv_launch_k(int grid, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const TcConvParams& q,
                                     cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_conv_kernel<ACT, RES, BK, PATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCV_SMEM_BYTES) !=
+    if (cudaFuncSetAttribute(tc_conv_kernel<ACT, RES, BK, PATCH, SCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCV_SMEM_BYTES) !=
         cudaSuccess)
       return "cannot raise dynamic shared memory for tc_conv_kernel";
     attr_set = true;
   }
-  launch_k(tc_conv_kernel<ACT, RES, BK, PATCH>, dim3(grid), dim3(TC_THREADS), TCV_SMEM_BYTES, st, a, b, o, q);
+  launch_k(tc_conv_kernel<ACT, RES, BK, PATCH, SCALE>, dim3(grid), dim3(TC_THREADS), TCV_SMEM_BYTES, st, a, b, o, q);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 template <int ACT, int RES>
 inline const char* tc_conv_launch_t(int grid, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const TcConvParams& q,
                                     cudaStream_t st) {
+  if constexpr (ACT == ACT_NONE) {
+    if (q.a_scale != nullptr) return tc_conv_launch_k<ACT, RES, 64, false, true>(grid, a, b, o, q, st);
+  }
   if (q.mode == 2)
     return q.bk == 32 ? tc_conv_launch_k<ACT, RES, 32, true>(grid, a, b, o, q, st) : tc_conv_launch_k<ACT, RES, 64, true>(grid, a, b, o, q, st);
   return q.bk == 32 ? tc_conv_launch_k<ACT, RES, 32, false>(grid, a, b, o, q, st) : tc_conv_launch_k<ACT, RES, 64, false>(grid, a, b, o, q, st);
@@ -1153,7 +1239,7 @@ inline const char* tc_conv_dispatch(int act, int res_mode, int grid, const CUten
 inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool res_first, cudaStream_t st) {
   TcConvParams q;
   // Squeeze-excitation scale fused into the A tiles in shared memory (scaler warps 11-14; opt-in, see tc_fuse_se()).
-  q.a_scale = tc_can_fuse_se(p.R, p.stride, p.Cin) ? p.a_scale : nullptr;
+  q.a_scale = tc_can_fuse_se(p.R, p.stride, p.Cin, p.act) ? p.a_scale : nullptr;
   q.a_scale_P = p.Hin * p.Win;
   q.res = p.res; q.bias = w.d_bias;
   const int bk0 = p.Cin <= 32 ? 32 : 64;  // 64B-swizzled half-width stages only when they do not add k-blocks
@@ -1212,6 +1298,16 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
     if (q.nstages < 2) return "operand ring too small for this tile";
     q.b_resident = (q.mode == 2 && (p.Cout + bn - 1) / bn == 1 && num_kb <= q.nstages) ? 1 : 0;
     if (q.b_resident) q.nstages = num_kb;
+    if (q.a_scale != nullptr) {
+      // SCALE: ring stages hold the weights only; three A slots (written by the loader warps) behind them; the four
+      // epilogue warps use one slab each, so the ring region is the extended 176 KB one
+      q.epi_single = 1;
+      q.stage_stride = (q.b_rows * q.bk * 2 + 1023) / 1024 * 1024;
+      q.nstages = (TCV_RING_BYTES + 8 * TCV_SLAB_BYTES - 3 * TC_A_BYTES) / q.stage_stride;
+      if (q.nstages > TCV_MAX_STAGES) q.nstages = TCV_MAX_STAGES;
+      if (q.nstages < 2) return "operand ring too small for this tile";
+      q.patch_off = q.nstages * q.stage_stride;
+    }
   }
   q.n_tiles = (p.Cout + bn - 1) / bn;
   {

@@ -17,6 +17,7 @@ ap.add_argument('--joints', type=int, default=24)
 ap.add_argument('--precision', default='bf16')
 ap.add_argument('--ops', required=True)
 ap.add_argument('--reps', type=int, default=1)
+ap.add_argument('--fused', action='store_true', help='run the fused FusedMBConv block (fmb_kernel) that starts at each op')
 args = ap.parse_args()
 dev = torch.device('cuda', 0)
 model = bench.build_model(args, dev)
@@ -30,6 +31,9 @@ for nm in args.ops.split(','):
     res = torch.randn((args.batch,) + io['out_shape'], generator=g).to(dev) if io['residual'] else None
     sc = torch.rand(args.batch, io['in_shape'][2], generator=g).to(dev) if io['scale'] else None
     for _ in range(args.reps):
-        eng.debug_run_op(i, x, res, sc)
+        if args.fused:
+            eng.debug_run_fused_block(i, x)
+        else:
+            eng.debug_run_op(i, x, res, sc)
     torch.cuda.synchronize()
     print('ran', nm, io)

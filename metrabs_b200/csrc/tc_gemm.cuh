@@ -396,7 +396,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], SCALE ? 4 : TCV_EPI_WARPS);
+      // one-chunk tiles (Cout <= 64, e.g. the 32->32 stage-1 convs) alternate between the two epilogue warp groups, and each
+      // accumulator buffer is only ever read by ONE group: its hand-back must not wait for the other group, which is still busy
+      // with the previous tile (it did until round 2: the groups ran strictly one after the other, 3400 cycles per tile)
+      mbar_init(&tmem_empty[i], (SCALE || (p.n_tiles == 1 && p.Cout <= 64)) ? 4 : TCV_EPI_WARPS);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&patch_full[i], p.b_resident ? 3 : 2);   // one arrive per loader warp
@@ -846,7 +849,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t acc_phase = 0, slab_count = 0;
     const __nv_bfloat16* __restrict__ res = (const __nv_bfloat16*)p.res;
     const int rows_per_q = 32 >> p.tile_w_log2;  // tile rows covered by one warp's 32 lanes (spatial modes)
+    const bool one_chunk = !SCALE && p.n_tiles == 1 && p.Cout <= 64;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      if (one_chunk && (par ^ (tile_i & 1)) != 0) {
+        // one-chunk tiles belong to ONE warp group (even tiles: warps 0-3 / accumulator 0, odd tiles: warps 4-7 / accumulator
+        // 1); the other group must not even wait for the tile's tmem_full: nothing holds the MMA warp back from completing that
+        // barrier's NEXT phase before a lagging non-owner has looked at this one (parity waits cannot tell phase k from k + 2)
+        ++tile_i;
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       const int m_blk = t / p.n_tiles, n_blk = t - m_blk * p.n_tiles;
       const int n0 = n_blk * p.bn;
       const int n_valid = min(p.bn, p.Cout - n0);
@@ -966,8 +978,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         ++slab_count;
       }
-      if (!released) {  // this warp had no chunk in the tile (narrow last tile): still hand the accumulator back
-        tc_fence_before();
+      if (!released && !(p.n_tiles == 1 && p.Cout <= 64)) {  // no chunk for this warp in the tile (narrow last tile): still
+        tc_fence_before();                                   // hand the accumulator back (one-chunk kernels: owner group only)
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       }

@@ -61,82 +61,6 @@ __device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
                : "r"(taddr));
 }
 
-// ---- CTA-pair (cta_group::2) helpers: PTX forms of the CUTLASS sm100 2-SM recipes (cute/arch/mma_sm100_umma.hpp
-// SM100_MMA_F16BF16_2x1SM_SS, cutlass/arch/barrier.h umma_arrive_multicast_2x1SM, cute/arch/tmem_allocator_sm100.hpp Allocator2Sm)
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// D[tmem, both CTAs] (+)= A[smem of each CTA: its 128 rows] * B[smem: N/2 rows from each CTA], issued by ONE thread of the leader
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive (once all prior tcgen05.mma of this thread have completed) on the mbarrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"((uint16_t)3)
-               : "memory");
-}
-// arrive on the mbarrier at this offset in the LEADER CTA (rank 0 of the pair), from either CTA
-__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar, bool is_leader) {
-  if (is_leader) {  // own barrier: the plain CTA-local arrive
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-    return;
-  }
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(bar));
-  // relaxed: the data the barrier guards was written to THIS CTA's shared memory and made visible to the async proxy
-  // (fence.proxy.async) before the arrive is issued; a release.cluster arrive cost ~800 cycles per call (measured)
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
-// 2-SM TMA load of a [rows][64 bf16] box: data into THIS CTA's shared memory, transaction bytes onto the mbarrier at the same
-// offset in the LEADER CTA (CUTLASS SM100_TMA_2SM_LOAD: the CTA-rank bit of the shared::cluster barrier address is cleared)
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
-      : "memory");
-}
-// wait with cluster-scope acquire (the barrier receives arrivals from the peer CTA)
-__device__ __forceinline__ bool mbar_try_wait_cl(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, P1;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait_cl(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_cl(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) {
-      printf("metrabs_b200: cluster mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
-    }
-  }
-}
-// kind::f16 instruction descriptor for a pair: D fp32, A/B bf16, both K-major, M = 256, N = n
-__host__ __device__ inline uint32_t umma_idesc_bf16_m256(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-}
-
 #define FMB_TRACE(base, code)                                                     \
   do {                                                                            \
     if (trace_on && tr < 127) {                                                   \

@@ -158,6 +158,82 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// ---- CTA-pair (cta_group::2) helpers: PTX forms of the CUTLASS sm100 2-SM recipes (cute/arch/mma_sm100_umma.hpp
+// SM100_MMA_F16BF16_2x1SM_SS, cutlass/arch/barrier.h umma_arrive_multicast_2x1SM, cute/arch/tmem_allocator_sm100.hpp Allocator2Sm)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// D[tmem, both CTAs] (+)= A[smem of each CTA: its 128 rows] * B[smem: N/2 rows from each CTA], issued by ONE thread of the leader
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior tcgen05.mma of this thread have completed) on the mbarrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// arrive on the mbarrier at this offset in the LEADER CTA (rank 0 of the pair), from either CTA
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar, bool is_leader) {
+  if (is_leader) {  // own barrier: the plain CTA-local arrive
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    return;
+  }
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(bar));
+  // relaxed: the data the barrier guards was written to THIS CTA's shared memory and made visible to the async proxy
+  // (fence.proxy.async) before the arrive is issued; a release.cluster arrive cost ~800 cycles per call (measured)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// 2-SM TMA load of a [rows][64 bf16] box: data into THIS CTA's shared memory, transaction bytes onto the mbarrier at the same
+// offset in the LEADER CTA (CUTLASS SM100_TMA_2SM_LOAD: the CTA-rank bit of the shared::cluster barrier address is cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+// wait with cluster-scope acquire (the barrier receives arrivals from the peer CTA)
+__device__ __forceinline__ bool mbar_try_wait_cl(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cl(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cl(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {
+      printf("metrabs_b200: cluster mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+// kind::f16 instruction descriptor for a pair: D fp32, A/B bf16, both K-major, M = 256, N = n
+__host__ __device__ inline uint32_t umma_idesc_bf16_m256(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
 // ------------------------------------------------------------------------------------------- conv/GEMM kernel
 // constants shared with the fused head kernel (fixed 4-stage ring of [A 16 KB | B 32 KB] stages)
 constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4, TC_MAX_BN = 256;
@@ -214,6 +290,7 @@ struct TcConvParams {
   int bk;       // K elements per ring stage (host-side copy of the BK template argument)
   int trace_cta; // the CTA that writes the clock64 trace
   int rot;       // modes 0 / 1: rotate the start of each CTA's K loop (see the A producer); 0 with the fused SE scalers
+  int pair;        // flat GEMM run by CTA pairs (PAIRM kernel): b_rows = HALF the weight rows of a tile
   int epi_single;  // mode 0, long K: ONE epilogue slab per warp; the freed 32 KB extend the operand ring to 176 KB
 };
 
@@ -365,7 +442,12 @@ struct TileWalk {
 // of the time) read the activations from global memory into registers three k-blocks ahead, multiply by s[crop(row)][k] and
 // store the bf16 products straight into 128B-swizzled A slots; only the weights use the TMA ring.  The in-flight A bytes
 // live in registers instead of ring stages, and there is no second barrier hop between "landed" and "scaled".
-template <int ACT, int RES, int BK, bool PATCH, bool SCALE = false>
+//
+// PAIRM (flat 1x1 GEMMs, BK = 64): two CTAs of a cluster compute a 256-row x bn tile with tcgen05.mma.cta_group::2 issued by
+// the leader: each CTA loads its own 128 rows of A and HALF of the weight tile (the tensor core reads the other half from the
+// peer's shared memory), so a ring stage is 16 KB + bn x 64 B instead of 16 KB + bn x 128 B and the weight bytes that cross the
+// L2 -> SM port - what bounds the MBConv expand / projection GEMMs - halve.
+template <int ACT, int RES, int BK, bool PATCH, bool SCALE = false, bool PAIRM = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const TcConvParams p) {
@@ -399,7 +481,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // one-chunk tiles (Cout <= 64, e.g. the 32->32 stage-1 convs) alternate between the two epilogue warp groups, and each
       // accumulator buffer is only ever read by ONE group: its hand-back must not wait for the other group, which is still busy
       // with the previous tile (it did until round 2: the groups ran strictly one after the other, 3400 cycles per tile)
-      mbar_init(&tmem_empty[i], (SCALE || (p.n_tiles == 1 && p.Cout <= 64)) ? 4 : TCV_EPI_WARPS);
+      mbar_init(&tmem_empty[i], PAIRM ? 2 * TCV_EPI_WARPS : (SCALE || (p.n_tiles == 1 && p.Cout <= 64)) ? 4 : TCV_EPI_WARPS);  // (the host never pairs Cout <= 64)
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&patch_full[i], p.b_resident ? 3 : 2);   // one arrive per loader warp
@@ -407,10 +489,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_barrier_init();
   }
-  if (warp == 10) tmem_alloc(tmem_slot, 512);
+  if (warp == 10) {
+    if constexpr (PAIRM) {  // same logical warp in both CTAs (Allocator2Sm contract)
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc(tmem_slot, 512);
+    }
+  }
+  const uint32_t rank = PAIRM ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIRM) cluster_sync_all();  // both CTAs' barriers initialised and TMEM allocated before any cross-CTA traffic
+  else __syncthreads();
   tc_fence_after();
+  // tile walk: CTA (pair) `walk_first` takes work units walk_first, walk_first + walk_step, ...; a unit is (row block, N tile),
+  // a row block being 128 rows (256 for a pair: rows [256 m + 128 rank, +128) belong to CTA `rank`)
+  const int walk_first = PAIRM ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int walk_step = PAIRM ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   // warp-uniform by construction (shuffle from lane 0): lets the compiler keep the accumulator address in a uniform
   // register instead of re-broadcasting it with an ELECT / R2UR loop in front of every tcgen05.mma
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
@@ -423,7 +519,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     cta_t0 = clock64();
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_g0));
   }
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = (PAIRM ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
   const uint32_t a_bytes = (patch_mode || SCALE) ? 0u : (uint32_t)TC_BM * BK * 2;  // A bytes inside a ring stage
   const uint32_t b_bytes = (uint32_t)p.b_rows * BK * 2;
   const int nstages = p.nstages;
@@ -445,21 +541,26 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t stage = 0, phase = 0, sa = smem_base;
     int tr = 0;
     const int kchunks = pin(p.kchunks);
-    TileWalk tw_(blockIdx.x, gridDim.x, p.n_tiles);
+    TileWalk tw_(walk_first, walk_step, p.n_tiles);
     // K rotation (opt-in, MTB_TC_ROT=1): CTA i starts every tile's K loop at k-block (i mod num_kb) and wraps, so that the
     // CTAs of a wave do not read the SAME weight k-block at the same time.  Hypothesis was L2 same-line serialisation on
     // the long-K / one-N-tile projection GEMMs; measured: no change (2.354 vs 2.357 ms per 18 launches), so it is off.
     const int rot_kb = p.rot ? (int)(blockIdx.x % (unsigned)num_kb) : 0;
     if (p.mode == 0) {
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
-        const int row0 = tw_.m_blk * TC_BM;
+      for (int t = walk_first; t < total_tiles; t += walk_step, tw_.next()) {
+        const int row0 = (PAIRM ? 2 * tw_.m_blk + (int)rank : tw_.m_blk) * TC_BM;
         int kc = rot_kb;
 #pragma unroll 1
         for (int i = 0; i < kchunks; ++i) {
           mbar_wait_a(empty0 + stage * 8, phase ^ 1);
           if (elect_one()) {
-            mbar_expect_tx_a(full0 + stage * 8, a_bytes);
-            tma_load_2d_a(sa, &tmA, full0 + stage * 8, kc * BK, row0);
+            if constexpr (PAIRM) {  // both CTAs' A tiles complete on the LEADER's barrier
+              if (leader) mbar_expect_tx_a(full0 + stage * 8, 2u * a_bytes);
+              tma_load_2d_2sm(sa, &tmA, full0 + stage * 8, kc * BK, row0);
+            } else {
+              mbar_expect_tx_a(full0 + stage * 8, a_bytes);
+              tma_load_2d_a(sa, &tmA, full0 + stage * 8, kc * BK, row0);
+            }
             if (trace_on && tr < 256) p.trace[tr++] = clock64();
           }
           __syncwarp();
@@ -471,7 +572,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
       const int R = pin(p.R), S = pin(p.S), dil = pin(p.dil);
       const int tap0 = rot_kb / kchunks, kc0 = rot_kb - tap0 * kchunks, r0 = tap0 / S, s0 = tap0 - r0 * S;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
+      for (int t = walk_first; t < total_tiles; t += walk_step, tw_.next()) {
         const int m_blk = tw_.m_blk;
         const int tw = m_blk % p.tiles_w;
         const int th = (m_blk / p.tiles_w) % p.tiles_h;
@@ -515,16 +616,22 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // same K rotation as the A producer (mode 2 keeps the natural order: its MMA loop derives the patch offset from it)
       const int rot_kb = (p.rot && !patch_mode) ? (int)(blockIdx.x % (unsigned)num_kb) : 0;
       const int tap0 = rot_kb / kchunks, kc0 = rot_kb - tap0 * kchunks;
-      TileWalk tw_(blockIdx.x, gridDim.x, p.n_tiles);
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
-        const int nrow = tw_.n_blk * bn;
+      TileWalk tw_(walk_first, walk_step, p.n_tiles);
+      for (int t = walk_first; t < total_tiles; t += walk_step, tw_.next()) {
+        // PAIRM: this CTA stages rows [n0 + rank * n_mma / 2, + n_mma / 2) of the weight tile (n_mma = the MMA's N)
+        const int nrow = PAIRM ? tw_.n_blk * bn + (int)rank * ((((min(bn, p.Cout - tw_.n_blk * bn)) + 15) & ~15) >> 1) : tw_.n_blk * bn;
         int tap = tap0, kc = kc0;
 #pragma unroll 1
         for (int i = 0; i < num_kb; ++i) {
           mbar_wait_a(empty0 + stage * 8, phase ^ 1);
           if (elect_one()) {
-            mbar_expect_tx_a(full0 + stage * 8, b_bytes);
-            tma_load_2d_a(sb, &tmB, full0 + stage * 8, tap * Cin + kc * BK, nrow);
+            if constexpr (PAIRM) {
+              if (leader) mbar_expect_tx_a(full0 + stage * 8, 2u * b_bytes);
+              tma_load_2d_2sm(sb, &tmB, full0 + stage * 8, tap * Cin + kc * BK, nrow);
+            } else {
+              mbar_expect_tx_a(full0 + stage * 8, b_bytes);
+              tma_load_2d_a(sb, &tmB, full0 + stage * 8, tap * Cin + kc * BK, nrow);
+            }
           }
           __syncwarp();
           if (++kc == kchunks) { kc = 0; if (++tap == taps) tap = 0; }
@@ -533,8 +640,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 10) {
-    // ===== MMA issuer (whole warp walks the pipeline, one elected lane issues) =====
+  } else if (warp == 10 && leader) {
+    // ===== MMA issuer (whole warp walks the pipeline, one elected lane issues; PAIRM: the leader CTA only) =====
     int tr = 0;
     uint32_t acc = 0, acc_phase = 0, pb = 0, pb_phase = 0;
     // constant high words of the operand descriptors: SBO | version 1 | layout type
@@ -549,13 +656,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_full0 = smem_u32(tmem_full), tmem_empty0 = smem_u32(tmem_empty);
     const uint32_t patch_full0 = smem_u32(patch_full), patch_empty0 = smem_u32(patch_empty);
     const int bn = pin(p.bn), Cout = pin(p.Cout);
-    TileWalk tw_(blockIdx.x, gridDim.x, p.n_tiles);
+    TileWalk tw_(walk_first, walk_step, p.n_tiles);
     if constexpr (SCALE) {
       // ---- SCALE: B streams through the ring, A sits in one of three slots written by the loader warps ----
       uint32_t stage = 0, phase = 0, b16 = base16, as = 0, a_phase = 0;
       const uint32_t aslot16 = base16 + ((uint32_t)p.patch_off >> 4);
       const uint32_t a_full0 = smem_u32(scaled), a_empty0 = patch_empty0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
+      for (int t = walk_first; t < total_tiles; t += walk_step, tw_.next()) {
         const int n_valid = min(bn, Cout - tw_.n_blk * bn);
         const uint32_t idesc = umma_idesc_bf16((n_valid + 15) & ~15);
         mbar_wait_a(tmem_empty0 + acc * 8, acc_phase ^ 1);
@@ -585,10 +692,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (!patch_mode) {
       // ---- modes 0 / 1: both operands stream through the ring; the k-block loop does not depend on the tap ----
       uint32_t stage = 0, phase = 0, a16 = base16;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
+      for (int t = walk_first; t < total_tiles; t += walk_step, tw_.next()) {
         const int n_valid = min(bn, Cout - tw_.n_blk * bn);
-        const uint32_t idesc = umma_idesc_bf16((n_valid + 15) & ~15);
-        mbar_wait_a(tmem_empty0 + acc * 8, acc_phase ^ 1);
+        const uint32_t idesc = PAIRM ? umma_idesc_bf16_m256((n_valid + 15) & ~15) : umma_idesc_bf16((n_valid + 15) & ~15);
+        if constexpr (PAIRM) mbar_wait_cl(tmem_empty0 + acc * 8, acc_phase ^ 1);  // collects the peer's epilogue warps too
+        else mbar_wait_a(tmem_empty0 + acc * 8, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TC_MAX_BN;
 #pragma unroll 1
@@ -598,12 +706,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (elect_one()) {
             if (trace_on && tr < 256) p.trace[256 + tr++] = clock64();
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(d_tmem, make_desc(a16 + 2 * k, hi_sw), make_desc(a16 + b_off16 + 2 * k, hi_sw), idesc, (uint32_t)(kb | k));
-            umma_commit_a(empty0 + stage * 8);  // frees the ring slot once these MMAs have read it
+            for (int k = 0; k < BK / 16; ++k) {
+              if constexpr (PAIRM)
+                umma_bf16_2sm(d_tmem, make_desc(a16 + 2 * k, hi_sw), make_desc(a16 + b_off16 + 2 * k, hi_sw), idesc, (uint32_t)(kb | k));
+              else
+                umma_bf16(d_tmem, make_desc(a16 + 2 * k, hi_sw), make_desc(a16 + b_off16 + 2 * k, hi_sw), idesc, (uint32_t)(kb | k));
+            }
+            if constexpr (PAIRM) umma_commit_2sm(empty0 + stage * 8);  // both CTAs may refill this slot
+            else umma_commit_a(empty0 + stage * 8);  // frees the ring slot once these MMAs have read it
             if (kb == num_kb - 1) {
               if (trace_on && tr < 256) p.trace[256 + tr++] = -clock64();  // (negative) all MMAs of the tile issued
-              umma_commit_a(tmem_full0 + acc * 8);  // accumulator complete -> epilogue
+              if constexpr (PAIRM) umma_commit_2sm(tmem_full0 + acc * 8);  // both CTAs' epilogues may read their accumulators
+              else umma_commit_a(tmem_full0 + acc * 8);  // accumulator complete -> epilogue
             }
           }
           __syncwarp();
@@ -619,12 +733,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int kchunks = pin(p.kchunks);
       const uint32_t patch_off16 = (uint32_t)p.patch_off >> 4, patch_bytes16 = (uint32_t)p.patch_bytes >> 4;
       uint32_t stage = 0, phase = 0, b16 = base16;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tw_.next()) {
+      for (int t = walk_first; t < total_tiles; t += walk_step, tw_.next()) {
         const int n_valid = min(bn, Cout - tw_.n_blk * bn);
         const uint32_t idesc = umma_idesc_bf16((n_valid + 15) & ~15);
         mbar_wait_a(tmem_empty0 + acc * 8, acc_phase ^ 1);
         mbar_wait_a(patch_full0 + pb * 8, pb_phase);
-        if (b_res && t == (int)blockIdx.x)
+        if (b_res && t == walk_first)
           for (int kb = 0; kb < num_kb; ++kb) mbar_wait_a(full0 + kb * 8, 0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TC_MAX_BN;
@@ -705,7 +819,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t a_full0 = smem_u32(scaled), a_empty0 = smem_u32(patch_empty);
       uint4 av[3][4];
       // load cursor (runs three k-blocks ahead of the store cursor)
-      int lt = blockIdx.x, lkc = 0;
+      int lt = walk_first, lkc = 0;
       auto issue = [&](uint4 (&dst)[4]) {
         const int m0 = (lt / n_tiles) * TC_BM + rb;
         const int k = lkc * 64 + j * 8;
@@ -715,12 +829,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           dst[i] = make_uint4(0u, 0u, 0u, 0u);  // M tail / K tail: zeros, as the TMA fill of the unscaled path
           if (lt < total_tiles && m < p.M && k < Cin) dst[i] = __ldg(reinterpret_cast<const uint4*>(A + (size_t)m * Cin + k));
         }
-        if (++lkc == kchunks) { lkc = 0; lt += gridDim.x; }
+        if (++lkc == kchunks) { lkc = 0; lt += walk_step; }
       };
 #pragma unroll
       for (int d = 0; d < 3; ++d) issue(av[d]);
       uint32_t as = 0, a_phase = 0;
-      int t = blockIdx.x, kc = 0;
+      int t = walk_first, kc = 0;
       const float* srow[4] = {p.a_scale, p.a_scale, p.a_scale, p.a_scale};
       bool rok[4] = {false, false, false, false};
       while (t < total_tiles) {
@@ -768,7 +882,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) mbar_arrive_a(a_full0 + as * 8);
             if (++as == 3u) { as = 0; a_phase ^= 1; }
             issue(av[d]);  // refill this register set: three k-blocks ahead
-            if (++kc == kchunks) { kc = 0; t += gridDim.x; }
+            if (++kc == kchunks) { kc = 0; t += walk_step; }
           }
         }
       }
@@ -785,7 +899,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // two tiles of copies in flight per loader warp: tile t+1 is issued before tile t is waited for and handed over
     int pb = 0, pb_sig = 0, pending = 0, ltr = 0;
     uint32_t pb_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = walk_first; t < total_tiles; t += walk_step) {
       const int m_blk = t / p.n_tiles;
       const int tw = m_blk % p.tiles_w;
       const int th = (m_blk / p.tiles_w) % p.tiles_h;
@@ -849,8 +963,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t acc_phase = 0, slab_count = 0;
     const __nv_bfloat16* __restrict__ res = (const __nv_bfloat16*)p.res;
     const int rows_per_q = 32 >> p.tile_w_log2;  // tile rows covered by one warp's 32 lanes (spatial modes)
-    const bool one_chunk = !SCALE && p.n_tiles == 1 && p.Cout <= 64;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const bool one_chunk = !SCALE && !PAIRM && p.n_tiles == 1 && p.Cout <= 64;
+    for (int t = walk_first; t < total_tiles; t += walk_step) {
       if (one_chunk && (par ^ (tile_i & 1)) != 0) {
         // one-chunk tiles belong to ONE warp group (even tiles: warps 0-3 / accumulator 0, odd tiles: warps 4-7 / accumulator
         // 1); the other group must not even wait for the tile's tmem_full: nothing holds the MMA warp back from completing that
@@ -859,7 +973,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
-      const int m_blk = t / p.n_tiles, n_blk = t - m_blk * p.n_tiles;
+      const int m_unit = t / p.n_tiles, n_blk = t - m_unit * p.n_tiles;
+      const int m_blk = PAIRM ? 2 * m_unit + (int)rank : m_unit;  // this CTA's 128-row block
       const int n0 = n_blk * p.bn;
       const int n_valid = min(p.bn, p.Cout - n0);
       bool valid;
@@ -905,6 +1020,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane < 16) {
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
           if (lane * 4 < ncols) bv = *reinterpret_cast<const float4*>(p.bias + n0 + c0 + lane * 4);
+          if constexpr (ACT == ACT_SILU && RES != 2) {  // staged HALVED: SiLU(v + b) = h + h tanh(h), h = 0.5 v + 0.5 b (one FMA)
+            bv.x *= 0.5f; bv.y *= 0.5f; bv.z *= 0.5f; bv.w *= 0.5f;
+          }
           *reinterpret_cast<float4*>(bias_s + lane * 4) = bv;
         }
         uint8_t* slab = slabs + (p.epi_single ? 0u : (slab_count & 1)) * TCV_SLAB_BYTES;
@@ -934,7 +1052,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (hf == 1 && ch + ch_step >= nchunks) {  // last TMEM read of this warp in the tile
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+              if constexpr (PAIRM) mbar_arrive_leader(smem_u32(&tmem_empty[acc]), leader);
+              else mbar_arrive(&tmem_empty[acc]);
+            }
             released = true;
           }
 #pragma unroll
@@ -944,6 +1065,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cb + g * 8);
               const float4 b1 = *reinterpret_cast<const float4*>(bias_s + cb + g * 8 + 4);
               float o[8];
+              if constexpr (ACT == ACT_SILU && RES != 2) {
+                // packed pairs (FFMA2): h = 0.5 v + 0.5 b, out = h + h tanh(h) [+ residual] - the arithmetic of tc_act<ACT_SILU>
+                // on (v + b), bit for bit (scaling by 0.5 is exact), in 2.5 instead of 4.5 instructions per element
+                const f32x2 hb[4] = {f2_pack(b0.x, b0.y), f2_pack(b0.z, b0.w), f2_pack(b1.x, b1.y), f2_pack(b1.z, b1.w)};
+                const f32x2 half2 = f2_pack(0.5f, 0.5f);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const f32x2 h = f2_fma(f2_pack(__uint_as_float(v[g * 8 + 2 * i]), __uint_as_float(v[g * 8 + 2 * i + 1])), half2, hb[i]);
+                  float h0, h1;
+                  f2_unpack(h, h0, h1);
+                  f32x2 y = f2_fma(h, f2_pack(tanh_approx(h0), tanh_approx(h1)), h);
+                  if constexpr (RES == 1) {
+                    const unsigned wdi = i == 0 ? rv[g].x : i == 1 ? rv[g].y : i == 2 ? rv[g].z : rv[g].w;
+                    y = f2_add(y, f2_pack(__uint_as_float(wdi << 16), __uint_as_float(wdi & 0xffff0000u)));
+                  }
+                  f2_unpack(y, o[2 * i], o[2 * i + 1]);
+                }
+              } else {
               o[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; o[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
               o[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; o[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
               o[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; o[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
@@ -959,6 +1098,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] = tc_act<ACT>(o[i]);
+              }
               }
               __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
@@ -978,10 +1118,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         ++slab_count;
       }
-      if (!released && !(p.n_tiles == 1 && p.Cout <= 64)) {  // no chunk for this warp in the tile (narrow last tile): still
+      if (!released && !one_chunk) {  // no chunk for this warp in the tile (narrow last tile): still
         tc_fence_before();                                   // hand the accumulator back (one-chunk kernels: owner group only)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          if constexpr (PAIRM) mbar_arrive_leader(smem_u32(&tmem_empty[acc]), leader);
+          else mbar_arrive(&tmem_empty[acc]);
+        }
       }
       if (p.trace && (int)blockIdx.x == p.trace_cta && threadIdx.x == 0 && etr < 256) p.trace[512 + etr++] = clock64();
       ++tile_i;
@@ -990,7 +1133,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) tma_store_wait_all();  // global writes complete before the CTA exits
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIRM) cluster_sync_all();  // neither CTA leaves while the pair's MMAs / remote arrivals may still touch it
+  else __syncthreads();
   if (p.trace && threadIdx.x == 0) {  // per-CTA totals: cycles and nanoseconds from start to drained pipeline
     unsigned long long g1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
@@ -999,7 +1143,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 10) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIRM) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -1092,7 +1237,7 @@ struct TcWeights {
     CUtensorMap a, b, o;
     const void* in = nullptr;
     const void* out = nullptr;
-    int B = -1, bn = 0;
+    int B = -1, bn = 0, pair = 0;
   };
   mutable std::vector<MapSet> map_sets;
   mutable size_t map_rr = 0;
@@ -1121,6 +1266,15 @@ inline bool tc_fuse_se() {
 // the scaler warps of tc_conv_kernel handle flat 1x1 GEMMs with 128-byte (BK = 64) A rows and no activation (projections)
 inline bool tc_can_fuse_se(int R, int stride, int cin, int act = ACT_NONE) {
   return tc_fuse_se() && R == 1 && stride == 1 && cin > 32 && cin % 8 == 0 && act == ACT_NONE;
+}
+
+inline bool tc_pair_enabled() {  // MTB_TC_PAIR=0: flat GEMMs on single CTAs (A/B runs)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTB_TC_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 inline bool tc_patch_disabled() {  // MTB_DISABLE_PATCH=1: 3x3 convs fall back to the per-tap TMA mode (A/B testing)
@@ -1202,18 +1356,33 @@ inline int tc_pick_bn(int cout, int m_tiles, int num_kb, int bk) {
   return best;
 }
 
-template <int ACT, int RES, int BK, bool PATCH, bool SCALE = false>
+template <int ACT, int RES, int BK, bool PATCH, bool SCALE = false, bool PAIRM = false>
 inline const char* tc_conv_launch_k(int grid, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const TcConvParams& q,
                                     cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_conv_kernel<ACT, RES, BK, PATCH, SCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCV_SMEM_BYTES) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(tc_conv_kernel<ACT, RES, BK, PATCH, SCALE, PAIRM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TCV_SMEM_BYTES) != cudaSuccess)
       return "cannot raise dynamic shared memory for tc_conv_kernel";
     attr_set = true;
   }
-  launch_k(tc_conv_kernel<ACT, RES, BK, PATCH, SCALE>, dim3(grid), dim3(TC_THREADS), TCV_SMEM_BYTES, st, a, b, o, q);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  if constexpr (PAIRM) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TCV_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, tc_conv_kernel<ACT, RES, BK, PATCH, SCALE, PAIRM>, a, b, o, q);
+  } else {
+    launch_k(tc_conv_kernel<ACT, RES, BK, PATCH, SCALE, PAIRM>, dim3(grid), dim3(TC_THREADS), TCV_SMEM_BYTES, st, a, b, o, q);
+    e = cudaGetLastError();
+  }
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 template <int ACT, int RES>
@@ -1222,6 +1391,7 @@ inline const char* tc_conv_launch_t(int grid, const CUtensorMap& a, const CUtens
   if constexpr (ACT == ACT_NONE) {
     if (q.a_scale != nullptr) return tc_conv_launch_k<ACT, RES, 64, false, true>(grid, a, b, o, q, st);
   }
+  if (q.pair) return tc_conv_launch_k<ACT, RES, 64, false, false, true>(grid, a, b, o, q, st);
   if (q.mode == 2)
     return q.bk == 32 ? tc_conv_launch_k<ACT, RES, 32, true>(grid, a, b, o, q, st) : tc_conv_launch_k<ACT, RES, 64, true>(grid, a, b, o, q, st);
   return q.bk == 32 ? tc_conv_launch_k<ACT, RES, 32, false>(grid, a, b, o, q, st) : tc_conv_launch_k<ACT, RES, 64, false>(grid, a, b, o, q, st);
@@ -1279,11 +1449,17 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
   q.m_tiles = q.mode == 0 ? (q.M + TC_BM - 1) / TC_BM : p.B * q.tiles_w * q.tiles_h;
   const int bn = tc_pick_bn(p.Cout, q.m_tiles, q.taps * q.kchunks, q.bk);
   q.bn = bn;
+  // CTA pairs for the flat GEMMs that re-read a wide weight tile per k-block (MBConv expand / projection, last conv, ResNet 1x1)
+  // Measured (V2-L, 256 crops, profiles/r2_tc_pair_vs_single.txt): projections with K >= 1344 gain 4-17 %, the 640 -> 3840
+  // expand 7 %; the short-K expand GEMMs (K <= 384) are bound by their SiLU epilogue, not by operand traffic, and lose 1-6 %.
+  q.pair = (tc_pair_enabled() && q.mode == 0 && q.a_scale == nullptr && q.bk == 64 && p.Cout > 64 && q.taps * q.kchunks >= 8 &&
+            (long)((q.m_tiles + 1) / 2) * ((p.Cout + bn - 1) / bn) >= 74) ? 1 : 0;  // at least one unit per pair of SMs
   {
     const int a_bytes = q.mode == 2 ? 0 : TC_BM * q.bk * 2;
     // weight box: no zero-fill rows when a single N tile covers Cout (a 256-row box for Cout = 32 cost 8x the shared-memory
     // fill and kept the weights from staying resident)
     q.b_rows = (p.Cout + bn - 1) / bn == 1 ? (p.Cout + 15) / 16 * 16 : bn;
+    if (q.pair) q.b_rows /= 2;  // each CTA of a pair stages half of the tile's weight rows
     q.stage_stride = (a_bytes + q.b_rows * q.bk * 2 + 1023) / 1024 * 1024;
     q.patch_bytes = q.mode == 2 ? (planes0 * TC_PLANE_BYTES + 1023) / 1024 * 1024 : 0;
     const int num_kb = q.taps * q.kchunks;
@@ -1329,7 +1505,7 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
   }
   const TcWeights::MapSet* ms = nullptr;
   for (const TcWeights::MapSet& c : w.map_sets)
-    if (c.in == p.in && c.out == p.out && c.B == p.B && c.bn == bn) { ms = &c; break; }
+    if (c.in == p.in && c.out == p.out && c.B == p.B && c.bn == bn && c.pair == q.pair) { ms = &c; break; }
   if (!ms) {
     TcWeights::MapSet c;
     const char* e = q.mode == 0 ? make_tmap_2d(&c.a, p.in, (uint64_t)q.M, (uint64_t)p.Cin, TC_BM, (uint32_t)q.bk)
@@ -1341,7 +1517,7 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
     e = q.mode == 0 ? make_tmap_2d(&c.o, p.out, (uint64_t)q.M, (uint64_t)p.Cout, 32)
                     : make_tmap_nhwc(&c.o, p.out, p.B, p.Hout, p.Wout, p.Cout, 1, TC_BK, (uint32_t)q.tile_w, (uint32_t)(32 / q.tile_w));
     if (e) return e;
-    c.in = p.in; c.out = p.out; c.B = p.B; c.bn = bn;
+    c.in = p.in; c.out = p.out; c.B = p.B; c.bn = bn; c.pair = q.pair;
     if (w.map_sets.size() < 16) {
       w.map_sets.push_back(c);
       ms = &w.map_sets.back();
@@ -1351,8 +1527,9 @@ inline const char* tc_conv_launch(const TcWeights& w, const ConvParams& p, bool 
       ++w.map_rr;
     }
   }
-  const int total = q.m_tiles * q.n_tiles;
+  const int total = (q.pair ? (q.m_tiles + 1) / 2 : q.m_tiles) * q.n_tiles;
   int grid = total < 148 ? total : 148;
+  if (q.pair) grid = total < 74 ? 2 * total : 148;  // whole pairs
   { static int g_env = -1; if (g_env < 0) { const char* e = getenv("MTB_TC_GRID"); g_env = e ? atoi(e) : 0; } if (g_env > 0 && g_env < grid) grid = g_env; }
   const int res_mode = p.res ? (res_first ? 2 : 1) : 0;
   q.trace = nullptr;

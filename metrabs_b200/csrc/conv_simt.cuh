@@ -598,6 +598,71 @@ __global__ void __launch_bounds__(128) stem_conv_wide_kernel(StemParams p) {
 }
 
 // ----------------------------------------------------------------------------------------------------------
+// stem, third form: the EfficientNet stem itself (3x3, stride 2, 3 input channels, all CPT = Cout output channels per thread),
+// fully unrolled; two output channels per FFMA2 (same IEEE fma per channel and the same tap order as the forms above: the
+// results are bit-identical), every weight float4 a shared-memory broadcast.  stem_conv_wide_kernel ran this layer at 13
+// TFLOP/s (7.4x its HBM floor): runtime tap loops, 64-bit address arithmetic per tap and one scalar FMA per weight.
+// ----------------------------------------------------------------------------------------------------------
+template <typename TOut, int CPT>
+__global__ void __launch_bounds__(128) stem3x3s2_kernel(StemParams p) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float sw[];  // weights [27][Cout] + bias [Cout]
+  for (int i = threadIdx.x; i < 27 * CPT; i += blockDim.x) sw[i] = p.w[i];
+  float* sb = sw + 27 * CPT;
+  for (int i = threadIdx.x; i < CPT; i += blockDim.x) sb[i] = p.bias[i];
+  __syncthreads();
+  TOut* __restrict__ out = reinterpret_cast<TOut*>(p.out);
+  const size_t total = (size_t)p.B * p.Hout * p.Wout;
+  const size_t plane = (size_t)p.Hin * p.Win;
+  for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(pix % p.Wout);
+    const size_t t = pix / p.Wout;
+    const int oh = (int)(t % p.Hout);
+    const int b = (int)(t / p.Hout);
+    f32x2 acc[CPT / 2];
+#pragma unroll
+    for (int j = 0; j < CPT / 2; ++j) acc[j] = f2_pack(sb[2 * j], sb[2 * j + 1]);
+    const float* img = p.in + (size_t)b * 3 * plane;
+    const int ih0 = oh * 2 - p.pad_t, iw0 = ow * 2 - p.pad_l;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = ih0 + r;
+      const bool rok = ih >= 0 && ih < p.Hin;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int iw = iw0 + s;
+        if (rok && iw >= 0 && iw < p.Win) {  // an out-of-image tap contributes nothing (the reference pads AFTER x*2-1)
+          const float* px = img + (size_t)ih * p.Win + iw;
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci) {
+            const float v = __ldg(px + ci * plane) * p.pre_scale[ci] + p.pre_shift[ci];
+            const f32x2 vv = f2_pack(v, v);
+            const float4* wrow = reinterpret_cast<const float4*>(sw + ((r * 3 + s) * 3 + ci) * CPT);
+#pragma unroll
+            for (int j = 0; j < CPT / 4; ++j) {
+              const float4 wv = wrow[j];
+              acc[2 * j] = f2_fma(vv, f2_pack(wv.x, wv.y), acc[2 * j]);
+              acc[2 * j + 1] = f2_fma(vv, f2_pack(wv.z, wv.w), acc[2 * j + 1]);
+            }
+          }
+        }
+      }
+    }
+    float o[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT / 2; ++j) f2_unpack(acc[j], o[2 * j], o[2 * j + 1]);
+    act_dispatch(p.act, [&](auto tag) {
+      constexpr int ACT = decltype(tag)::value;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) o[j] = act_t<ACT>(o[j]);
+    });
+#pragma unroll
+    for (int j = 0; j < CPT; j += 4) store4<TOut>(out + pix * CPT + j, make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
 // global average pool over the spatial axes (squeeze of squeeze-excitation): in [B,P,C] -> mean [B,C] fp32.
 // grid (ceil(C/128), B), block (32, 8).
 // ----------------------------------------------------------------------------------------------------------

@@ -734,6 +734,15 @@ double op_bytes(const mtb_handle* h, const Op& op, int B) {
 }
 
 // ---------------------------------------------------------------------------------------------- executor
+bool stem_fast_enabled() {  // MTB_STEM_FAST=0: the generic stem kernel (A/B runs, bit-equality test)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTB_STEM_FAST");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 bool pdl_se_enabled() {  // MTB_PDL_SE=1: programmatic dependent launch for the squeeze-excitation chain only
   static int v = -1;
   if (v < 0) {
@@ -770,7 +779,10 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
       p.R = op.R; p.S = op.S; p.stride = op.stride; p.pad_t = op.pad_t; p.pad_l = op.pad_l; p.act = op.act;
       size_t smem = ((size_t)op.R * op.S * op.Cin + 1) * op.Cout * 4;
       const size_t pixels = (size_t)B * op.Hout * op.Wout;
-      if (op.Cout % 32 == 0) launch_k(stem_conv_wide_kernel<T, 32>, dim3(grid_for(pixels * (op.Cout / 32), 128)), dim3(128), smem, st, p);
+      const bool effnet_stem = op.R == 3 && op.S == 3 && op.Cin == 3 && op.stride == 2 && stem_fast_enabled();
+      if (effnet_stem && op.Cout == 32) launch_k(stem3x3s2_kernel<T, 32>, dim3(grid_for(pixels, 128)), dim3(128), (size_t)28 * 32 * 4, st, p);
+      else if (effnet_stem && op.Cout == 24) launch_k(stem3x3s2_kernel<T, 24>, dim3(grid_for(pixels, 128)), dim3(128), (size_t)28 * 24 * 4, st, p);
+      else if (op.Cout % 32 == 0) launch_k(stem_conv_wide_kernel<T, 32>, dim3(grid_for(pixels * (op.Cout / 32), 128)), dim3(128), smem, st, p);
       else if (op.Cout % 24 == 0) launch_k(stem_conv_wide_kernel<T, 24>, dim3(grid_for(pixels * (op.Cout / 24), 128)), dim3(128), smem, st, p);
       else if (op.Cout % 16 == 0) launch_k(stem_conv_wide_kernel<T, 16>, dim3(grid_for(pixels * (op.Cout / 16), 128)), dim3(128), smem, st, p);
       else launch_k(stem_conv_kernel<T>, dim3(grid_for(pixels * (op.Cout / 4), 256)), dim3(256), smem, st, p);

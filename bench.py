@@ -567,6 +567,15 @@ def run_b200(args):
                 'avg_launch_us': prof_dom['ms'] * 1e3 / prof_dom['launches'],
                 'share_of_step': prof_all[dom_name]['ms'] / total_ms_all,
                 'class_ms_warm_step': {n: round(v['ms'], 3) for n, v in prof_all.items()}}
+        # the other tcgen05 conv kernel of the step (fused FusedMBConv blocks) and both together: the dominant CLASS holds the
+        # layers that were not fused, so its fraction alone understates what the tensor-core kernels of the step achieve
+        tc_names = [n for n in ('tc_conv_kernel', 'fmb_kernel', 'tc32_conv_kernel') if n in prof_all and prof_all[n]['flops'] > 0]
+        if bound == 'tensor' and len(tc_names) > 1:
+            fl = sum(prof_all[n]['flops'] for n in tc_names)
+            ms = sum(prof_all[n]['ms'] for n in tc_names)
+            roof['tensor_core_kernels'] = {n: {'ms': round(prof_all[n]['ms'], 3), 'achieved': prof_all[n]['flops'] / (prof_all[n]['ms'] / 1e3) / 1e12,
+                                               'frac': prof_all[n]['flops'] / (prof_all[n]['ms'] / 1e3) / 1e12 / peak} for n in tc_names}
+            roof['tensor_core_kernels']['combined'] = {'ms': round(ms, 3), 'achieved': fl / (ms / 1e3) / 1e12, 'frac': fl / (ms / 1e3) / 1e12 / peak}
         if precision == 'tf32x3' and bound == 'tensor':
             roof['note'] = ('achieved counts the USEFUL conv FLOPs (2*MACs); the kernel issues three tf32 MMAs per product at half '
                             'the bf16 rate, so its ceiling is peak/6')

@@ -311,6 +311,12 @@ double mtb_backbone_flops_per_crop(const mtb_handle* h);
  * back to the strip kernel. */
 int mtb_debug_dw_plan(int height, int width, int* crops_per_item, int* rows_per_item, int* row_bands, int* stage_bytes);
 
+/* Host-side plan and weight re-pack of the fused FusedMBConv kernel (no device needed; tests/test_host_plans.py): the shared-memory
+ * plan for a block shape (all outputs 0 when the shape is not covered) and the stage images of the two weight matrices
+ * (w1 [cexp][9*cin], w2 [cout][cexp], any 16-bit element type; pair = 1: the half-per-CTA images of the cta_group::2 kernel). */
+int mtb_debug_fmb_plan(int cin, int cexp, int cout, int pair, int* nstages, int* npatch, int* stage_bytes, int* smem_bytes);
+int mtb_debug_fmb_pack(const uint16_t* w1, const uint16_t* w2, int cin, int cexp, int cout, int pair, uint16_t* img1, uint16_t* img2);
+
 #ifdef __cplusplus
 }
 #endif

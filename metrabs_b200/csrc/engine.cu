@@ -1969,6 +1969,22 @@ int mtb_debug_run_fused_block(mtb_handle* h, int op_index, const float* in, int 
 int64_t mtb_last_launch_count(const mtb_handle* h) { return h ? h->launches : 0; }
 double mtb_backbone_flops_per_crop(const mtb_handle* h) { return h ? h->flops_per_crop : 0.0; }
 
+int mtb_debug_fmb_plan(int cin, int cexp, int cout, int pair, int* nstages, int* npatch, int* stage_bytes, int* smem_bytes) {
+  if (!nstages || !npatch || !stage_bytes || !smem_bytes) return fail(nullptr, MTB_ERR_INVALID_ARG, "invalid arguments");
+  *nstages = *npatch = *stage_bytes = *smem_bytes = 0;
+  if (!fmb_shape_ok(cin, cexp, cout) || (pair && (cexp % FMB_NC != 0 || cin != cout))) return MTB_OK;
+  const FmbPlan pl = fmb_plan(cin, cexp, cout, pair != 0);
+  if (!pl.ok) return MTB_OK;
+  *nstages = pl.nstages; *npatch = pl.npatch; *stage_bytes = pl.stage_bytes; *smem_bytes = pl.smem_bytes;
+  return MTB_OK;
+}
+
+int mtb_debug_fmb_pack(const uint16_t* w1, const uint16_t* w2, int cin, int cexp, int cout, int pair, uint16_t* img1, uint16_t* img2) {
+  if (!w1 || !w2 || !img1 || !img2 || !fmb_shape_ok(cin, cexp, cout)) return fail(nullptr, MTB_ERR_INVALID_ARG, "invalid arguments");
+  fmb_pack_images(w1, w2, cin, cexp, cout, pair ? 2 : 1, img1, img2);
+  return MTB_OK;
+}
+
 int mtb_debug_dw_plan(int height, int width, int* crops_per_item, int* rows_per_item, int* row_bands, int* stage_bytes) {
   if (height <= 0 || width <= 0 || !crops_per_item || !rows_per_item || !row_bands || !stage_bytes)
     return fail(nullptr, MTB_ERR_INVALID_ARG, "invalid arguments");

@@ -549,9 +549,7 @@ inline FmbPlan fmb_plan(int Cin, int Cexp, int Cout, bool pair) {
   f.stage_bytes = (FMB_NC * std::max(Cin, Cout) * 2 / (pair ? 2 : 1) + 1023) / 1024 * 1024;
   const int slab = 8 * 32 * (Cout / 2) * 2;
   const int bias = ((Cexp + Cout) * 4 + 127) / 128 * 128;
-  static int na2_env = -1;
-  if (na2_env < 0) { const char* e = getenv("MTB_FMB_NA2"); na2_env = e ? atoi(e) : 1; }
-  f.na2 = na2_env == 2 ? 2 : 1;
+  f.na2 = 1;  // one GEMM-2 operand buffer: a second one measured 2.5 % faster on Cin = 64 but does not fit next to the Cin = 96 ring
   for (int np = 3; np >= 2; --np) {
     const int fixed = f.na2 * FMB_A2_BYTES + slab + bias + 512 + np * f.patch_bytes;
     const int ns = std::min((FMB_SMEM_BUDGET - fixed) / f.stage_bytes, FMB_MAX_STAGES);
@@ -584,6 +582,29 @@ inline const char* make_tmap_2d_dense(CUtensorMap* m, const void* ptr, uint64_t 
   return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled(2d dense) failed";
 }
 
+// Host-side re-pack of the two weight matrices into the shared-memory images of the ring stages (any 16-bit element type):
+//   h1 [Cexp][9*Cin] (k = tap*Cin + c)  ->  i1: for chunk c, tap t, half h: [Cin/8 planes][rows/halves][8]   (rows = chunk width)
+//   h2 [Cout][Cexp]                     ->  i2: for chunk c,        half h: [rows/8 planes][Cout/halves][8]
+// halves = 1: single-CTA kernel; halves = 2: one half per CTA of a pair (each half is one contiguous TMA box).
+template <typename E>
+inline void fmb_pack_images(const E* h1, const E* h2, int Cin, int Cexp, int Cout, int halves, E* i1, E* i2) {
+  const int K1 = 9 * Cin;
+  const int nch = (Cexp + FMB_NC - 1) / FMB_NC;
+  size_t o1 = 0, o2 = 0;
+  for (int c = 0; c < nch; ++c) {
+    const int wc = std::min(FMB_NC, Cexp - c * FMB_NC);
+    for (int tap = 0; tap < 9; ++tap)
+      for (int hf = 0; hf < halves; ++hf)
+        for (int j = 0; j < Cin / 8; ++j)
+          for (int n = hf * (wc / halves); n < (hf + 1) * (wc / halves); ++n)
+            for (int e = 0; e < 8; ++e) i1[o1++] = h1[(size_t)(c * FMB_NC + n) * K1 + tap * Cin + j * 8 + e];
+    for (int hf = 0; hf < halves; ++hf)
+      for (int j = 0; j < wc / 8; ++j)
+        for (int n = hf * (Cout / halves); n < (hf + 1) * (Cout / halves); ++n)
+          for (int e = 0; e < 8; ++e) i2[o2++] = h2[(size_t)n * Cexp + c * FMB_NC + j * 8 + e];
+  }
+}
+
 // w1: bf16 [Cexp][9*Cin] (k = tap*Cin + c), w2: bf16 [Cout][Cexp] (device copies of the two convs' tensor-core weights)
 inline const char* fmb_prepare(FmbWeights& f, const TcWeights& w1, const TcWeights& w2, std::vector<void*>& allocs) {
   f.ready = false;
@@ -596,24 +617,9 @@ inline const char* fmb_prepare(FmbWeights& f, const TcWeights& w1, const TcWeigh
   std::vector<__nv_bfloat16> h1((size_t)f.Cexp * K1), h2((size_t)f.Cout * f.Cexp);
   if (cudaMemcpy(h1.data(), w1.d_w, h1.size() * 2, cudaMemcpyDeviceToHost) != cudaSuccess) return "cudaMemcpy failed";
   if (cudaMemcpy(h2.data(), w2.d_w, h2.size() * 2, cudaMemcpyDeviceToHost) != cudaSuccess) return "cudaMemcpy failed";
-  const int nch = (f.Cexp + FMB_NC - 1) / FMB_NC;
   for (int v = 0; v < 2; ++v) {
-    // v = 0: a block is [K/8 planes][rows][8]; v = 1: [half][K/8 planes][rows/2][8] (one half per CTA of a pair)
-    const int halves = v + 1;
     std::vector<__nv_bfloat16> i1(h1.size()), i2(h2.size());
-    size_t o1 = 0, o2 = 0;
-    for (int c = 0; c < nch; ++c) {
-      const int wc = std::min(FMB_NC, f.Cexp - c * FMB_NC);
-      for (int tap = 0; tap < 9; ++tap)
-        for (int hf = 0; hf < halves; ++hf)
-          for (int j = 0; j < f.Cin / 8; ++j)
-            for (int n = hf * (wc / halves); n < (hf + 1) * (wc / halves); ++n)
-              for (int e = 0; e < 8; ++e) i1[o1++] = h1[(size_t)(c * FMB_NC + n) * K1 + tap * f.Cin + j * 8 + e];
-      for (int hf = 0; hf < halves; ++hf)
-        for (int j = 0; j < wc / 8; ++j)
-          for (int n = hf * (f.Cout / halves); n < (hf + 1) * (f.Cout / halves); ++n)
-            for (int e = 0; e < 8; ++e) i2[o2++] = h2[(size_t)n * f.Cexp + c * FMB_NC + j * 8 + e];
-    }
+    fmb_pack_images(h1.data(), h2.data(), f.Cin, f.Cexp, f.Cout, v + 1, i1.data(), i2.data());
     if (cudaMalloc((void**)&f.d_w1[v], i1.size() * 2) != cudaSuccess) return "cudaMalloc failed";
     allocs.push_back(f.d_w1[v]);
     if (cudaMalloc((void**)&f.d_w2[v], i2.size() * 2) != cudaSuccess) return "cudaMalloc failed";

@@ -680,6 +680,17 @@ bool dw_strip_eligible(const Op& op) {
 // number of partial pooling slices the fused depthwise kernel writes (= its gridDim.y)
 constexpr int kDwOW = 4;  // outputs per thread along W in dwconv3x3_pool_bf16_kernel (measured: 4 -> 3.65 ms, 2 -> 4.25 ms per 128 crops)
 // stride-1 3x3 depthwise ops run the TMA-staged kernel (dw_tma.cuh); MTB_DW_TMA=0 falls back to the strip kernel (A/B runs)
+// MTB_DW_F32_TMA=1: the 3xTF32 mode runs the fp32 variant of the TMA-staged depthwise kernel instead of the fp32 strip kernel.
+// OFF: measured 11.08 vs 9.92 ms per 256 crops (V2-L; joints 6.9e-6 vs 7.4e-6 from the oracle) - with 32 channels per item and the
+// exact expf / divide SiLU of the parity mode the kernel is more issue-bound than the strip kernel is latency-bound.
+bool dw_f32_tma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTB_DW_F32_TMA");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 bool dw_tma_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -688,16 +699,20 @@ bool dw_tma_enabled() {
   }
   return v == 1;
 }
-DwTmaPlan dw_tma_plan_for(const Op& op, bool bf16_tc = true) {
+// tma_ok: the handle runs a mode the TMA-staged kernel covers (bf16 tensor-core mode; 3xTF32 mode: its fp32 variant, C % 4 == 0)
+DwTmaPlan dw_tma_plan_for(const Op& op, bool tma_ok = true) {
   DwTmaPlan none;
-  if (!bf16_tc) return none;  // the TMA-staged kernel is bf16-only; the 3xTF32 mode runs the fp32 strip kernel
+  if (!tma_ok) return none;
   if (!dw_tma_enabled() || !dw_strip_eligible(op) || op.stride != 1 || op.Hin != op.Hout || op.Win != op.Wout) return none;
   DwTmaPlan pl = dw_tma_plan(op.Hout, op.Wout);
   if (!pl.ok || pl.n_rb > kPoolSlices) return none;
   return pl;
 }
-int dw_pool_slices(const Op& dw, bool bf16_tc = true) {
-  const DwTmaPlan pl = dw_tma_plan_for(dw, bf16_tc);
+bool dw_tma_mode(const mtb_handle* h, const Op& op) {
+  return h->cfg.precision == MTB_PRECISION_BF16_TC || (h->cfg.precision == MTB_PRECISION_TF32X3 && op.Cout % 4 == 0 && dw_f32_tma_enabled());
+}
+int dw_pool_slices(const Op& dw, bool tma_ok = true) {
+  const DwTmaPlan pl = dw_tma_plan_for(dw, tma_ok);
   if (pl.ok) return pl.n_rb;
   const int strips = dw.Hout * ((dw.Wout + kDwOW - 1) / kDwOW);
   return std::min((strips + 7) / 8, kPoolSlices);
@@ -824,8 +839,16 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
             else launch_k(dwconv3x3_pool_bf16_kernel<2, ACT_HSWISH, kDwOW>, dim3(grid), dim3(block), 0, st, p, pooled);
           }
         } else if (h->cfg.precision == MTB_PRECISION_TF32X3 && dw_strip_eligible(op) && op.Cout % 4 == 0) {
-          // fp32 strip kernel: 4 channels x 4 pixels per thread, SE squeeze fused (partial slices summed by fc1)
           float* pooled = op.fused_pool ? (float*)buf_ptr(ws, BUF_SMALL0, features) : nullptr;
+          const DwTmaPlan tma_plan = dw_tma_plan_for(op, dw_tma_mode(h, op));
+          if (tma_plan.ok) {  // the TMA-staged kernel, fp32 variant (exact activation)
+            const char* e = dw_tma_launch(op.dw_cache, tma_plan, p.in, p.out, op.d_w, op.d_bias, pooled, B, op.Hout, op.Wout, op.Cout,
+                                          op.pad_t, op.pad_l, op.act, st, true);
+            if (e) return fail(h, MTB_ERR_CUDA, "depthwise (TMA, fp32) launch %s: %s", op.name.c_str(), e);
+            h->launches++;
+            break;
+          }
+          // fp32 strip kernel: 4 channels x 4 pixels per thread, SE squeeze fused (partial slices summed by fc1)
           dim3 grid((op.Cout / 4 + 31) / 32, dw_pool_slices(op, false), B), block(32, 8);
 #define MTB_DWF32(ST, AC) launch_k(dwconv3x3_pool_f32_kernel<ST, AC, kDwOW>, dim3(grid), dim3(block), 0, st, p, pooled)
           if (op.act == ACT_SILU) { if (op.stride == 1) MTB_DWF32(1, ACT_SILU); else MTB_DWF32(2, ACT_SILU); }
@@ -841,7 +864,7 @@ int run_op_t(mtb_handle* h, const Op& op, const float* crops, int B, const Works
         launch_k(maxpool_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, st, p);
       } else if (op.small_io) {
         if (op.pool_src > 0 && h->ops[op.pool_src].fused_pool) {  // input = partial pooling slices of the depthwise kernel
-          p.a_splits = dw_pool_slices(h->ops[op.pool_src - 1], h->cfg.precision == MTB_PRECISION_BF16_TC);
+          p.a_splits = dw_pool_slices(h->ops[op.pool_src - 1], dw_tma_mode(h, h->ops[op.pool_src - 1]));
           p.a_split_stride = (size_t)B * op.Cin;
         }
         float* final_out = (float*)p.out;

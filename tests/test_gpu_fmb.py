@@ -34,7 +34,8 @@ def _block_reference(sd, spec, names, i, x):
 
 
 @pytest.mark.parametrize('name,side,batch', [('efficientnetv2-s', 256, 3), ('efficientnetv2-l', 256, 2), ('efficientnetv2-l', 384, 1),
-                                             ('efficientnetv2-m', 192, 2), ('efficientnetv2-tiny', 64, 5)])  # tiny: Cin 16, one 64-wide chunk
+                                             ('efficientnetv2-m', 192, 2), ('efficientnetv2-tiny', 64, 5),  # tiny: Cin 16, one 64-wide chunk
+                                             ('efficientnetv2-l', 32, 3)])  # 8x8 / 4x4 maps, 3 crops: an ODD number of tiles (a CTA pair runs a dummy tile)
 def test_fused_block_vs_conv2d_and_unfused(H, name, side, batch):
     pcfg = port.PathConfig(proc_side=side)
     spec = port.effnet_spec(name)
